@@ -1,0 +1,68 @@
+"""Loader for libecc_b200.so (the C ABI declared in include/ecc_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing, importing a compute entry
+point raises.  Build it with `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C epipolarconsistency_b200/csrc`.
+"""
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libecc_b200.so")
+
+c_ctx = C.c_void_p
+c_vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/ecc_b200.h declares
+SIGNATURES = {
+    "ecc_version": (C.c_int, []),
+    "ecc_create": (C.c_int, [C.c_int, C.POINTER(c_ctx)]),
+    "ecc_destroy": (None, [c_ctx]),
+    "ecc_last_error": (C.c_char_p, [c_ctx]),
+    "ecc_set_stream": (C.c_int, [c_ctx, c_vp]),
+    "ecc_synchronize": (C.c_int, [c_ctx]),
+    "ecc_radon_compute": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
+    "ecc_radon_bin_sizes": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ecc_set_radon_intermediates": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "ecc_set_projection_matrices": (C.c_int, [c_ctx, c_vp, C.c_int]),
+    "ecc_update_projection_matrix": (C.c_int, [c_ctx, C.c_int, c_vp]),
+    "ecc_set_object_radius": (C.c_int, [c_ctx, C.c_double]),
+    "ecc_get_object_radius": (C.c_int, [c_ctx, C.POINTER(C.c_double)]),
+    "ecc_set_epipolar_plane_step": (C.c_int, [c_ctx, C.c_double]),
+    "ecc_set_interpolation": (C.c_int, [c_ctx, C.c_int]),
+    "ecc_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),
+    "ecc_evaluate_range": (C.c_int, [c_ctx, C.c_longlong, C.c_longlong, c_vp, C.POINTER(C.c_double)]),
+    "ecc_evaluate_indices": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.POINTER(C.c_double)]),
+    "ecc_evaluate_batch": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
+    "ecc_pair_sample_counts": (C.c_int, [c_ctx, c_vp]),
+    "ecc_partition_pairs": (C.c_int, [c_ctx, C.c_int, c_vp]),
+    "ecc_make_circular_trajectory": (None, [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, c_vp]),
+    "ecc_synth_projections": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
+    "ecc_profile_enable": (C.c_int, [c_ctx, C.c_int]),
+    "ecc_profile_reset": (C.c_int, [c_ctx]),
+    "ecc_profile_get": (C.c_int, [c_ctx, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+}
+
+_lib = None
+
+
+class EccLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Returns the ctypes handle of libecc_b200.so with all signatures set.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EccLibraryMissing(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with `make -C epipolarconsistency_b200/csrc`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,388 @@
+"""Host-side mirror of the reference's operator interface for the hot path, on top of the C ABI.
+
+The reference's public interface for this path is three C++ classes (code/LibEpipolarConsistency/):
+`EpipolarConsistency::Metric` (EpipolarConsistency.h:49-94), `MetricRadonIntermediate`
+(EpipolarConsistencyRadonIntermediate.h:21-106) and `RadonIntermediate` (RadonIntermediate.h:18-128).
+The C++ facade with those exact names lives in include/EpipolarConsistency/; this module is the same
+interface for Python drivers (tests, bench, torch.distributed runs): same method names, argument
+meaning and return values.  All compute goes through libecc_b200.so -- nothing here computes on the
+CPU, and the oracle is never imported.
+
+Device memory is held in torch tensors (plumbing only); host data are numpy arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FILTER_DERIVATIVE, FILTER_RAMP, FILTER_NONE = 0, 1, 2
+POST_IDENTITY, POST_SQRT, POST_LOG = 0, 1, 2
+INTERP_TEXTURE, INTERP_EXACT = 0, 1
+
+
+class EccError(RuntimeError):
+    pass
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor (host or device), or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return x.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(x)}")
+
+
+class Context:
+    """One GPU + one stream (ecc_context).  Thin, explicit wrapper of the C ABI."""
+
+    def __init__(self, device=-1, stream=None):
+        self.lib = _lib.load()
+        h = _lib.c_ctx()
+        rc = self.lib.ecc_create(int(device), C.byref(h))
+        if rc != 0:
+            raise EccError(f"ecc_create(device={device}) failed with {rc}: no usable CUDA device? "
+                           "(this library has no CPU fallback)")
+        self.h = h
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ecc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EccError(f"libecc_b200 error {rc}: {self.lib.ecc_last_error(self.h).decode()}")
+
+    # -- plumbing
+    def set_stream(self, stream):
+        """stream: torch.cuda.Stream, raw cudaStream_t int, or None for the context's own."""
+        raw = None if stream is None else int(getattr(stream, "cuda_stream", stream))
+        self._check(self.lib.ecc_set_stream(self.h, raw))
+
+    def synchronize(self):
+        self._check(self.lib.ecc_synchronize(self.h))
+
+    # -- Radon
+    def radon_compute(self, images, n_alpha, n_t, filter=FILTER_DERIVATIVE, post=POST_IDENTITY,
+                      interp=INTERP_TEXTURE, out=None):
+        """images: (n, n_v, n_u) float32, numpy (host) or torch cuda tensor.  Returns the dtrs
+        (n, n_t, n_alpha) in the same kind of memory (or writes into `out`)."""
+        n, n_v, n_u = images.shape
+        if out is None:
+            if isinstance(images, np.ndarray):
+                out = np.empty((n, n_t, n_alpha), np.float32)
+            else:
+                import torch
+                out = torch.empty((n, n_t, n_alpha), dtype=torch.float32, device=images.device)
+        self._check(self.lib.ecc_radon_compute(self.h, _ptr(images), n, n_u, n_v, n_alpha, n_t, filter, post,
+                                               interp, _ptr(out)))
+        return out
+
+    @staticmethod
+    def radon_bin_sizes(n_u, n_v, n_alpha, n_t):
+        a, t = C.c_double(), C.c_double()
+        _lib.load().ecc_radon_bin_sizes(n_u, n_v, n_alpha, n_t, C.byref(a), C.byref(t))
+        return a.value, t.value
+
+    # -- metric state
+    def set_radon_intermediates(self, dtrs, n_u, n_v, is_derivative=True, step_alpha=None, step_t=None):
+        n, n_t, n_alpha = dtrs.shape
+        sa, st = self.radon_bin_sizes(n_u, n_v, n_alpha, n_t)
+        self._dtrs_keepalive = dtrs  # borrowed by the library when on the device
+        self._check(self.lib.ecc_set_radon_intermediates(
+            self.h, _ptr(dtrs), n, n_alpha, n_t, sa if step_alpha is None else step_alpha,
+            st if step_t is None else step_t, n_u, n_v, int(is_derivative)))
+
+    def set_projection_matrices(self, Ps):
+        Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
+        self._check(self.lib.ecc_set_projection_matrices(self.h, _ptr(Ps), Ps.shape[0]))
+
+    def update_projection_matrix(self, index, P):
+        P = np.ascontiguousarray(P, np.float64).reshape(12)
+        self._check(self.lib.ecc_update_projection_matrix(self.h, int(index), _ptr(P)))
+
+    def set_object_radius(self, r):
+        self._check(self.lib.ecc_set_object_radius(self.h, float(r)))
+
+    def get_object_radius(self):
+        r = C.c_double()
+        self._check(self.lib.ecc_get_object_radius(self.h, C.byref(r)))
+        return r.value
+
+    def set_epipolar_plane_step(self, dkappa):
+        self._check(self.lib.ecc_set_epipolar_plane_step(self.h, float(dkappa)))
+
+    def set_interpolation(self, interp):
+        self._check(self.lib.ecc_set_interpolation(self.h, int(interp)))
+
+    # -- evaluation
+    def evaluate(self, cost_image=None, want_mean=True):
+        m = C.c_double()
+        self._check(self.lib.ecc_evaluate(self.h, _ptr(cost_image), C.byref(m) if want_mean else None))
+        return m.value if want_mean else None
+
+    def evaluate_range(self, begin, end, cost_image=None, want_sum=True):
+        s = C.c_double()
+        self._check(self.lib.ecc_evaluate_range(self.h, int(begin), int(end), _ptr(cost_image),
+                                                C.byref(s) if want_sum else None))
+        return s.value if want_sum else None
+
+    def evaluate_indices(self, idx4, out=None, want_mean=True):
+        n_pairs = idx4.shape[0]
+        m = C.c_double()
+        self._check(self.lib.ecc_evaluate_indices(self.h, _ptr(idx4), n_pairs, _ptr(out),
+                                                  C.byref(m) if want_mean else None))
+        return m.value if want_mean else None
+
+    def evaluate_batch(self, Ps_sets, idx4=None, out=None, want_means=True):
+        if isinstance(Ps_sets, np.ndarray):
+            Ps_sets = np.ascontiguousarray(Ps_sets, np.float64)
+        n_sets = Ps_sets.shape[0]
+        n_pairs = 0 if idx4 is None else idx4.shape[0]
+        means = np.zeros(n_sets, np.float64) if want_means else None
+        self._check(self.lib.ecc_evaluate_batch(self.h, _ptr(Ps_sets), n_sets, _ptr(idx4), n_pairs, _ptr(out),
+                                                _ptr(means)))
+        return means
+
+    def pair_sample_counts(self, n_views):
+        counts = np.zeros(n_views * (n_views - 1) // 2, np.int32)
+        self._check(self.lib.ecc_pair_sample_counts(self.h, _ptr(counts)))
+        return counts
+
+    def partition_pairs(self, n_parts):
+        bounds = np.zeros(n_parts + 1, np.int64)
+        self._check(self.lib.ecc_partition_pairs(self.h, int(n_parts), _ptr(bounds)))
+        return bounds
+
+    # -- synthetic data
+    def synth_projections(self, Ps, n_u, n_v, ellipsoids, images, cos_weight=True, zero_border=True):
+        Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
+        ell = np.ascontiguousarray(ellipsoids, np.float64).reshape(-1, 7)
+        self._check(self.lib.ecc_synth_projections(self.h, _ptr(Ps), Ps.shape[0], n_u, n_v, _ptr(ell), ell.shape[0],
+                                                   int(cos_weight), int(zero_border), _ptr(images)))
+        return images
+
+    # -- instrumentation
+    def profile_enable(self, on=True):
+        self._check(self.lib.ecc_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._check(self.lib.ecc_profile_reset(self.h))
+
+    def profile_get(self, family):
+        ms, n = C.c_double(), C.c_longlong()
+        self._check(self.lib.ecc_profile_get(self.h, family.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def make_circular_trajectory(n_proj, sid, sdd, n_u, n_v, max_angle_deg, pixel_spacing):
+    """ProjTable::makeCircularTrajectory (HeaderOnly/Utils/Projtable.hxx:138-165); (n,12) col-major."""
+    Ps = np.zeros((n_proj, 12), np.float64)
+    _lib.load().ecc_make_circular_trajectory(n_proj, sid, sdd, n_u, n_v, max_angle_deg, pixel_spacing, _ptr(Ps))
+    return Ps
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class RadonIntermediate:
+    """Mirror of EpipolarConsistency::RadonIntermediate (RadonIntermediate.h:18-128).
+
+    Constructed from a projection image (computes right away, RadonIntermediate.cpp:17-31) or from an
+    existing dtr image plus its geometry (RadonIntermediate.cpp:69-80,105-123)."""
+
+    Derivative, Ramp, NoFilter = FILTER_DERIVATIVE, FILTER_RAMP, FILTER_NONE
+    Identity, SquareRoot, Logarithm = POST_IDENTITY, POST_SQRT, POST_LOG
+
+    def __init__(self, projection=None, size_alpha=0, size_t=0, filter=FILTER_DERIVATIVE, post_process=POST_IDENTITY,
+                 *, dtr=None, original_size=None, interp=INTERP_TEXTURE, ctx=None):
+        self.ctx = ctx or default_context()
+        self.m_filter = filter
+        self._cpu = None
+        if projection is not None:
+            import torch
+            img = projection
+            if isinstance(img, np.ndarray):
+                img = torch.from_numpy(np.ascontiguousarray(img, np.float32)).cuda()
+            self.n_y, self.n_x = img.shape
+            self.n_alpha, self.n_t = int(size_alpha), int(size_t)
+            self._gpu = self.ctx.radon_compute(img[None], self.n_alpha, self.n_t, filter, post_process, interp)[0]
+        else:
+            self.replaceRadonIntermediateData(dtr, original_size, filter)
+        self.m_bin_size_angle, self.m_bin_size_distance = Context.radon_bin_sizes(self.n_x, self.n_y, self.n_alpha,
+                                                                                  self.n_t)
+
+    @classmethod
+    def _from_device(cls, tensor, n_x, n_y, filter, ctx):
+        self = cls.__new__(cls)
+        self.ctx, self.m_filter, self._cpu, self._gpu = ctx, filter, None, tensor
+        self.n_t, self.n_alpha = tensor.shape
+        self.n_x, self.n_y = n_x, n_y
+        self.m_bin_size_angle, self.m_bin_size_distance = Context.radon_bin_sizes(n_x, n_y, self.n_alpha, self.n_t)
+        return self
+
+    def replaceRadonIntermediateData(self, dtr, original_size, filter=FILTER_DERIVATIVE):
+        import torch
+        self._cpu = np.ascontiguousarray(dtr, np.float32)
+        self._gpu = torch.from_numpy(self._cpu).cuda()
+        self.n_t, self.n_alpha = self._cpu.shape
+        self.n_x, self.n_y = original_size
+        self.m_filter = filter
+
+    def getFilter(self):
+        return self.m_filter
+
+    def isDerivative(self):
+        return self.m_filter == FILTER_DERIVATIVE
+
+    def readback(self, gpu_memory_only=False):
+        if not gpu_memory_only:
+            self._cpu = self._gpu.cpu().numpy()
+
+    def data(self):
+        """CPU image (n_t rows x n_alpha); valid after readback()."""
+        return self._cpu
+
+    def getTexture(self):
+        """The reference returns its texture wrapper; callers use it to make the dtr GPU resident."""
+        return self._gpu
+
+    def getRadonBinNumber(self, dim):
+        return self.n_t if dim else self.n_alpha
+
+    def getOriginalImageSize(self, dim):
+        return self.n_y if dim else self.n_x
+
+    def getRadonBinSize(self, dim=1):
+        return self.m_bin_size_distance if dim else self.m_bin_size_angle
+
+
+def compute_radon_intermediates(images, size_alpha, size_t, filter=FILTER_DERIVATIVE, post_process=POST_IDENTITY,
+                                interp=INTERP_TEXTURE, ctx=None):
+    """Batched form of the RadonIntermediate image constructor: one launch chain for all projections.
+    images: (n, n_v, n_u) numpy or torch-cuda.  Returns a list of RadonIntermediate views into one
+    contiguous device tensor (which MetricRadonIntermediate then borrows without copying)."""
+    import torch
+    ctx = ctx or default_context()
+    if isinstance(images, np.ndarray):
+        images = torch.from_numpy(np.ascontiguousarray(images, np.float32)).cuda()
+    n, n_v, n_u = images.shape
+    block = ctx.radon_compute(images, size_alpha, size_t, filter, post_process, interp)
+    return [RadonIntermediate._from_device(block[k], n_u, n_v, filter, ctx) for k in range(n)]
+
+
+class MetricRadonIntermediate:
+    """Mirror of EpipolarConsistency::MetricRadonIntermediate
+    (EpipolarConsistencyRadonIntermediate.h:21-106, .cpp:41-322) incl. the Metric base interface."""
+
+    def __init__(self, Ps=None, dtrs=None, ctx=None):
+        self.ctx = ctx or Context()
+        self.Ps = np.zeros((0, 12))
+        self.dtrs = []
+        if Ps is not None:
+            self.setProjectionMatrices(Ps)
+        if dtrs is not None:
+            self.setRadonIntermediates(dtrs)
+
+    # -- Metric base
+    def setObjectRadius(self, radius_mm=0.0):
+        self.ctx.set_object_radius(radius_mm)
+        return self
+
+    def getObjectRadius(self):
+        return self.ctx.get_object_radius()
+
+    def setEpipolarPlaneStep(self, dkappa_rad=0.0):
+        self.ctx.set_epipolar_plane_step(dkappa_rad)
+        return self
+
+    setdKappa = setEpipolarPlaneStep
+
+    def setProjectionMatrices(self, Ps):
+        self.Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12).copy()
+        self.ctx.set_projection_matrices(self.Ps)
+        return self
+
+    def getProjectionMatrices(self):
+        return self.Ps
+
+    def getNumberOfProjetions(self):  # [sic], as in the reference
+        return self.Ps.shape[0]
+
+    def useCorrelation(self, corr=True):
+        if corr:
+            raise EccError("correlation mode is not part of the hot path (SURVEY.md row N4)")
+        return self
+
+    def setInterpolation(self, interp):
+        self.ctx.set_interpolation(interp)
+        return self
+
+    # -- Radon intermediates
+    def setRadonIntermediates(self, dtrs):
+        import torch
+        self.dtrs = list(dtrs)
+        d0 = self.dtrs[0]
+        tensors = [d._gpu for d in self.dtrs]
+        # zero-copy when the dtrs are consecutive views of one block (compute_radon_intermediates)
+        stride = d0.n_t * d0.n_alpha * 4
+        base = tensors[0].data_ptr()
+        contiguous = all(t.data_ptr() == base + k * stride and t.is_contiguous() for k, t in enumerate(tensors))
+        if contiguous and tensors[0]._base is not None and tensors[0]._base.dim() == 3:
+            block = tensors[0]._base[:len(tensors)]
+        else:
+            block = torch.stack(tensors).contiguous()
+        self._block = block
+        self.ctx.set_radon_intermediates(block, d0.n_x, d0.n_y, d0.isDerivative(),
+                                         step_alpha=d0.getRadonBinSize(0), step_t=d0.getRadonBinSize(1))
+        return self
+
+    def getRadonIntermediates(self):
+        return self.dtrs
+
+    # -- evaluation
+    def evaluate(self, arg=None, out=None):
+        """evaluate()                 -> mean over all pairs
+        evaluate(cost_image)          -> same, n*n float32 image gets entry [j, i] = pair (i<j)
+        evaluate(views: set)          -> all pairs among the listed views
+        evaluate(indices (k,4), out)  -> explicit (P0,P1,dtr0,dtr1) list"""
+        if arg is None:
+            return self.ctx.evaluate(None)
+        if isinstance(arg, (set, frozenset)):
+            v = sorted(arg)
+            idx = np.array([(a, b, a, b) for ia, a in enumerate(v) for b in v[ia + 1:]], np.int32).reshape(-1, 4)
+            return self.ctx.evaluate_indices(idx, out)
+        arr = arg
+        if isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.ndim == 2 and arr.shape[0] == arr.shape[1] \
+                and arr.shape[0] == self.Ps.shape[0] and out is None:
+            return self.ctx.evaluate(arr)
+        idx = np.ascontiguousarray(arr, np.int32).reshape(-1, 4)
+        return self.ctx.evaluate_indices(idx, out)
+
+    def evaluateBatch(self, Ps_sets, indices=None, out=None):
+        """New capability: score K projection-matrix sets in one launch (means per set)."""
+        idx = None if indices is None else np.ascontiguousarray(indices, np.int32).reshape(-1, 4)
+        return self.ctx.evaluate_batch(np.ascontiguousarray(Ps_sets, np.float64), idx, out)

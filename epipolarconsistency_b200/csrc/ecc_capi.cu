@@ -1,0 +1,763 @@
+// ecc_capi.cu -- the C ABI of libecc_b200 (include/ecc_b200.h): context, host logic, launches.
+//
+// Host logic restated from the reference's C++ classes (code/LibEpipolarConsistency/):
+//   MetricRadonIntermediate::setRadonIntermediates   EpipolarConsistencyRadonIntermediate.cpp:87-106
+//   MetricRadonIntermediate::setProjectionMatrices   EpipolarConsistencyRadonIntermediate.cpp:134-163
+//   MetricRadonIntermediate::evaluate (3 overloads)  EpipolarConsistencyRadonIntermediate.cpp:166-322
+//   Metric::getObjectRadius / estimateObjectRadius   EpipolarConsistency.cpp:35-47,76-84
+//   RadonIntermediate::compute                       RadonIntermediate.cpp:198-211
+// Differences by design: all state lives in one context per GPU, every copy and launch is
+// asynchronous on the context's stream with one synchronisation at the end of a call that returns
+// a value, errors are returned instead of exit().
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "ecc_geometry.cuh"
+#include "ecc_internal.h"
+
+using namespace eccb200;
+
+namespace eccb200 {
+
+int fail(ecc_context* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+int cuda_fail(ecc_context* ctx, cudaError_t e, const char* what, const char* file, int line)
+{
+    std::string m = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) +
+                    ") in " + what + " at " + file + ":" + std::to_string(line);
+    return fail(ctx, ECC_ERR_CUDA, m);
+}
+
+bool is_device_pointer(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_bytes(ecc_context* ctx, void** ptr, size_t* cap, size_t bytes)
+{
+    if (*cap >= bytes && *ptr) return ECC_OK;
+    if (*ptr) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ECC_CUDA(ctx, cudaFree(*ptr));
+        *ptr = nullptr;
+        *cap = 0;
+    }
+    ECC_CUDA(ctx, cudaMalloc(ptr, bytes ? bytes : 16));
+    *cap = bytes ? bytes : 16;
+    return ECC_OK;
+}
+
+int ensure_pinned(ecc_context* ctx, size_t bytes)
+{
+    if (ctx->pinned_bytes >= bytes && ctx->pinned_h) return ECC_OK;
+    if (ctx->pinned_h) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ECC_CUDA(ctx, cudaFreeHost(ctx->pinned_h));
+        ctx->pinned_h = nullptr;
+        ctx->pinned_bytes = 0;
+    }
+    ECC_CUDA(ctx, cudaHostAlloc(&ctx->pinned_h, bytes ? bytes : 16, cudaHostAllocDefault));
+    ctx->pinned_bytes = bytes ? bytes : 16;
+    return ECC_OK;
+}
+
+int prof_begin(ecc_context* ctx, int family)
+{
+    if (!ctx->profiling) return -1;
+    ProfileSlot s;
+    s.family = family;
+    if (cudaEventCreate(&s.start) != cudaSuccess || cudaEventCreate(&s.stop) != cudaSuccess) return -1;
+    cudaEventRecord(s.start, ctx->stream);
+    ctx->prof_slots.push_back(s);
+    return (int)ctx->prof_slots.size() - 1;
+}
+
+void prof_end(ecc_context* ctx, int slot)
+{
+    if (slot < 0) return;
+    cudaEventRecord(ctx->prof_slots[slot].stop, ctx->stream);
+}
+
+void prof_collect(ecc_context* ctx)
+{
+    if (ctx->prof_slots.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->prof_slots) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.start, s.stop) == cudaSuccess) {
+            ctx->prof_ms[s.family] += ms;
+            ctx->prof_launches[s.family] += 1;
+        }
+        cudaEventDestroy(s.start);
+        cudaEventDestroy(s.stop);
+    }
+    ctx->prof_slots.clear();
+}
+
+}  // namespace eccb200
+
+namespace {
+
+struct Guard {  // make the context's device current for the duration of a call
+    explicit Guard(ecc_context* c) { cudaSetDevice(c->device); }
+};
+
+size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+void destroy_dtr_textures(ecc_context* ctx)
+{
+    for (auto t : ctx->dtr_tex_h) cudaDestroyTextureObject(t);
+    ctx->dtr_tex_h.clear();
+}
+
+// Fills the launch record with everything that depends only on the context state.
+int fill_launch(ecc_context* ctx, PairLaunch& L)
+{
+    if (ctx->n_views <= 0) return fail(ctx, ECC_ERR_STATE, "projection matrices not set");
+    if (ctx->n_dtrs <= 0 || !ctx->dtrs_d) return fail(ctx, ECC_ERR_STATE, "Radon intermediates not set");
+    double radius = 0;
+    int rc = ecc_get_object_radius(ctx, &radius);
+    if (rc) return rc;
+    L.n_views = ctx->n_views;
+    L.n_sets = 1;
+    L.pair_begin = 0;
+    L.n_pairs = 0;
+    L.idx4_d = nullptr;
+    L.Cs_d = ctx->Cs_d;
+    L.PinvTs_d = ctx->PinvTs_d;
+    L.tex_d = ctx->dtr_tex_d;
+    L.dtrs_d = ctx->dtrs_d;
+    L.dtr_pitch = ctx->dtr_pitch;
+    L.dtr_stride = ctx->dtr_stride;
+    L.n_dtrs = ctx->n_dtrs;
+    L.n_alpha = ctx->n_alpha;
+    L.n_t = ctx->n_t;
+    L.half_nu = ctx->n_u * 0.5f;
+    L.half_nv = ctx->n_v * 0.5f;
+    // launcher sizing as in the reference (EpipolarConsistencyRadonIntermediate.cu:320,347-358)
+    L.range_t = ctx->n_t * ctx->step_t;
+    L.image_diagonal = ctx->n_t * ctx->step_t * 2.f;
+    L.radius = (float)radius;
+    L.dkappa = (float)ctx->dkappa;
+    const int max_samples = (L.dkappa <= 0.f) ? (int)L.image_diagonal : (int)(ECC_PI_F * 0.5f / L.dkappa);
+    L.sample_cap = (max_samples + 255) / 256 * 256;
+    L.is_derivative = ctx->is_derivative;
+    L.interp = ctx->interp;
+    L.vals_d = nullptr;
+    L.image_d = nullptr;
+    return ECC_OK;
+}
+
+int upload_and_derive(ecc_context* ctx, const double* Ps, size_t count, double** Ps_d, float** Cs_d,
+                      float** A_d, size_t* cap)
+{
+    if (*cap < count) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*Ps_d) cudaFree(*Ps_d);
+        if (*Cs_d) cudaFree(*Cs_d);
+        if (*A_d) cudaFree(*A_d);
+        *Ps_d = nullptr; *Cs_d = nullptr; *A_d = nullptr; *cap = 0;
+        ECC_CUDA(ctx, cudaMalloc(Ps_d, sizeof(double) * 12 * count));
+        ECC_CUDA(ctx, cudaMalloc(Cs_d, sizeof(float) * 4 * count));
+        ECC_CUDA(ctx, cudaMalloc(A_d, sizeof(float) * 12 * count));
+        *cap = count;
+    }
+    ECC_CUDA(ctx, cudaMemcpyAsync(*Ps_d, Ps, sizeof(double) * 12 * count, cudaMemcpyDefault, ctx->stream));
+    return launch_derive_views(ctx, *Ps_d, (int)count, *A_d, *Cs_d);
+}
+
+// Batch-mode buffers live outside the context struct's main set so that the current matrices stay valid.
+struct BatchBuffers {
+    double* Ps_d = nullptr;
+    float* Cs_d = nullptr;
+    float* A_d = nullptr;
+    size_t cap = 0;
+};
+std::map<ecc_context*, BatchBuffers>& batch_buffers()
+{
+    static std::map<ecc_context*, BatchBuffers> m;
+    return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ecc_version(void) { return ECC_B200_VERSION; }
+
+int ecc_create(int device, ecc_context** out)
+{
+    if (!out) return ECC_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return ECC_ERR_CUDA;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return ECC_ERR_CUDA;
+    if (device >= count) return ECC_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return ECC_ERR_CUDA;
+    ecc_context* ctx = new ecc_context();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return ECC_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return ECC_OK;
+}
+
+void ecc_destroy(ecc_context* ctx)
+{
+    if (!ctx) return;
+    Guard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    prof_collect(ctx);
+    destroy_dtr_textures(ctx);
+    free_image_pool(ctx);
+    auto it = batch_buffers().find(ctx);
+    if (it != batch_buffers().end()) {
+        cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d);
+        batch_buffers().erase(it);
+    }
+    void* bufs[] = {ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, ctx->vals_d,
+                    ctx->sums_d, ctx->idx_d, ctx->counts_d, ctx->img_stage_d, ctx->out_stage_d, ctx->cost_d};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* ecc_last_error(const ecc_context* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int ecc_set_stream(ecc_context* ctx, void* cuda_stream)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ECC_OK;
+}
+
+int ecc_synchronize(ecc_context* ctx)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ECC_OK;
+}
+
+void ecc_radon_bin_sizes(int n_u, int n_v, int n_alpha, int n_t, double* step_alpha, double* step_t)
+{
+    const double diagonal = std::sqrt((double)n_v * n_v + (double)n_u * n_u);
+    if (step_t) *step_t = diagonal / n_t;
+    if (step_alpha) *step_alpha = 3.1415926535897931 / n_alpha;
+}
+
+int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n_u, int n_v, int n_alpha,
+                      int n_t, int filter, int post, int interp, float* dtrs_out)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!images || !dtrs_out || n_images < 0 || n_u < 2 || n_v < 2 || n_alpha < 1 || n_t < 1)
+        return fail(ctx, ECC_ERR_INVALID, "ecc_radon_compute: bad argument");
+    if (filter == ECC_FILTER_RAMP)
+        return fail(ctx, ECC_ERR_UNSUPPORTED, "ramp filter is not part of the hot path (SURVEY.md row N4)");
+    if (filter != ECC_FILTER_DERIVATIVE && filter != ECC_FILTER_NONE) return fail(ctx, ECC_ERR_INVALID, "bad filter");
+    if (post < 0 || post > 2) return fail(ctx, ECC_ERR_INVALID, "bad post_process");
+    if (interp != ECC_INTERP_TEXTURE && interp != ECC_INTERP_EXACT) return fail(ctx, ECC_ERR_INVALID, "bad interp");
+    if (n_images == 0) return ECC_OK;
+    const bool in_dev = is_device_pointer(images), out_dev = is_device_pointer(dtrs_out);
+    const size_t img_elems = (size_t)n_u * n_v, dtr_elems = (size_t)n_alpha * n_t;
+    if (in_dev && out_dev) return radon_batch(ctx, images, n_images, n_u, n_v, n_alpha, n_t, filter, post, interp, dtrs_out);
+    // Host memory on either side: stream the batch through device staging in chunks.
+    const int chunk = n_images < 32 ? n_images : 32;
+    int rc;
+    if (!in_dev && (rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * img_elems * chunk))) return rc;
+    if (!out_dev && (rc = ensure_bytes(ctx, (void**)&ctx->out_stage_d, &ctx->out_stage_bytes, sizeof(float) * dtr_elems * chunk))) return rc;
+    for (int first = 0; first < n_images; first += chunk) {
+        const int n = (n_images - first < chunk) ? n_images - first : chunk;
+        const float* src = images + (size_t)first * img_elems;
+        if (!in_dev) {
+            ECC_CUDA(ctx, cudaMemcpyAsync(ctx->img_stage_d, src, sizeof(float) * img_elems * n, cudaMemcpyHostToDevice, ctx->stream));
+            src = ctx->img_stage_d;
+        }
+        float* dst = out_dev ? dtrs_out + (size_t)first * dtr_elems : ctx->out_stage_d;
+        rc = radon_batch(ctx, src, n, n_u, n_v, n_alpha, n_t, filter, post, interp, dst);
+        if (rc) return rc;
+        if (!out_dev)
+            ECC_CUDA(ctx, cudaMemcpyAsync(dtrs_out + (size_t)first * dtr_elems, dst, sizeof(float) * dtr_elems * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ECC_OK;
+}
+
+int ecc_set_radon_intermediates(ecc_context* ctx, const float* dtrs, int n_dtrs, int n_alpha, int n_t,
+                                double step_alpha, double step_t, int n_u, int n_v, int is_derivative)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!dtrs || n_dtrs < 1 || n_alpha < 1 || n_t < 1 || n_u < 1 || n_v < 1)
+        return fail(ctx, ECC_ERR_INVALID, "ecc_set_radon_intermediates: bad argument");
+    const bool dev = is_device_pointer(dtrs);
+    const size_t tight_stride = (size_t)n_alpha * n_t;
+    // Texture objects over linear memory need a 32-byte aligned pitch and a 512-byte aligned base.
+    const bool borrowable = dev && (n_alpha % 8 == 0) && ((tight_stride * sizeof(float)) % 512 == 0) &&
+                            ((uintptr_t)dtrs % 512 == 0);
+    const float* base;
+    size_t pitch, stride;
+    if (borrowable) {
+        base = dtrs;
+        pitch = n_alpha;
+        stride = tight_stride;
+    } else {
+        pitch = round_up(n_alpha, 8);
+        stride = round_up(pitch * n_t, 128);
+        int rc = ensure_bytes(ctx, (void**)&ctx->dtrs_owned, &ctx->dtrs_owned_bytes, sizeof(float) * stride * n_dtrs);
+        if (rc) return rc;
+        if (pitch == (size_t)n_alpha && stride == tight_stride) {
+            ECC_CUDA(ctx, cudaMemcpyAsync(ctx->dtrs_owned, dtrs, sizeof(float) * stride * n_dtrs, cudaMemcpyDefault, ctx->stream));
+        } else {
+            ECC_CUDA(ctx, cudaMemsetAsync(ctx->dtrs_owned, 0, sizeof(float) * stride * n_dtrs, ctx->stream));
+            for (int k = 0; k < n_dtrs; k++)
+                ECC_CUDA(ctx, cudaMemcpy2DAsync(ctx->dtrs_owned + stride * k, sizeof(float) * pitch, dtrs + tight_stride * k,
+                                                sizeof(float) * n_alpha, sizeof(float) * n_alpha, n_t, cudaMemcpyDefault, ctx->stream));
+        }
+        base = ctx->dtrs_owned;
+    }
+    const bool same_layout = (base == ctx->dtrs_d && n_dtrs == ctx->n_dtrs && n_alpha == ctx->n_alpha && n_t == ctx->n_t &&
+                              pitch == ctx->dtr_pitch && stride == ctx->dtr_stride && (int)ctx->dtr_tex_h.size() == n_dtrs);
+    if (!same_layout) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        destroy_dtr_textures(ctx);
+        ctx->dtr_tex_h.resize(n_dtrs, 0);
+        for (int k = 0; k < n_dtrs; k++) {
+            cudaResourceDesc res = {};
+            res.resType = cudaResourceTypePitch2D;
+            res.res.pitch2D.devPtr = const_cast<float*>(base + stride * k);
+            res.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+            res.res.pitch2D.width = n_alpha;
+            res.res.pitch2D.height = n_t;
+            res.res.pitch2D.pitchInBytes = sizeof(float) * pitch;
+            cudaTextureDesc td = {};
+            td.normalizedCoords = 1;  // as the reference's dtr textures (RadonIntermediate.cpp:192)
+            td.filterMode = cudaFilterModeLinear;
+            td.addressMode[0] = cudaAddressModeClamp;
+            td.addressMode[1] = cudaAddressModeClamp;
+            td.readMode = cudaReadModeElementType;
+            ECC_CUDA(ctx, cudaCreateTextureObject(&ctx->dtr_tex_h[k], &res, &td, nullptr));
+        }
+        size_t cap_bytes = ctx->dtr_tex_cap * sizeof(cudaTextureObject_t);
+        int rc = ensure_bytes(ctx, (void**)&ctx->dtr_tex_d, &cap_bytes, sizeof(cudaTextureObject_t) * n_dtrs);
+        ctx->dtr_tex_cap = cap_bytes / sizeof(cudaTextureObject_t);
+        if (rc) return rc;
+        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->dtr_tex_d, ctx->dtr_tex_h.data(), sizeof(cudaTextureObject_t) * n_dtrs,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->dtrs_d = base;
+    ctx->dtr_pitch = pitch;
+    ctx->dtr_stride = stride;
+    ctx->n_dtrs = n_dtrs;
+    ctx->n_alpha = n_alpha;
+    ctx->n_t = n_t;
+    ctx->n_u = n_u;
+    ctx->n_v = n_v;
+    ctx->step_alpha = (float)step_alpha;
+    ctx->step_t = (float)step_t;
+    ctx->is_derivative = is_derivative ? 1 : 0;
+    return ECC_OK;
+}
+
+int ecc_set_projection_matrices(ecc_context* ctx, const double* Ps, int n)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (n < 0 || (n > 0 && !Ps)) return fail(ctx, ECC_ERR_INVALID, "ecc_set_projection_matrices: bad argument");
+    ctx->n_views = n;
+    ctx->Ps_h.resize((size_t)12 * n);
+    if (n == 0) return ECC_OK;
+    if (is_device_pointer(Ps)) {
+        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->Ps_h.data(), Ps, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        std::memcpy(ctx->Ps_h.data(), Ps, sizeof(double) * 12 * n);
+    }
+    return upload_and_derive(ctx, ctx->Ps_h.data(), n, &ctx->Ps_d, &ctx->Cs_d, &ctx->PinvTs_d, &ctx->Ps_cap);
+}
+
+int ecc_update_projection_matrix(ecc_context* ctx, int index, const double* P)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!P || index < 0 || index >= ctx->n_views) return fail(ctx, ECC_ERR_INVALID, "ecc_update_projection_matrix: bad index");
+    // the stream may still be reading the previous host copy of this matrix (async H2D from pageable
+    // memory completes before the call returns, so overwriting is safe)
+    std::memcpy(&ctx->Ps_h[(size_t)12 * index], P, sizeof(double) * 12);
+    ECC_CUDA(ctx, cudaMemcpyAsync(ctx->Ps_d + (size_t)12 * index, &ctx->Ps_h[(size_t)12 * index], sizeof(double) * 12,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    return launch_derive_views(ctx, ctx->Ps_d + (size_t)12 * index, 1, ctx->PinvTs_d + (size_t)12 * index,
+                               ctx->Cs_d + (size_t)4 * index);
+}
+
+int ecc_set_object_radius(ecc_context* ctx, double r)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    ctx->object_radius = r;
+    return ECC_OK;
+}
+
+int ecc_get_object_radius(ecc_context* ctx, double* radius)
+{
+    if (!ctx || !radius) return ECC_ERR_INVALID;
+    if (ctx->object_radius > 0) {
+        *radius = ctx->object_radius;
+        return ECC_OK;
+    }
+    if (ctx->n_views == 0) {
+        *radius = 0;
+        return ECC_OK;
+    }
+    // estimateObjectRadius on the first matrix: focal lengths from the rows of the left 3x3 block,
+    // field of view from the image size, times the source's distance to the origin.
+    const double* P = ctx->Ps_h.data();
+    const double m1[3] = {P[0], P[3], P[6]}, m2[3] = {P[1], P[4], P[7]}, m3[3] = {P[2], P[5], P[8]};
+    auto cross = [](const double* a, const double* b, double* c) {
+        c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    double U[3], V[3], t[3];
+    cross(m3, m2, U);
+    cross(m3, m1, V);
+    const double nU = std::sqrt(dot(U, U)), nV = std::sqrt(dot(V, V));
+    for (int k = 0; k < 3; k++) { U[k] /= nU; V[k] /= nV; }
+    cross(V, m3, t);
+    const double fu = dot(m1, t);
+    cross(U, m3, t);
+    const double fv = dot(m2, t);
+    const double fov = std::fmax(std::fabs(std::atan(0.5 * ctx->n_u / fu)), std::fabs(std::atan(0.5 * ctx->n_v / fv)));
+    double m[4];
+    for (int k = 0; k < 4; k++) {
+        int c[3], q = 0;
+        for (int j = 0; j < 4; j++)
+            if (j != k) c[q++] = j;
+        m[k] = det3d(P[0 + 3 * c[0]], P[0 + 3 * c[1]], P[0 + 3 * c[2]], P[1 + 3 * c[0]], P[1 + 3 * c[1]],
+                     P[1 + 3 * c[2]], P[2 + 3 * c[0]], P[2 + 3 * c[1]], P[2 + 3 * c[2]]);
+        if (k & 1) m[k] = -m[k];
+    }
+    const double C[3] = {m[0] / m[3], m[1] / m[3], m[2] / m[3]};
+    *radius = std::sin(fov) * std::sqrt(dot(C, C));
+    return ECC_OK;
+}
+
+int ecc_set_epipolar_plane_step(ecc_context* ctx, double dkappa)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    ctx->dkappa = dkappa;
+    return ECC_OK;
+}
+
+int ecc_set_interpolation(ecc_context* ctx, int interp)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    if (interp != ECC_INTERP_TEXTURE && interp != ECC_INTERP_EXACT) return fail(ctx, ECC_ERR_INVALID, "bad interp");
+    ctx->interp = interp;
+    return ECC_OK;
+}
+
+int ecc_evaluate_range(ecc_context* ctx, long long pair_begin, long long pair_end, float* cost_image, double* sum)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    PairLaunch L;
+    int rc = fill_launch(ctx, L);
+    if (rc) return rc;
+    const long long n = ctx->n_views, total = n * (n - 1) / 2;
+    if (ctx->n_dtrs < ctx->n_views) return fail(ctx, ECC_ERR_STATE, "all-pairs evaluation needs one dtr per projection matrix");
+    if (pair_begin < 0 || pair_end > total || pair_begin > pair_end) return fail(ctx, ECC_ERR_INVALID, "pair range out of bounds");
+    const long long count = pair_end - pair_begin;
+    if (sum) *sum = 0.0;
+    if (count == 0) return ECC_OK;
+    size_t cap = ctx->vals_cap * sizeof(float);
+    if ((rc = ensure_bytes(ctx, (void**)&ctx->vals_d, &cap, sizeof(float) * count))) return rc;
+    ctx->vals_cap = cap / sizeof(float);
+    L.pair_begin = pair_begin;
+    L.n_pairs = count;
+    L.vals_d = ctx->vals_d;
+    const bool img_dev = cost_image && is_device_pointer(cost_image);
+    if (cost_image) {
+        if (img_dev) {
+            L.image_d = cost_image;
+        } else {
+            L.image_d = nullptr;  // scatter on the host from the compact values instead
+        }
+    }
+    if ((rc = launch_pairs(ctx, L))) return rc;
+    if (sum) {
+        size_t scap = ctx->sums_cap * sizeof(double);
+        if ((rc = ensure_bytes(ctx, (void**)&ctx->sums_d, &scap, sizeof(double)))) return rc;
+        ctx->sums_cap = scap / sizeof(double);
+        if ((rc = launch_sum_sets(ctx, ctx->vals_d, count, 1, ctx->sums_d))) return rc;
+    }
+    const bool host_image = cost_image && !img_dev;
+    if (sum || host_image) {
+        const size_t need = sizeof(double) + (host_image ? sizeof(float) * count : 0);
+        if ((rc = ensure_pinned(ctx, need))) return rc;
+        double* sum_h = (double*)ctx->pinned_h;
+        float* vals_h = (float*)((char*)ctx->pinned_h + sizeof(double));
+        if (sum) ECC_CUDA(ctx, cudaMemcpyAsync(sum_h, ctx->sums_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_image) ECC_CUDA(ctx, cudaMemcpyAsync(vals_h, ctx->vals_d, sizeof(float) * count, cudaMemcpyDeviceToHost, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (sum) *sum = *sum_h;
+        if (host_image) {
+            // entries i + j*n for the evaluated pairs only; everything else keeps the caller's values
+            int i, j;
+            pair_from_index(pair_begin, (int)n, i, j);
+            for (long long k = 0; k < count; k++) {
+                cost_image[(size_t)i + (size_t)j * n] = vals_h[k];
+                if (++j >= n) { ++i; j = i + 1; }
+            }
+        }
+    }
+    return ECC_OK;
+}
+
+int ecc_evaluate(ecc_context* ctx, float* cost_image, double* mean)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    const long long n = ctx->n_views, total = n * (n - 1) / 2;
+    double sum = 0.0;
+    int rc = ecc_evaluate_range(ctx, 0, total, cost_image, mean ? &sum : nullptr);
+    if (rc) return rc;
+    if (mean) *mean = total ? sum / (double)total : 0.0;
+    return ECC_OK;
+}
+
+static int stage_indices(ecc_context* ctx, const int* idx4, int n_pairs, const int** idx_d)
+{
+    if (is_device_pointer(idx4) && ((uintptr_t)idx4 % 16 == 0)) {
+        *idx_d = idx4;
+        return ECC_OK;
+    }
+    size_t cap = ctx->idx_cap * sizeof(int);
+    int rc = ensure_bytes(ctx, (void**)&ctx->idx_d, &cap, sizeof(int) * 4 * n_pairs);
+    ctx->idx_cap = cap / sizeof(int);
+    if (rc) return rc;
+    ECC_CUDA(ctx, cudaMemcpyAsync(ctx->idx_d, idx4, sizeof(int) * 4 * n_pairs, cudaMemcpyDefault, ctx->stream));
+    *idx_d = ctx->idx_d;
+    return ECC_OK;
+}
+
+static int check_indices(ecc_context* ctx, const int* idx4, int n_pairs)
+{
+    // the reference checks only in debug builds (EpipolarConsistencyRadonIntermediate.cpp:248-275);
+    // out-of-range indices would fault the GPU, so host-side lists are always checked here.
+    if (is_device_pointer(idx4)) return ECC_OK;
+    for (int k = 0; k < n_pairs; k++) {
+        const int* q = idx4 + 4 * k;
+        if (q[0] < 0 || q[0] >= ctx->n_views || q[1] < 0 || q[1] >= ctx->n_views || q[2] < 0 || q[2] >= ctx->n_dtrs ||
+            q[3] < 0 || q[3] >= ctx->n_dtrs)
+            return fail(ctx, ECC_ERR_INVALID, "index array contains invalid indices");
+    }
+    return ECC_OK;
+}
+
+int ecc_evaluate_indices(ecc_context* ctx, const int* idx4, int n_pairs, float* out, double* mean)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (n_pairs < 0 || (n_pairs > 0 && !idx4)) return fail(ctx, ECC_ERR_INVALID, "ecc_evaluate_indices: bad argument");
+    PairLaunch L;
+    int rc = fill_launch(ctx, L);
+    if (rc) return rc;
+    if (mean) *mean = 0.0;
+    if (n_pairs == 0) return ECC_OK;
+    if ((rc = check_indices(ctx, idx4, n_pairs))) return rc;
+    if ((rc = stage_indices(ctx, idx4, n_pairs, &L.idx4_d))) return rc;
+    const bool out_dev = out && is_device_pointer(out);
+    if (out_dev) {
+        L.vals_d = out;
+    } else {
+        size_t cap = ctx->vals_cap * sizeof(float);
+        if ((rc = ensure_bytes(ctx, (void**)&ctx->vals_d, &cap, sizeof(float) * n_pairs))) return rc;
+        ctx->vals_cap = cap / sizeof(float);
+        L.vals_d = ctx->vals_d;
+    }
+    L.n_pairs = n_pairs;
+    if ((rc = launch_pairs(ctx, L))) return rc;
+    if (mean) {
+        size_t scap = ctx->sums_cap * sizeof(double);
+        if ((rc = ensure_bytes(ctx, (void**)&ctx->sums_d, &scap, sizeof(double)))) return rc;
+        ctx->sums_cap = scap / sizeof(double);
+        if ((rc = launch_sum_sets(ctx, L.vals_d, n_pairs, 1, ctx->sums_d))) return rc;
+    }
+    const bool host_out = out && !out_dev;
+    if (mean || host_out) {
+        if ((rc = ensure_pinned(ctx, sizeof(double) + sizeof(float) * (size_t)n_pairs))) return rc;
+        double* sum_h = (double*)ctx->pinned_h;
+        float* vals_h = (float*)((char*)ctx->pinned_h + sizeof(double));
+        if (mean) ECC_CUDA(ctx, cudaMemcpyAsync(sum_h, ctx->sums_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_out) ECC_CUDA(ctx, cudaMemcpyAsync(vals_h, L.vals_d, sizeof(float) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (mean) *mean = *sum_h / (double)n_pairs;
+        if (host_out) std::memcpy(out, vals_h, sizeof(float) * n_pairs);
+    }
+    return ECC_OK;
+}
+
+int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, const int* idx4, int n_pairs, float* out,
+                       double* means)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!Ps_sets || n_sets < 1) return fail(ctx, ECC_ERR_INVALID, "ecc_evaluate_batch: bad argument");
+    PairLaunch L;
+    int rc = fill_launch(ctx, L);
+    if (rc) return rc;
+    const long long n = ctx->n_views;
+    if (idx4) {
+        if (n_pairs < 1) return fail(ctx, ECC_ERR_INVALID, "ecc_evaluate_batch: empty pair list");
+        if ((rc = check_indices(ctx, idx4, n_pairs))) return rc;
+        if ((rc = stage_indices(ctx, idx4, n_pairs, &L.idx4_d))) return rc;
+        L.n_pairs = n_pairs;
+    } else {
+        if (ctx->n_dtrs < ctx->n_views) return fail(ctx, ECC_ERR_STATE, "all-pairs evaluation needs one dtr per projection matrix");
+        L.n_pairs = n * (n - 1) / 2;
+    }
+    BatchBuffers& B = batch_buffers()[ctx];
+    if ((rc = upload_and_derive(ctx, Ps_sets, (size_t)n_sets * n, &B.Ps_d, &B.Cs_d, &B.A_d, &B.cap))) return rc;
+    L.Cs_d = B.Cs_d;
+    L.PinvTs_d = B.A_d;
+    L.n_sets = n_sets;
+    const size_t items = (size_t)n_sets * L.n_pairs;
+    const bool out_dev = out && is_device_pointer(out);
+    if (out_dev) {
+        L.vals_d = out;
+    } else {
+        size_t cap = ctx->vals_cap * sizeof(float);
+        if ((rc = ensure_bytes(ctx, (void**)&ctx->vals_d, &cap, sizeof(float) * items))) return rc;
+        ctx->vals_cap = cap / sizeof(float);
+        L.vals_d = ctx->vals_d;
+    }
+    if ((rc = launch_pairs(ctx, L))) return rc;
+    if (means) {
+        size_t scap = ctx->sums_cap * sizeof(double);
+        if ((rc = ensure_bytes(ctx, (void**)&ctx->sums_d, &scap, sizeof(double) * n_sets))) return rc;
+        ctx->sums_cap = scap / sizeof(double);
+        if ((rc = launch_sum_sets(ctx, L.vals_d, L.n_pairs, n_sets, ctx->sums_d))) return rc;
+    }
+    const bool host_out = out && !out_dev;
+    if (means || host_out) {
+        if ((rc = ensure_pinned(ctx, sizeof(double) * n_sets + (host_out ? sizeof(float) * items : 0)))) return rc;
+        double* sums_h = (double*)ctx->pinned_h;
+        float* vals_h = (float*)((char*)ctx->pinned_h + sizeof(double) * n_sets);
+        if (means) ECC_CUDA(ctx, cudaMemcpyAsync(sums_h, ctx->sums_d, sizeof(double) * n_sets, cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_out) ECC_CUDA(ctx, cudaMemcpyAsync(vals_h, L.vals_d, sizeof(float) * items, cudaMemcpyDeviceToHost, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (means)
+            for (int s = 0; s < n_sets; s++) means[s] = sums_h[s] / (double)L.n_pairs;
+        if (host_out) std::memcpy(out, vals_h, sizeof(float) * items);
+    }
+    return ECC_OK;
+}
+
+int ecc_pair_sample_counts(ecc_context* ctx, int* counts)
+{
+    if (!ctx || !counts) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    PairLaunch L;
+    int rc = fill_launch(ctx, L);
+    if (rc) return rc;
+    const long long n = ctx->n_views, total = n * (n - 1) / 2;
+    if (total == 0) return ECC_OK;
+    L.n_pairs = total;
+    size_t cap = ctx->counts_cap * sizeof(int);
+    if ((rc = ensure_bytes(ctx, (void**)&ctx->counts_d, &cap, sizeof(int) * total))) return rc;
+    ctx->counts_cap = cap / sizeof(int);
+    if ((rc = launch_pair_counts(ctx, L, ctx->counts_d))) return rc;
+    ECC_CUDA(ctx, cudaMemcpyAsync(counts, ctx->counts_d, sizeof(int) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ECC_OK;
+}
+
+int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds)
+{
+    if (!ctx || !bounds || n_parts < 1) return ECC_ERR_INVALID;
+    const long long n = ctx->n_views, total = n * (n - 1) / 2;
+    std::vector<int> counts((size_t)total);
+    if (total) {
+        int rc = ecc_pair_sample_counts(ctx, counts.data());
+        if (rc) return rc;
+    }
+    double all = 0;
+    for (long long k = 0; k < total; k++) all += counts[k] + 16;  // +16: fixed per-pair cost (K0/K1 maps)
+    bounds[0] = 0;
+    double run = 0;
+    int part = 1;
+    for (long long k = 0; k < total && part < n_parts; k++) {
+        run += counts[k] + 16;
+        while (part < n_parts && run >= all * part / n_parts) bounds[part++] = k + 1;
+    }
+    while (part <= n_parts) bounds[part++] = total;
+    return ECC_OK;
+}
+
+int ecc_synth_projections(ecc_context* ctx, const double* Ps, int n, int n_u, int n_v, const double* ellipsoids,
+                          int n_ellipsoids, int cos_weight, int zero_border, float* images)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!Ps || !images || n < 1 || n_u < 1 || n_v < 1 || (n_ellipsoids > 0 && !ellipsoids))
+        return fail(ctx, ECC_ERR_INVALID, "ecc_synth_projections: bad argument");
+    if (!is_device_pointer(images)) return fail(ctx, ECC_ERR_INVALID, "ecc_synth_projections: images must be device memory");
+    return synth_projections(ctx, Ps, n, n_u, n_v, ellipsoids, n_ellipsoids, cos_weight, zero_border, images);
+}
+
+int ecc_profile_enable(ecc_context* ctx, int on)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!on) prof_collect(ctx);
+    ctx->profiling = on != 0;
+    return ECC_OK;
+}
+
+int ecc_profile_reset(ecc_context* ctx)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    prof_collect(ctx);
+    for (int f = 0; f < FAM_COUNT; f++) {
+        ctx->prof_ms[f] = 0;
+        ctx->prof_launches[f] = 0;
+    }
+    return ECC_OK;
+}
+
+int ecc_profile_get(ecc_context* ctx, const char* family, double* total_ms, long long* launches)
+{
+    if (!ctx || !family) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    static const char* names[FAM_COUNT] = {"radon", "pairs", "geometry", "reduce", "synth"};
+    prof_collect(ctx);
+    for (int f = 0; f < FAM_COUNT; f++)
+        if (std::strcmp(family, names[f]) == 0) {
+            if (total_ms) *total_ms = ctx->prof_ms[f];
+            if (launches) *launches = ctx->prof_launches[f];
+            return ECC_OK;
+        }
+    return fail(ctx, ECC_ERR_INVALID, "unknown kernel family");
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// ecc_internal.h -- context object and launcher declarations of libecc_b200 (not installed).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ecc_b200.h"
+
+namespace eccb200 {
+
+// Kernel families for the per-launch event profile.
+enum Family { FAM_RADON = 0, FAM_PAIRS, FAM_GEOMETRY, FAM_REDUCE, FAM_SYNTH, FAM_COUNT };
+
+struct ProfileSlot {
+    cudaEvent_t start, stop;
+    int family;
+};
+
+// Input-image staging for the Radon kernel: a pool of CUDA arrays (2-D tiled layout for the texture
+// units) with one linear-filter texture object each.
+struct ImagePool {
+    int n_u = 0, n_v = 0, count = 0;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> tex_h;
+    cudaTextureObject_t* tex_d = nullptr;
+};
+
+}  // namespace eccb200
+
+struct ecc_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // stream all work is issued on
+    cudaStream_t own_stream = nullptr;  // created by ecc_create
+    int sm_count = 148;
+    std::string last_error;
+
+    // ---- projection matrices ----
+    int n_views = 0;
+    std::vector<double> Ps_h;   // n_views*12, host copy (getProjectionMatrices, auto radius)
+    double* Ps_d = nullptr;     // device staging for derive kernel (capacity Ps_cap matrices)
+    float* Cs_d = nullptr;      // n*4
+    float* PinvTs_d = nullptr;  // n*12
+    size_t Ps_cap = 0;          // capacity in matrices of Ps_d / Cs_d / PinvTs_d
+
+    // ---- radon intermediates ----
+    int n_dtrs = 0, n_alpha = 0, n_t = 0, n_u = 0, n_v = 0, is_derivative = 1;
+    float step_alpha = 0.f, step_t = 0.f;
+    const float* dtrs_d = nullptr;  // [n_dtrs][n_t][dtr_pitch]
+    size_t dtr_pitch = 0;           // floats per row
+    size_t dtr_stride = 0;          // floats per dtr
+    float* dtrs_owned = nullptr;    // non-null when the context owns the storage
+    size_t dtrs_owned_bytes = 0;
+    std::vector<cudaTextureObject_t> dtr_tex_h;
+    cudaTextureObject_t* dtr_tex_d = nullptr;
+    size_t dtr_tex_cap = 0;
+
+    // ---- settings ----
+    double object_radius = 0.0;
+    double dkappa = 0.0;
+    int interp = ECC_INTERP_TEXTURE;
+
+    // ---- scratch ----
+    float* vals_d = nullptr;  // one float per evaluated (set,pair)
+    size_t vals_cap = 0;
+    double* sums_d = nullptr;  // one double per set
+    size_t sums_cap = 0;
+    int* idx_d = nullptr;  // uploaded index list
+    size_t idx_cap = 0;
+    int* counts_d = nullptr;
+    size_t counts_cap = 0;
+    float* img_stage_d = nullptr;  // device staging for host images / host dtr output
+    size_t img_stage_bytes = 0;
+    float* out_stage_d = nullptr;
+    size_t out_stage_bytes = 0;
+    void* pinned_h = nullptr;  // pinned host staging
+    size_t pinned_bytes = 0;
+    float* cost_d = nullptr;  // n*n device cost image when the caller's is on the host
+    size_t cost_cap = 0;
+
+    eccb200::ImagePool pool;
+
+    // ---- profiling ----
+    bool profiling = false;
+    std::vector<eccb200::ProfileSlot> prof_slots;
+    double prof_ms[eccb200::FAM_COUNT] = {0, 0, 0, 0, 0};
+    long long prof_launches[eccb200::FAM_COUNT] = {0, 0, 0, 0, 0};
+};
+
+namespace eccb200 {
+
+int fail(ecc_context* ctx, int code, const std::string& msg);
+int cuda_fail(ecc_context* ctx, cudaError_t e, const char* what, const char* file, int line);
+
+#define ECC_CUDA(ctx, call)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) return eccb200::cuda_fail((ctx), e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// RAII-less profile bracket: begin returns a slot index or -1.
+int prof_begin(ecc_context* ctx, int family);
+void prof_end(ecc_context* ctx, int slot);
+void prof_collect(ecc_context* ctx);
+
+bool is_device_pointer(const void* p);
+int ensure_bytes(ecc_context* ctx, void** ptr, size_t* cap, size_t bytes);
+int ensure_pinned(ecc_context* ctx, size_t bytes);
+
+// ---- launchers (ecc_pairs.cu) ----
+struct PairLaunch {
+    // problem
+    int n_views;           // matrices per set
+    int n_sets;            // 1 unless batched
+    long long pair_begin;  // all-pairs mode: first pair of the enumeration
+    long long n_pairs;     // pairs per set
+    const int* idx4_d;     // pair list (device) or null for all-pairs
+    const float* Cs_d;     // n_sets*n_views*4
+    const float* PinvTs_d; // n_sets*n_views*12
+    // dtrs
+    const cudaTextureObject_t* tex_d;
+    const float* dtrs_d;
+    size_t dtr_pitch, dtr_stride;
+    int n_dtrs, n_alpha, n_t;
+    float half_nu, half_nv, range_t, image_diagonal;
+    float radius, dkappa;
+    int sample_cap;
+    int is_derivative;
+    int interp;
+    // outputs
+    float* vals_d;   // n_sets*n_pairs
+    float* image_d;  // all-pairs: n_views*n_views cost image or null (only with n_sets==1)
+};
+int launch_pairs(ecc_context* ctx, const PairLaunch& L);
+int launch_pair_counts(ecc_context* ctx, const PairLaunch& L, int* counts_d);
+int launch_sum_sets(ecc_context* ctx, const float* vals_d, long long n_pairs, int n_sets,
+                    double* sums_d);
+int launch_derive_views(ecc_context* ctx, const double* Ps_d, int n, float* PinvTs_d, float* Cs_d);
+
+// ---- launchers (ecc_radon.cu) ----
+int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
+                int n_alpha, int n_t, int filter, int post, int interp, float* out_d);
+void free_image_pool(ecc_context* ctx);
+
+// ---- launchers (ecc_synth.cu) ----
+int synth_projections(ecc_context* ctx, const double* Ps_h, int n, int n_u, int n_v,
+                      const double* ell_h, int n_ell, int cos_weight, int zero_border,
+                      float* images_d);
+
+}  // namespace eccb200

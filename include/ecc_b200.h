@@ -1,0 +1,164 @@
+/* ecc_b200.h -- C ABI of the B200-native Epipolar-Consistency hot path (libecc_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/Eigen/torch types.  It replaces
+ * the host<->device seam of the reference (aaichert/EpipolarConsistency, paths relative to its
+ * code/ directory):
+ *
+ *   void epipolarConsistency(int n_x,int n_y,int num_dtrs,char* dtrs_d,int n_alpha,int n_t,
+ *        float step_alpha,float step_t,int num_Ps,float* Cs_d,float* PinvTs_d,int num_pairs,
+ *        int* indices_d,float* K01s_d,float* out_d,float object_radius_mm,float dkappa,
+ *        bool isDerivative,bool use_corr,float* out_corr_d)
+ *        -- LibEpipolarConsistency/EpipolarConsistencyRadonIntermediate.cpp:16-37 (decl.),
+ *           EpipolarConsistencyRadonIntermediate.cu:278-409 (def.)
+ *   void computeDerivLineIntegrals(cudaTextureObject_t in,int n_x,int n_y,int n_alpha,int n_t,
+ *        int filter,int post_process,float* out_d)
+ *        -- LibEpipolarConsistency/RadonIntermediate.cpp:12 (decl.), RadonIntermediate.cu:149-170
+ *
+ * plus the host logic around them that the reference keeps in C++ classes
+ * (MetricRadonIntermediate::setProjectionMatrices / setRadonIntermediates / evaluate*,
+ * EpipolarConsistencyRadonIntermediate.cpp:87-106,134-163,166-322; RadonIntermediate::compute,
+ * RadonIntermediate.cpp:198-211).  The C++ facade in include/EpipolarConsistency/ re-creates
+ * those classes on top of this ABI.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative ECC_ERR_* otherwise (the reference calls
+ *     exit() on CUDA errors, LibUtilsCuda/UtilsCuda.hxx:14-28); ecc_last_error() gives the text.
+ *   - Projection matrices: 3x4, doubles, COLUMN-major (P[r+3c], Eigen default), n of them packed.
+ *   - Images: n_v rows of n_u floats.  Radon intermediates ("dtrs"): n_t rows of n_alpha floats,
+ *     alpha fastest, bin (ix,iy) <-> alpha=(ix/n_alpha-1/2)pi, t=(iy/n_t-1/2)diag
+ *     (RadonIntermediate.cu:44-52).
+ *   - Data pointers marked [h|d] may be host or device memory; the library asks the CUDA runtime
+ *     which.  Everything else is host memory.
+ *   - One context = one GPU + one stream.  Calls on one context must be serialised by the caller.
+ *   - There is no CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef ECC_B200_H
+#define ECC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECC_B200_VERSION 100
+
+enum {
+    ECC_OK = 0,
+    ECC_ERR_CUDA = -1,        /* a CUDA runtime call failed                       */
+    ECC_ERR_INVALID = -2,     /* bad argument                                     */
+    ECC_ERR_STATE = -3,       /* matrices / dtrs not set, size mismatch           */
+    ECC_ERR_UNSUPPORTED = -4  /* e.g. ramp filter (reference RadonIntermediate.cu:173-237, "next" row N4) */
+};
+
+/* RadonIntermediate::Filter / PostProcess, LibEpipolarConsistency/RadonIntermediate.h:21-28 */
+enum { ECC_FILTER_DERIVATIVE = 0, ECC_FILTER_RAMP = 1, ECC_FILTER_NONE = 2 };
+enum { ECC_POST_IDENTITY = 0, ECC_POST_SQRT = 1, ECC_POST_LOG = 2 };
+
+/* Bilinear interpolation flavour.
+ * ECC_INTERP_TEXTURE: the GPU's texture filter (1.8 fixed-point weights) exactly as the reference
+ *   CUDA path uses it (LibUtilsCuda/CudaBindlessTexture.cpp:36-40) -- the drop-in default.
+ * ECC_INTERP_EXACT: full fp32 weights (the "CPU float path" numerics). */
+enum { ECC_INTERP_TEXTURE = 0, ECC_INTERP_EXACT = 1 };
+
+typedef struct ecc_context ecc_context;
+
+int ecc_version(void);
+
+/* Context life cycle.  device < 0 selects the current CUDA device. */
+int ecc_create(int device, ecc_context** ctx);
+void ecc_destroy(ecc_context* ctx);
+const char* ecc_last_error(const ecc_context* ctx);
+/* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL restores the context's own. */
+int ecc_set_stream(ecc_context* ctx, void* cuda_stream);
+int ecc_synchronize(ecc_context* ctx);
+
+/* ---- Radon intermediates ----------------------------------------------------------------------
+ * Batched replacement of RadonIntermediate(image,...)+compute() -> computeDerivLineIntegrals
+ * (RadonIntermediate.cpp:17-31,198-211; kernel RadonIntermediate.cu:31-143).
+ * images [h|d]: n_images * n_v * n_u floats.  dtrs_out [h|d]: n_images * n_t * n_alpha floats.
+ * Asynchronous on the context's stream when both pointers are device memory. */
+int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n_u, int n_v,
+                      int n_alpha, int n_t, int filter, int post_process, int interp,
+                      float* dtrs_out);
+/* Bin sizes exactly as RadonIntermediate::compute sets them (RadonIntermediate.cpp:204-206). */
+void ecc_radon_bin_sizes(int n_u, int n_v, int n_alpha, int n_t, double* step_alpha,
+                         double* step_t);
+
+/* ---- Metric state (MetricRadonIntermediate) ------------------------------------------------ */
+
+/* setRadonIntermediates (EpipolarConsistencyRadonIntermediate.cpp:87-106).  dtrs [h|d]:
+ * n_dtrs * n_t * n_alpha floats.  Device memory is BORROWED (the reference's rule "do not delete
+ * or change dtrs during lifetime of Metric", EpipolarConsistencyRadonIntermediate.h:45) unless its
+ * alignment forces a private copy; host memory is uploaded into a buffer the context owns. */
+int ecc_set_radon_intermediates(ecc_context* ctx, const float* dtrs, int n_dtrs, int n_alpha,
+                                int n_t, double step_alpha, double step_t, int n_u, int n_v,
+                                int is_derivative);
+
+/* setProjectionMatrices (EpipolarConsistencyRadonIntermediate.cpp:134-163): pseudo-inverse
+ * transposes and source positions are derived on the device in fp64 and stored as fp32. */
+int ecc_set_projection_matrices(ecc_context* ctx, const double* Ps, int n);
+/* Replace one matrix of the current set (tracking loops change a single view per step,
+ * Gui/SingleImageMotion.h:84-90). */
+int ecc_update_projection_matrix(ecc_context* ctx, int index, const double* P);
+
+/* Metric::setObjectRadius / getObjectRadius (EpipolarConsistency.cpp:70-84), 0 = automatic. */
+int ecc_set_object_radius(ecc_context* ctx, double radius_mm);
+int ecc_get_object_radius(ecc_context* ctx, double* radius_mm);
+/* Metric::setEpipolarPlaneStep / setdKappa (EpipolarConsistency.cpp:86-89), 0 = automatic. */
+int ecc_set_epipolar_plane_step(ecc_context* ctx, double dkappa_rad);
+int ecc_set_interpolation(ecc_context* ctx, int interp);
+
+/* ---- Metric evaluation ------------------------------------------------------------------------
+ * evaluate(float* cost_image) (EpipolarConsistencyRadonIntermediate.cpp:166-225): all n(n-1)/2
+ * pairs.  cost_image [h|d], nullable: n*n floats, entry i+j*n (i<j) receives the pair's value,
+ * all other entries keep the caller's values.  mean (nullable): arithmetic mean over pairs. */
+int ecc_evaluate(ecc_context* ctx, float* cost_image, double* mean);
+
+/* Same, restricted to pairs [pair_begin, pair_end) of the get_ij enumeration
+ * (EpipolarConsistencyCommon.hxx:52-79); sum = plain sum of those pairs' values.  This is the
+ * unit of multi-GPU partitioning. */
+int ecc_evaluate_range(ecc_context* ctx, long long pair_begin, long long pair_end,
+                       float* cost_image, double* sum);
+
+/* evaluate(indices,out) (EpipolarConsistencyRadonIntermediate.cpp:267-322): idx4 holds
+ * (P0,P1,dtr0,dtr1) per pair.  idx4 [h|d]; out [h|d], nullable: n_pairs floats. */
+int ecc_evaluate_indices(ecc_context* ctx, const int* idx4, int n_pairs, float* out, double* mean);
+
+/* Batched mode (new capability): n_sets complete projection-matrix sets
+ * (n_sets * n * 12 doubles, n = number of matrices per set = current n of the context) scored
+ * against the same dtrs in one launch.  idx4 nullable (all pairs).  out [h|d], nullable:
+ * n_sets * n_pairs floats in pair-list order (all pairs: get_ij order).  means: n_sets doubles. */
+int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, const int* idx4,
+                       int n_pairs, float* out, double* means);
+
+/* Number of kappa samples each pair takes (the work measure for equal-work partitioning), in
+ * get_ij order; counts: n(n-1)/2 ints, host. */
+int ecc_pair_sample_counts(ecc_context* ctx, int* counts);
+/* Cut the pair enumeration into n_parts contiguous ranges of (nearly) equal total kappa samples;
+ * bounds: n_parts+1 entries, bounds[0]=0, bounds[n_parts]=n(n-1)/2. */
+int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds);
+
+/* ---- Host helpers that the reference keeps next to the metric ------------------------------ */
+
+/* ProjTable::makeCircularTrajectory (HeaderOnly/Utils/Projtable.hxx:138-165). Ps: n*12 doubles. */
+void ecc_make_circular_trajectory(int n_proj, double sid, double sdd, int n_u, int n_v,
+                                  double max_angle_deg, double pixel_spacing, double* Ps);
+/* Synthetic cone-beam projections of ellipsoids (7 doubles each: centre, semi-axes, density) with
+ * cosine weighting (Gui/PreProccess.cpp:146-166) and zeroed border; images [d]: n*n_v*n_u. */
+int ecc_synth_projections(ecc_context* ctx, const double* Ps, int n, int n_u, int n_v,
+                          const double* ellipsoids, int n_ellipsoids, int cos_weight,
+                          int zero_border, float* images);
+
+/* ---- Instrumentation ------------------------------------------------------------------------
+ * With profiling on, every kernel launch is bracketed by CUDA events on the context's stream.
+ * ecc_profile_get sums them up per kernel family ("radon", "pairs", "geometry", "reduce",
+ * "synth").  Querying synchronises the stream. */
+int ecc_profile_enable(ecc_context* ctx, int on);
+int ecc_profile_reset(ecc_context* ctx);
+int ecc_profile_get(ecc_context* ctx, const char* family, double* total_ms, long long* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECC_B200_H */

@@ -1,0 +1,574 @@
+// ecc_oracle.cpp -- CPU oracle (test infrastructure, see ecc_oracle.h for the rules of use).
+//
+// Every function restates one piece of the reference (aaichert/EpipolarConsistency); the file:line
+// it follows is given above each function, relative to the reference's code/ directory.  The code
+// is written from the algorithm description, not copied: structure, names and the linear-algebra
+// routes (cofactors instead of Householder QR) are ours.  Where the reference's device code would
+// be contracted to FMA by nvcc we say so with an explicit fmaf(); everything else is plain fp32
+// (build with -ffp-contract=off, see Makefile).
+#include "ecc_oracle.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// The reference's device code uses this literal (EpipolarConsistencyCommon.hxx:141,155,
+// RadonIntermediate.cu:8); as a float it is 3.14159274f.
+const float kPiF = 3.14159265359f;
+const double kPiD = 3.14159265358979323846;
+
+// ---------------------------------------------------------------------------------------------
+// Texture-unit model.  CUDA linear filtering (LibUtilsCuda/CudaBindlessTexture.cpp:36-40 sets
+// linear + clamp): texel centre i sits at coordinate i+0.5, so the fetch position is xb = x-0.5,
+// i = floor(xb), weight = frac(xb); indices are clamped to the edge.  TEX8 stores the weight in
+// 1.8 fixed point.  Rounding rule calibrated on a B200 (tools/tex_probe.cu, profiles/): the
+// position is rounded to the nearest 1/256 (half up), which may carry into the texel index.
+// ---------------------------------------------------------------------------------------------
+struct Tap {
+    int i0, i1;
+    float w;  // weight of i1
+};
+
+inline Tap make_tap(float x, int n, int interp)
+{
+    Tap t;
+    float xb = x - 0.5f;
+    float fl;
+    if (interp == ORACLE_INTERP_TEX8) {
+        float q = floorf(xb * 256.0f + 0.5f);  // position in 1/256 texels
+        fl = floorf(q * (1.0f / 256.0f));
+        t.w = (q - fl * 256.0f) * (1.0f / 256.0f);
+    } else {
+        fl = floorf(xb);
+        t.w = xb - fl;
+    }
+    // Guard the float->int conversion against absurd coordinates (clamp makes them equivalent).
+    if (fl < -2.0f) fl = -2.0f;
+    if (fl > (float)n) fl = (float)n;
+    int i = (int)fl;
+    t.i0 = std::min(std::max(i, 0), n - 1);
+    t.i1 = std::min(std::max(i + 1, 0), n - 1);
+    return t;
+}
+
+inline float bilinear(const float* img, int w, int h, float x, float y, int interp)
+{
+    const Tap tx = make_tap(x, w, interp);
+    const Tap ty = make_tap(y, h, interp);
+    const float* r0 = img + (size_t)ty.i0 * w;
+    const float* r1 = img + (size_t)ty.i1 * w;
+    const float a = tx.w, b = ty.w;
+    // CUDA programming guide, "Linear Filtering":
+    // (1-a)(1-b)T[i,j] + a(1-b)T[i+1,j] + (1-a)b T[i,j+1] + ab T[i+1,j+1]
+    return (1.0f - a) * (1.0f - b) * r0[tx.i0] + a * (1.0f - b) * r0[tx.i1] +
+           (1.0f - a) * b * r1[tx.i0] + a * b * r1[tx.i1];
+}
+
+inline void sort_four(float* v)
+{
+    // any correct sort gives the same middle pair (RadonIntermediate.cu:18-28 uses bubble sort)
+    std::sort(v, v + 4);
+}
+
+// One Radon bin.  RadonIntermediate.cu:31-143.  count_only: just return the sample count.
+inline float radon_bin(const float* img, int n_ui, int n_vi, int ix, int iy, int n_alpha, int n_t,
+                       bool derivative, int post, int interp, double* n_samples)
+{
+    const float n_u = (float)n_ui, n_v = (float)n_vi;
+    // :46-52 bin -> (alpha, tau)
+    const float x_rel = ix / (float)n_alpha - 0.5f;
+    const float y_rel = iy / (float)n_t - 0.5f;
+    const float diag = sqrtf(n_u * n_u + n_v * n_v);
+    const float alpha = x_rel * kPiF;
+    const float tau = y_rel * diag;
+    // :54-58 line in Hessian normal form, origin moved from the image centre to the corner
+    const float l0 = -sinf(alpha);
+    const float l1 = cosf(alpha);
+    float l2 = -tau;
+    l2 += -0.5f * n_u * l0 - 0.5f * n_v * l1;
+    // :61-65 foot point and direction
+    float o0 = -l2 * l0;
+    float o1 = -l2 * l1;
+    const float d0 = l1;
+    const float d1 = -l0;
+    // :71-84 clip against the box inset by one pixel
+    float ts[4] = {(1.0f - o0) / d0, (n_u - 1.0f - o0) / d0, (1.0f - o1) / d1,
+                   (n_v - 1.0f - o1) / d1};
+    if (d0 * d0 < 1e-12f) { ts[0] = -1e10f; ts[1] = 1e10f; }
+    if (d1 * d1 < 1e-12f) { ts[2] = -1e10f; ts[3] = 1e10f; }
+    sort_four(ts);
+    float t = ts[1];
+    const float t_max = ts[2];
+    // :89-92 reject lines that miss the image
+    const float pu = fmaf(t, d0, o0), pv = fmaf(t, d1, o1);
+    const bool inside = (pu <= n_u && pv <= n_v && pu >= 0 && pv >= 0);
+    if (!inside || t_max <= t) return 0.0f;
+    // :98-99 texel centres
+    o0 += 0.5f;
+    o1 += 0.5f;
+    const float step = 0.66f;  // :102 (double literal .66 stored in a float)
+    float sum = 0.0f;
+    if (!derivative) {
+        // :107-109
+        double cnt = 0;
+        for (; t <= t_max; t += step) {
+            if (img) sum += bilinear(img, n_ui, n_vi, fmaf(t, d0, o0), fmaf(t, d1, o1), interp);
+            cnt += 1;
+        }
+        if (n_samples) *n_samples += cnt;
+        return sum * step;
+    }
+    // :114-123 two parallel lines, half a pixel either side of the bin's line
+    o0 -= 0.5f * d1;
+    o1 += 0.5f * d0;
+    float sumo = 0.0f;
+    double cnt = 0;
+    for (; t <= t_max; t += step) {
+        const float x = fmaf(t, d0, o0), y = fmaf(t, d1, o1);
+        if (img) {
+            sum += bilinear(img, n_ui, n_vi, x, y, interp);
+            sumo += bilinear(img, n_ui, n_vi, x + d1, y - d0, interp);
+        }
+        cnt += 2;
+    }
+    if (n_samples) *n_samples += cnt;
+    const float result = (sum - sumo) * step;
+    // :125-140 post-processing
+    if (post == 1) return result < 0 ? -sqrtf(-result) : sqrtf(result);
+    if (post == 2) return result < 0 ? -logf(-result + 1.0f) : logf(result + 1.0f);
+    return result;
+}
+
+// Sample a Radon intermediate along an epipolar line.  EpipolarConsistencyRadonIntermediate.cu:70-84
+// with the dtr texture semantics of RadonIntermediate.cpp:192 (normalised, linear, clamp).
+inline float redundancy(const float* K, const float* dtr, int n_alpha, int n_t, float range_t,
+                        float x0, float x1, bool is_derivative, int interp)
+{
+    float line[3] = {fmaf(K[3], x1, K[0] * x0), fmaf(K[4], x1, K[1] * x0),
+                     fmaf(K[5], x1, K[2] * x0)};
+    const int flipped = oracle_line_to_sample(line, range_t);
+    const float v = bilinear(dtr, n_alpha, n_t, line[0] * (float)n_alpha, line[1] * (float)n_t,
+                             interp);
+    return (is_derivative && flipped) ? -v : v;
+}
+
+// CUDA's __sincosf is sin.approx/cos.approx (abs. error about 2^-21); we do not model its bits,
+// fast_sincos only selects float-rounded double results versus libm sinf/cosf.
+inline void sincos_model(float x, int fast, float* s, float* c)
+{
+    if (fast) {
+        *s = (float)sin((double)x);
+        *c = (float)cos((double)x);
+    } else {
+        *s = sinf(x);
+        *c = cosf(x);
+    }
+}
+
+inline void cross3(const double* a, const double* b, double* c)
+{
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline double norm3(const double* a) { return sqrt(dot3(a, a)); }
+inline double det3(double a, double b, double c, double d, double e, double f, double g, double h,
+                   double i)
+{
+    return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+}
+
+}  // namespace
+
+extern "C" {
+
+int oracle_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// EpipolarConsistencyCommon.hxx:52-79 -- row-major enumeration of the strict upper triangle.
+void oracle_get_ij(int k, int n, int* i, int* j)
+{
+    int row = 0;
+    int rest = k;  // index inside the current row
+    while (rest >= n - row - 1) {
+        rest -= n - row - 1;
+        row++;
+    }
+    *i = row;
+    *j = row + 1 + rest;
+}
+
+// xprojectionmatrix.hxx:20-52: PinvT = (P P^T)^-1 P  (== transpose of P^T (P P^T)^-1).
+void oracle_pinv_transpose(const double* P, float* PinvT)
+{
+    double G[9];  // Gram matrix P P^T, symmetric
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int k = 0; k < 4; k++) s += P[r + 3 * k] * P[c + 3 * k];
+            G[r + 3 * c] = s;
+        }
+    const double det = det3(G[0], G[3], G[6], G[1], G[4], G[7], G[2], G[5], G[8]);
+    double Gi[9];  // inverse by cofactors
+    Gi[0] = (G[4] * G[8] - G[7] * G[5]) / det;
+    Gi[3] = -(G[3] * G[8] - G[6] * G[5]) / det;
+    Gi[6] = (G[3] * G[7] - G[6] * G[4]) / det;
+    Gi[1] = -(G[1] * G[8] - G[7] * G[2]) / det;
+    Gi[4] = (G[0] * G[8] - G[6] * G[2]) / det;
+    Gi[7] = -(G[0] * G[7] - G[6] * G[1]) / det;
+    Gi[2] = (G[1] * G[5] - G[4] * G[2]) / det;
+    Gi[5] = -(G[0] * G[5] - G[3] * G[2]) / det;
+    Gi[8] = (G[0] * G[4] - G[3] * G[1]) / det;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += Gi[r + 3 * k] * P[k + 3 * c];
+            PinvT[r + 3 * c] = (float)s;
+        }
+}
+
+// xprojectionmatrix.hxx:93-105: right null vector of P, scaled so that the last entry is one.
+void oracle_source_position(const double* P, float* C)
+{
+    // null vector by 3x3 minors of the 3x4 matrix: C_k = (-1)^k det(P without column k)
+    double m[4];
+    for (int k = 0; k < 4; k++) {
+        int c[3], q = 0;
+        for (int j = 0; j < 4; j++)
+            if (j != k) c[q++] = j;
+        m[k] = det3(P[0 + 3 * c[0]], P[0 + 3 * c[1]], P[0 + 3 * c[2]], P[1 + 3 * c[0]],
+                    P[1 + 3 * c[1]], P[1 + 3 * c[2]], P[2 + 3 * c[0]], P[2 + 3 * c[1]],
+                    P[2 + 3 * c[2]]);
+        if (k & 1) m[k] = -m[k];
+    }
+    for (int k = 0; k < 4; k++) C[k] = (float)(m[k] / m[3]);
+}
+
+// EpipolarConsistency.cpp:35-47 (estimateObjectRadius), ProjectionMatrix.cpp:104-112
+// (getCameraFocalLengthPx), :70-76 (camera centre, de-homogenised).
+double oracle_object_radius(const double* P, int n_u, int n_v)
+{
+    const double m1[3] = {P[0], P[3], P[6]}, m2[3] = {P[1], P[4], P[7]}, m3[3] = {P[2], P[5], P[8]};
+    double U[3], V[3], t[3];
+    cross3(m3, m2, U);
+    cross3(m3, m1, V);
+    const double nU = norm3(U), nV = norm3(V);
+    for (int k = 0; k < 3; k++) { U[k] /= nU; V[k] /= nV; }
+    cross3(V, m3, t);
+    const double fu = dot3(m1, t);
+    cross3(U, m3, t);
+    const double fv = dot3(m2, t);
+    const double fov = std::max(fabs(atan(0.5 * n_u / fu)), fabs(atan(0.5 * n_v / fv)));
+    // camera centre in double (the reference uses an SVD null space here; same point)
+    double m[4];
+    for (int k = 0; k < 4; k++) {
+        int c[3], q = 0;
+        for (int j = 0; j < 4; j++)
+            if (j != k) c[q++] = j;
+        m[k] = det3(P[0 + 3 * c[0]], P[0 + 3 * c[1]], P[0 + 3 * c[2]], P[1 + 3 * c[0]],
+                    P[1 + 3 * c[1]], P[1 + 3 * c[2]], P[2 + 3 * c[0]], P[2 + 3 * c[1]],
+                    P[2 + 3 * c[2]]);
+        if (k & 1) m[k] = -m[k];
+    }
+    const double C[3] = {m[0] / m[3], m[1] / m[3], m[2] / m[3]};
+    return sin(fov) * norm3(C);
+}
+
+// EpipolarConsistencyCommon.hxx:82-149.  same_view stands for the reference's pointer test
+// C0==C1 (:108-113), which fires when both matrix indices are equal.
+void oracle_compute_k01(float half_nu, float half_nv, const float* C0, const float* C1,
+                        const float* P0invT, const float* P1invT, float object_radius_mm,
+                        float num_samples, float dkappa, int same_view, float* K0, float* K1)
+{
+    if (same_view) {
+        for (int k = 0; k < 8; k++) K0[k] = K1[k] = 0.0f;
+        return;
+    }
+    // :115-120 Pluecker coordinates of the join of the two source positions
+    const float b01 = C0[0] * C1[1] - C0[1] * C1[0];
+    const float b02 = C0[0] * C1[2] - C0[2] * C1[0];
+    const float b03 = C0[0] * C1[3] - C0[3] * C1[0];
+    const float b12 = C0[1] * C1[2] - C0[2] * C1[1];
+    const float b13 = C0[1] * C1[3] - C0[3] * C1[1];
+    const float b23 = C0[2] * C1[3] - C0[3] * C1[2];
+    // :122-123 norms of moment and direction
+    const float mom = sqrtf(b12 * b12 + b02 * b02 + b01 * b01);
+    const float dir = sqrtf(b03 * b03 + b13 * b13 + b23 * b23);
+    // :126-129 the two planes spanning the pencil: through the origin, and farthest from it
+    const float E[8] = {b12 / mom,
+                        -b02 / mom,
+                        b01 / mom,
+                        0.0f,
+                        (-b01 * b13 - b02 * b23) / (mom * dir),
+                        (b01 * b03 - b12 * b23) / (mom * dir),
+                        (b02 * b03 + b12 * b13) / (mom * dir),
+                        -mom / dir};
+    // :131-132 K = PinvT(3x4) * E(4x2), column-major
+    const float* Pi[2] = {P0invT, P1invT};
+    float* Ko[2] = {K0, K1};
+    for (int v = 0; v < 2; v++)
+        for (int c = 0; c < 2; c++)
+            for (int r = 0; r < 3; r++) {
+                float s = 0.0f;
+                for (int k = 0; k < 4; k++) s += Pi[v][r + 3 * k] * E[k + 4 * c];
+                Ko[v][r + 3 * c] = s;
+            }
+    // :82-89,134-135 lines relative to the image centre; scale by the kappa=0 line's normal
+    for (int v = 0; v < 2; v++) {
+        float* K = Ko[v];
+        K[2] += half_nu * K[0] + half_nv * K[1];
+        K[5] += half_nu * K[3] + half_nv * K[4];
+        const float len = sqrtf(K[0] * K[0] + K[1] * K[1]);
+        for (int k = 0; k < 6; k++) K[k] /= len;
+    }
+    // :137-148
+    K0[6] = mom / dir;
+    K0[7] = -2.0f * atan2f(-0.5f * dir, mom / dir);
+    K1[7] = (K0[6] <= object_radius_mm) ? 0.5f * kPiF : asinf(object_radius_mm / K0[6]);
+    K1[6] = (dkappa <= 0.0f) ? 2.0f * K1[7] / num_samples : dkappa;
+}
+
+// EpipolarConsistencyCommon.hxx:152-171
+int oracle_line_to_sample(float* line, float range_t)
+{
+    const float len = sqrtf(line[0] * line[0] + line[1] * line[1]);
+    float a = atan2f(line[1], line[0]) / kPiF;
+    if (a < 0) a += 2.0f;
+    float d = -(line[2] / len) / range_t + 0.5f;
+    int flipped = 0;
+    if (a > 1.0f) {
+        a -= 1.0f;
+        d = 1.0f - d;
+        flipped = 1;
+    }
+    line[0] = a;
+    line[1] = d;
+    return flipped;
+}
+
+void oracle_radon(const float* img, int n_u, int n_v, int n_alpha, int n_t, int filter, int post,
+                  int interp, float* out)
+{
+    const bool derivative = (filter == 0);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int iy = 0; iy < n_t; iy++)
+        for (int ix = 0; ix < n_alpha; ix++)
+            out[(size_t)iy * n_alpha + ix] =
+                radon_bin(img, n_u, n_v, ix, iy, n_alpha, n_t, derivative, post, interp, nullptr);
+}
+
+double oracle_radon_num_samples(int n_u, int n_v, int n_alpha, int n_t, int filter)
+{
+    double total = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : total)
+    for (int iy = 0; iy < n_t; iy++)
+        for (int ix = 0; ix < n_alpha; ix++) {
+            double c = 0;
+            radon_bin(nullptr, n_u, n_v, ix, iy, n_alpha, n_t, filter == 0, 0, 0, &c);
+            total += c;
+        }
+    return total;
+}
+
+double oracle_ecc(const double* Ps, int n_views, const float* dtrs, int n_dtrs, int n_alpha,
+                  int n_t, float step_alpha, float step_t, int n_u, int n_v, int is_derivative,
+                  double object_radius_mm, double dkappa_d, int interp, int fast_sincos,
+                  const int* idx4, int n_pairs, float* out, int* ksamples)
+{
+    (void)step_alpha;
+    (void)n_dtrs;
+    // EpipolarConsistencyRadonIntermediate.cpp:134-163 host preparation (double -> float)
+    std::vector<float> Cs((size_t)n_views * 4), PinvTs((size_t)n_views * 12);
+    for (int v = 0; v < n_views; v++) {
+        oracle_pinv_transpose(Ps + 12 * v, &PinvTs[12 * v]);
+        oracle_source_position(Ps + 12 * v, &Cs[4 * v]);
+    }
+    // Metric::getObjectRadius (EpipolarConsistency.cpp:76-84); passed on as float (.cpp:189,297)
+    if (!(object_radius_mm > 0))
+        object_radius_mm = n_views ? oracle_object_radius(Ps, n_u, n_v) : 0.0;
+    const float radius = (float)object_radius_mm;
+    const float dkappa = (float)dkappa_d;
+    // launcher sizing, EpipolarConsistencyRadonIntermediate.cu:320,347-358
+    const float image_diagonal = n_t * step_t * 2.0f;
+    const float range_t = n_t * step_t;
+    int max_num_samples = (dkappa <= 0.0f) ? (int)image_diagonal : (int)(kPiF * 0.5f / dkappa);
+    const int sample_cap = ((max_num_samples + 255) / 256) * 256;  // grid.y * block.y
+    const bool all_pairs = (idx4 == nullptr);
+    if (all_pairs) n_pairs = n_views * (n_views - 1) / 2;
+
+    double total = 0;
+    const size_t dtr_len = (size_t)n_alpha * n_t;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : total)
+    for (int p = 0; p < n_pairs; p++) {
+        int p0, p1, r0, r1;
+        if (all_pairs) {
+            oracle_get_ij(p, n_views, &p0, &p1);
+            r0 = p0;
+            r1 = p1;
+        } else {
+            p0 = idx4[4 * p + 0];
+            p1 = idx4[4 * p + 1];
+            r0 = idx4[4 * p + 2];
+            r1 = idx4[4 * p + 3];
+        }
+        float K0[8], K1[8];
+        oracle_compute_k01(n_u * 0.5f, n_v * 0.5f, &Cs[4 * p0], &Cs[4 * p1], &PinvTs[12 * p0],
+                           &PinvTs[12 * p1], radius, image_diagonal, dkappa, p0 == p1, K0, K1);
+        const float dk = K1[6], kmax = K1[7];
+        const float* d0 = dtrs + dtr_len * r0;
+        const float* d1 = dtrs + dtr_len * r1;
+        double acc = 0;
+        int m = 0;
+        // .cu:192-197 / :258-263 kappa grid; .cu:86-113 +/- kappa
+        for (; m < sample_cap; m++) {
+            const float kappa = fmaf(dk, (float)m, dk * 0.5f);
+            if (kappa >= kmax) break;
+            float s, c;
+            sincos_model(kappa, fast_sincos, &s, &c);
+            const float vp = redundancy(K0, d0, n_alpha, n_t, range_t, c, s, is_derivative, interp) -
+                             redundancy(K1, d1, n_alpha, n_t, range_t, c, s, is_derivative, interp);
+            c = -c;  // .cu:106: minus kappa via the oppositely oriented line
+            const float vm = redundancy(K0, d0, n_alpha, n_t, range_t, c, s, is_derivative, interp) -
+                             redundancy(K1, d1, n_alpha, n_t, range_t, c, s, is_derivative, interp);
+            const float consistency = (vp * vp + vm * vm) * K0[6];  // .cu:112
+            acc += (double)(consistency * dk);                      // .cu:204,269 (atomicAdd there)
+        }
+        const float value = (float)acc;
+        if (ksamples) ksamples[p] = m;
+        if (out) {
+            if (all_pairs) out[p0 + (size_t)p1 * n_views] = value;  // .cu:269
+            else out[p] = value;
+        }
+        total += (double)value;  // .cpp:216-224,312-321 with all weights 1
+    }
+    return n_pairs ? total / n_pairs : 0.0;
+}
+
+// Projtable.hxx:138-165; CameraOpenGL.hxx:11-31; ProjectionMatrix.cpp:12-18,133-145.
+void oracle_circular_trajectory(int n_proj, double sid, double sdd, int n_u, int n_v,
+                                double max_angle_deg, double pixel_spacing, double* Ps)
+{
+    const double fovy = atan(n_v * pixel_spacing / sdd);
+    const double f = n_v / (2.0 * tan(0.5 * fovy));  // cameraPerspective: height / (2 tan(fovy/2))
+    const double K[9] = {f, 0, 0, 0, f, 0, 0.5 * n_u, 0.5 * n_v, 1};  // column-major 3x3
+    const double ct = cos(0.5 * kPiD), st = sin(0.5 * kPiD);          // rotation about x by 90 deg
+    for (int i = 0; i < n_proj; i++) {
+        const double ang = i * (max_angle_deg / n_proj) / 180.0 * kPiD;
+        const double eye[3] = {sid * cos(ang), 0.0, sid * sin(ang)};
+        // cameraLookAt: rows of R are left, up, -forward
+        double fwd[3] = {-eye[0], -eye[1], -eye[2]};
+        const double nf = norm3(fwd);
+        for (int k = 0; k < 3; k++) fwd[k] /= nf;
+        const double up0[3] = {0, 1, 0};
+        double left[3], up[3];
+        cross3(up0, fwd, left);
+        const double nl = norm3(left);
+        for (int k = 0; k < 3; k++) left[k] /= nl;
+        cross3(fwd, left, up);
+        double R[9], t[3];  // R row-major here
+        for (int k = 0; k < 3; k++) { R[0 + k] = left[k]; R[3 + k] = up[k]; R[6 + k] = -fwd[k]; }
+        for (int r = 0; r < 3; r++) t[r] = -(R[3 * r] * eye[0] + R[3 * r + 1] * eye[1] + R[3 * r + 2] * eye[2]);
+        // P = K [R | t]  (3x4, kept as rows for the moment)
+        double Pm[3][4];
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 3; c++) {
+                double s = 0;
+                for (int k = 0; k < 3; k++) s += K[r + 3 * k] * R[3 * k + c];
+                Pm[r][c] = s;
+            }
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += K[r + 3 * k] * t[k];
+            Pm[r][3] = s;
+        }
+        auto normalize = [&](double (*M)[4]) {
+            double n3 = sqrt(M[2][0] * M[2][0] + M[2][1] * M[2][1] + M[2][2] * M[2][2]);
+            const double d = det3(M[0][0], M[0][1], M[0][2], M[1][0], M[1][1], M[1][2], M[2][0],
+                                  M[2][1], M[2][2]);
+            if (d < 0) n3 = -n3;
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 4; c++) M[r][c] *= (1.0 / n3);
+        };
+        normalize(Pm);  // makeProjectionMatrix normalises once
+        // right-multiply by T_rot_x: rows/cols 1,2 form [[ct,-st],[st,ct]]
+        double Q[3][4];
+        for (int r = 0; r < 3; r++) {
+            Q[r][0] = Pm[r][0];
+            Q[r][1] = Pm[r][1] * ct + Pm[r][2] * st;
+            Q[r][2] = -Pm[r][1] * st + Pm[r][2] * ct;
+            Q[r][3] = Pm[r][3];
+        }
+        normalize(Q);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) Ps[12 * i + r + 3 * c] = Q[r][c];
+    }
+}
+
+void oracle_project_ellipsoids(const double* P, int n_u, int n_v, const double* ell, int n_ell,
+                               int cos_weight, int zero_border, float* img)
+{
+    // Back-projection of pixel (u,v): ray direction M^-1 (u,v,1)^T from the source position C.
+    const double M[9] = {P[0], P[1], P[2], P[3], P[4], P[5], P[6], P[7], P[8]};  // col-major 3x3
+    const double det = det3(M[0], M[3], M[6], M[1], M[4], M[7], M[2], M[5], M[8]);
+    double Mi[9];
+    Mi[0] = (M[4] * M[8] - M[7] * M[5]) / det;
+    Mi[3] = -(M[3] * M[8] - M[6] * M[5]) / det;
+    Mi[6] = (M[3] * M[7] - M[6] * M[4]) / det;
+    Mi[1] = -(M[1] * M[8] - M[7] * M[2]) / det;
+    Mi[4] = (M[0] * M[8] - M[6] * M[2]) / det;
+    Mi[7] = -(M[0] * M[7] - M[6] * M[1]) / det;
+    Mi[2] = (M[1] * M[5] - M[4] * M[2]) / det;
+    Mi[5] = -(M[0] * M[5] - M[3] * M[2]) / det;
+    Mi[8] = (M[0] * M[4] - M[3] * M[1]) / det;
+    double C[3];
+    for (int r = 0; r < 3; r++) C[r] = -(Mi[r] * P[9] + Mi[r + 3] * P[10] + Mi[r + 6] * P[11]);
+    // Intrinsics for the cosine weight (PreProccess.cpp:146-166 uses K(0,0), K(0,2), K(1,2) of the
+    // RQ decomposition).  For K[R|t]: m3 = r3 (unit after normalisation), pp = (m1.m3, m2.m3),
+    // f = |m1 - ppu*m3|.
+    const double m1[3] = {P[0], P[3], P[6]}, m2[3] = {P[1], P[4], P[7]}, m3[3] = {P[2], P[5], P[8]};
+    const double n3 = dot3(m3, m3);
+    const double ppu = dot3(m1, m3) / n3, ppv = dot3(m2, m3) / n3;
+    double tmp[3] = {m1[0] - ppu * m3[0], m1[1] - ppu * m3[1], m1[2] - ppu * m3[2]};
+    const float sdd_px = (float)(norm3(tmp) / sqrt(n3));
+    const float ppuf = (float)ppu, ppvf = (float)ppv;
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < n_v; v++)
+        for (int u = 0; u < n_u; u++) {
+            double d[3];
+            for (int r = 0; r < 3; r++) d[r] = Mi[r] * u + Mi[r + 3] * v + Mi[r + 6];
+            const double dn = norm3(d);
+            for (int r = 0; r < 3; r++) d[r] /= dn;
+            double val = 0;
+            for (int e = 0; e < n_ell; e++) {
+                const double* q = ell + 7 * e;
+                // scale space so the ellipsoid becomes the unit sphere
+                const double o[3] = {(C[0] - q[0]) / q[3], (C[1] - q[1]) / q[4], (C[2] - q[2]) / q[5]};
+                const double w[3] = {d[0] / q[3], d[1] / q[4], d[2] / q[5]};
+                const double a = dot3(w, w), b = dot3(o, w), c = dot3(o, o) - 1.0;
+                const double disc = b * b - a * c;
+                if (disc > 0) val += q[6] * 2.0 * sqrt(disc) / a;  // chord length (|d| = 1)
+            }
+            float pix = (float)val;
+            if (cos_weight) {
+                const float pou = (float)u - ppuf, pov = (float)v - ppvf;
+                pix *= sdd_px / sqrtf(pou * pou + pov * pov + sdd_px * sdd_px);
+            }
+            if (zero_border && (u == 0 || v == 0 || u == n_u - 1 || v == n_v - 1)) pix = 0.0f;
+            img[(size_t)v * n_u + u] = pix;
+        }
+}
+
+}  // extern "C"

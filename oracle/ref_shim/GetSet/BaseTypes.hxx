@@ -1,0 +1,2 @@
+// Build shim (ours): forwards to the reference's vendored copy, see StringType.hxx in this directory.
+#include <NRRD/BaseTypes.hxx>

@@ -1,0 +1,182 @@
+"""ctypes bindings for the CPU oracle (oracle/libecc_oracle.so) and, when present, the reference's
+own code built into oracle/_ref/ (libecc_ref_host.so, libecc_ref_cuda.so).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs.  Nothing under epipolarconsistency_b200/ may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+INTERP_EXACT = 0
+INTERP_TEX8 = 1
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(ref=True):
+    """Compile oracle/libecc_oracle.so (and oracle/_ref/* when /root/reference exists)."""
+    targets = ["libecc_oracle.so"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-C", ORACLE_DIR] + targets, check=True, stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    path = os.path.join(ORACLE_DIR, "libecc_oracle.so")
+    if not os.path.exists(path):
+        build_oracle(ref=False)
+    L = C.CDLL(path)
+    L.oracle_get_ij.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.oracle_pinv_transpose.argtypes = [_f64p, _f32p]
+    L.oracle_source_position.argtypes = [_f64p, _f32p]
+    L.oracle_object_radius.argtypes = [_f64p, C.c_int, C.c_int]
+    L.oracle_object_radius.restype = C.c_double
+    L.oracle_compute_k01.argtypes = [C.c_float, C.c_float, _f32p, _f32p, _f32p, _f32p, C.c_float,
+                                     C.c_float, C.c_float, C.c_int, _f32p, _f32p]
+    L.oracle_line_to_sample.argtypes = [_f32p, C.c_float]
+    L.oracle_line_to_sample.restype = C.c_int
+    L.oracle_radon.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
+    L.oracle_radon_num_samples.argtypes = [C.c_int] * 5
+    L.oracle_radon_num_samples.restype = C.c_double
+    L.oracle_ecc.argtypes = [_f64p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                             C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.oracle_ecc.restype = C.c_double
+    L.oracle_circular_trajectory.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                             C.c_double, C.c_double, _f64p]
+    L.oracle_project_ellipsoids.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_int, _f32p]
+    L.oracle_max_threads.restype = C.c_int
+    _oracle = L
+    return L
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy-level helpers
+# ------------------------------------------------------------------------------------------------
+def get_ij(k, n):
+    i, j = C.c_int(), C.c_int()
+    oracle().oracle_get_ij(k, n, C.byref(i), C.byref(j))
+    return i.value, j.value
+
+
+def pinv_transpose(P):
+    out = np.zeros(12, np.float32)
+    oracle().oracle_pinv_transpose(np.ascontiguousarray(P, np.float64).reshape(12), out)
+    return out
+
+
+def source_position(P):
+    out = np.zeros(4, np.float32)
+    oracle().oracle_source_position(np.ascontiguousarray(P, np.float64).reshape(12), out)
+    return out
+
+
+def object_radius(P, n_u, n_v):
+    return oracle().oracle_object_radius(np.ascontiguousarray(P, np.float64).reshape(12), n_u, n_v)
+
+
+def compute_k01(half_nu, half_nv, C0, C1, P0invT, P1invT, radius, num_samples, dkappa, same_view=False):
+    K0 = np.zeros(8, np.float32)
+    K1 = np.zeros(8, np.float32)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    oracle().oracle_compute_k01(half_nu, half_nv, f(C0), f(C1), f(P0invT), f(P1invT), radius,
+                                num_samples, dkappa, int(same_view), K0, K1)
+    return K0, K1
+
+
+def line_to_sample(line, range_t):
+    l = np.ascontiguousarray(line, np.float32).copy()
+    flipped = oracle().oracle_line_to_sample(l, range_t)
+    return l, flipped
+
+
+def radon(img, n_alpha, n_t, filter=0, post=0, interp=INTERP_EXACT):
+    img = np.ascontiguousarray(img, np.float32)
+    n_v, n_u = img.shape
+    out = np.zeros((n_t, n_alpha), np.float32)
+    oracle().oracle_radon(img, n_u, n_v, n_alpha, n_t, filter, post, interp, out)
+    return out
+
+
+def radon_num_samples(n_u, n_v, n_alpha, n_t, filter=0):
+    return oracle().oracle_radon_num_samples(n_u, n_v, n_alpha, n_t, filter)
+
+
+def ecc(Ps, dtrs, n_u, n_v, is_derivative=True, object_radius_mm=0.0, dkappa=0.0,
+        interp=INTERP_EXACT, fast_sincos=False, idx4=None, want_out=True, want_ksamples=False):
+    """Returns (mean, out, ksamples).  Ps: (n,12) col-major doubles; dtrs: (m, n_t, n_alpha)."""
+    Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
+    dtrs = np.ascontiguousarray(dtrs, np.float32)
+    n = Ps.shape[0]
+    m, n_t, n_alpha = dtrs.shape
+    diag = np.sqrt(float(n_u) ** 2 + float(n_v) ** 2)
+    step_alpha = np.float32(np.pi / n_alpha)
+    step_t = np.float32(diag / n_t)
+    if idx4 is None:
+        n_pairs = n * (n - 1) // 2
+        out = np.zeros((n, n), np.float32) if want_out else None
+        idx_ptr = None
+    else:
+        idx4 = np.ascontiguousarray(idx4, np.int32).reshape(-1, 4)
+        n_pairs = idx4.shape[0]
+        out = np.zeros(n_pairs, np.float32) if want_out else None
+        idx_ptr = idx4.ctypes.data_as(C.c_void_p)
+    ks = np.zeros(n_pairs, np.int32) if want_ksamples else None
+    mean = oracle().oracle_ecc(Ps, n, dtrs, m, n_alpha, n_t, float(step_alpha), float(step_t), n_u, n_v,
+                               int(is_derivative), float(object_radius_mm), float(dkappa), interp,
+                               int(fast_sincos), idx_ptr, n_pairs,
+                               out.ctypes.data_as(C.c_void_p) if out is not None else None,
+                               ks.ctypes.data_as(C.c_void_p) if ks is not None else None)
+    return mean, out, ks
+
+
+def circular_trajectory(n, sid, sdd, n_u, n_v, max_angle_deg, pixel_spacing):
+    Ps = np.zeros((n, 12), np.float64)
+    oracle().oracle_circular_trajectory(n, sid, sdd, n_u, n_v, max_angle_deg, pixel_spacing, Ps)
+    return Ps
+
+
+def project_ellipsoids(P, n_u, n_v, ellipsoids, cos_weight=True, zero_border=True):
+    ell = np.ascontiguousarray(ellipsoids, np.float64).reshape(-1, 7)
+    img = np.zeros((n_v, n_u), np.float32)
+    oracle().oracle_project_ellipsoids(np.ascontiguousarray(P, np.float64).reshape(12), n_u, n_v, ell,
+                                       ell.shape[0], int(cos_weight), int(zero_border), img)
+    return img
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own code
+# ------------------------------------------------------------------------------------------------
+_ref_host = None
+
+
+def ref_host():
+    """The reference's host-callable headers compiled unchanged; None if not built."""
+    global _ref_host
+    if _ref_host is not None:
+        return _ref_host
+    path = os.path.join(ORACLE_DIR, "_ref", "libecc_ref_host.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_get_ij.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ref_pinv_transpose.argtypes = [_f64p, _f32p]
+    L.ref_source_position.argtypes = [_f64p, _f32p]
+    L.ref_compute_k01.argtypes = [C.c_float, C.c_float, _f32p, _f32p, _f32p, _f32p, C.c_float,
+                                  C.c_float, C.c_float, _f32p, _f32p]
+    L.ref_line_to_sample.argtypes = [_f32p, C.c_float]
+    L.ref_line_to_sample.restype = C.c_int
+    _ref_host = L
+    return L

@@ -1,0 +1,199 @@
+"""CPU tests: pin the oracle against the reference's own code (golden vectors generated from the
+reference headers, tests/golden/make_ref_host_vectors.py) and against the invariants the reference
+states in code and comments."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_host_vectors.npz")
+ELL = np.array([[0, 0, 0, 60, 40, 50, 1.0], [20, -10, 5, 20, 25, 15, 0.5], [-25, 15, -10, 15, 10, 20, -0.4]])
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLDEN)
+
+
+@pytest.fixture(scope="module")
+def small_scene():
+    n, n_u, n_v = 8, 160, 128
+    Ps = ol.circular_trajectory(n, 750, 1200, n_u, n_v, 200, 2.0)
+    imgs = np.stack([ol.project_ellipsoids(P, n_u, n_v, ELL) for P in Ps])
+    dtrs = np.stack([ol.radon(im, 192, 192) for im in imgs])
+    return dict(n=n, n_u=n_u, n_v=n_v, Ps=Ps, imgs=imgs, dtrs=dtrs)
+
+
+# ---- golden vectors from the reference headers ---------------------------------------------------
+@pytest.mark.parametrize("n", [2, 3, 7, 100, 496])
+def test_get_ij_matches_reference(gold, n):
+    tab = gold[f"get_ij_{n}"]
+    mine = np.array([ol.get_ij(k, n) for k in range(tab.shape[0])], np.int32)
+    assert np.array_equal(mine, tab)
+
+
+def test_get_ij_enumerates_every_pair_once():
+    n = 37
+    seen = {ol.get_ij(k, n) for k in range(n * (n - 1) // 2)}
+    assert seen == {(i, j) for i in range(n) for j in range(i + 1, n)}
+
+
+def test_pinv_and_source_match_reference(gold):
+    for P, A_ref, C_ref in zip(gold["Ps"], gold["pinvT"], gold["Cs"]):
+        A = ol.pinv_transpose(P)
+        Cc = ol.source_position(P)
+        assert np.max(np.abs(A - A_ref)) <= 2e-6 * np.max(np.abs(A_ref))
+        assert np.max(np.abs(Cc[:3] - C_ref[:3])) <= 2e-6 * np.max(np.abs(C_ref[:3])) + 1e-9
+        assert Cc[3] == 1.0
+
+
+def test_culaut_residuals(gold):
+    """P*C ~ 0 and P*(PinvT)^T ~ I (the checks of the reference's TestCudaUtils.cpp:39-57)."""
+    for P in gold["Ps"][:8]:
+        Pm = P.reshape(4, 3).T
+        A = ol.pinv_transpose(P).astype(np.float64).reshape(4, 3).T
+        Cc = ol.source_position(P).astype(np.float64)
+        assert np.max(np.abs(Pm @ Cc)) < 1e-3 * np.max(np.abs(Pm))
+        assert np.max(np.abs(Pm @ A.T - np.eye(3))) < 1e-5
+
+
+def test_compute_k01_matches_reference(gold):
+    Cs, A, pairs = gold["Cs"], gold["pinvT"], gold["pairs"]
+    for s, (radius, dk) in enumerate(gold["settings"]):
+        for q, (a, b) in enumerate(pairs):
+            K0, K1 = ol.compute_k01(160.0, 128.0, Cs[a], Cs[b], A[a], A[b], radius, 819.6, dk)
+            ref = gold["K01"][s, q]
+            got = np.concatenate([K0, K1])
+            scale = np.maximum(np.abs(ref), 1e-3)
+            assert np.max(np.abs(got - ref) / scale) < 2e-5, (s, q, got, ref)
+
+
+def test_line_to_sample_matches_reference(gold):
+    for line, ref in zip(gold["lines"], gold["samples"]):
+        l, flipped = ol.line_to_sample(line, 409.8)
+        assert flipped == int(ref[2])
+        assert abs(l[0] - ref[0]) < 1e-6 and abs(l[1] - ref[1]) < 1e-5 * max(1.0, abs(ref[1]))
+
+
+def test_live_reference_headers_if_built(gold):
+    """When oracle/_ref is present, call the reference's compiled headers directly on fresh inputs."""
+    R = ol.ref_host()
+    if R is None:
+        pytest.skip("oracle/_ref/libecc_ref_host.so not built")
+    rng = np.random.default_rng(7)
+    Ps = ol.circular_trajectory(5, 600, 1100, 200, 180, 360, 1.5) * (1 + 1e-3 * rng.standard_normal((5, 12)))
+    for P in Ps:
+        a = np.zeros(12, np.float32)
+        R.ref_pinv_transpose(P, a)
+        assert np.allclose(ol.pinv_transpose(P), a, rtol=2e-6, atol=1e-12)
+    for k in range(10):
+        i, j = C.c_int(), C.c_int()
+        R.ref_get_ij(k, 5, C.byref(i), C.byref(j))
+        assert (i.value, j.value) == ol.get_ij(k, 5)
+
+
+# ---- invariants of the Radon intermediate ----------------------------------------------------------
+def test_radon_layout_and_zero_rows(small_scene):
+    d = small_scene["dtrs"]
+    assert d.shape == (8, 192, 192)
+    # lines at |t| = diag/2 miss the image: exactly zero (RadonIntermediate.cu:89-92)
+    assert np.all(d[:, 0, :] == 0)
+    assert np.abs(d).max() > 1.0
+
+
+def test_radon_constant_image_line_length():
+    """No-filter Radon of a constant image = chord length of the one-pixel-inset box (within a step)."""
+    n_u, n_v, n_a, n_t = 96, 64, 64, 64
+    r = ol.radon(np.ones((n_v, n_u), np.float32), n_a, n_t, filter=2)
+    iy, ix = n_t // 2, n_a // 2  # alpha = 0, tau = 0: horizontal line through the centre
+    assert abs(r[iy, ix] - (n_u - 2)) <= 0.67
+    # alpha = -pi/2: vertical line through the centre
+    assert abs(r[iy, 0] - (n_v - 2)) <= 0.67
+
+
+def test_radon_derivative_is_difference_of_neighbouring_lines():
+    """Derivative filter of a ramp image I(u,v)=v: horizontal lines one pixel apart differ by -length."""
+    n_u, n_v = 80, 60
+    img = np.tile(np.arange(n_v, dtype=np.float32)[:, None], (1, n_u))
+    r = ol.radon(img, 64, 64, filter=0)
+    val = r[32, 32]  # alpha=0: normal (0,1); line at +1/2 minus line at -1/2 -> +1 per unit length
+    n_samples = np.floor((n_u - 2) / np.float32(0.66)) + 1
+    assert abs(val - n_samples * 0.66) < 1e-2 * abs(val)
+
+
+def test_radon_tex8_close_to_exact(small_scene):
+    im = small_scene["imgs"][0]
+    a = small_scene["dtrs"][0]
+    b = ol.radon(im, 192, 192, interp=ol.INTERP_TEX8)
+    rel = np.abs(a - b).max() / np.abs(a).max()
+    assert 0 < rel < 1e-2  # quantised weights differ, but only at the 1e-3 level
+
+
+def test_radon_sample_count_formula():
+    n_u, n_v, n_a, n_t = 160, 128, 96, 96
+    cnt = ol.radon_num_samples(n_u, n_v, n_a, n_t)
+    # mean chord = area of the inset box / diagonal ... per bin: 2 lines * chord / 0.66
+    est = 2.0 * (n_u - 2) * (n_v - 2) / (np.hypot(n_u, n_v) * 0.66) * n_a * n_t
+    assert abs(cnt - est) / est < 0.05
+
+
+# ---- invariants of the metric --------------------------------------------------------------------
+def test_grangeat_consistency(small_scene):
+    s = small_scene
+    mean, out, ks = ol.ecc(s["Ps"], s["dtrs"], s["n_u"], s["n_v"], want_ksamples=True)
+    assert mean > 0
+    Pp = s["Ps"].copy()
+    H = np.eye(3)
+    H[0, 2], H[1, 2] = 3.0, 2.0  # detector shift of view 2 by (3,2) px
+    Pp[2] = (H @ s["Ps"][2].reshape(4, 3).T).T.reshape(12)
+    mean_p, _, _ = ol.ecc(Pp, s["dtrs"], s["n_u"], s["n_v"])
+    assert mean_p > 10 * mean
+    # kappa sample count: auto dkappa = kappa_max/diag -> about diag samples per pair
+    assert np.all(np.abs(ks - np.hypot(s["n_u"], s["n_v"])) <= 1)
+
+
+def test_cost_image_layout_and_mean(small_scene):
+    s = small_scene
+    n = s["n"]
+    mean, out, _ = ol.ecc(s["Ps"], s["dtrs"], s["n_u"], s["n_v"])
+    vals = [out[j, i] for i in range(n) for j in range(i + 1, n)]  # entry i + j*n, i<j
+    assert all(v > 0 for v in vals)
+    assert np.all(np.triu(out) == 0)  # nothing on or above the diagonal of the x-fastest image
+    assert abs(np.mean(np.array(vals, np.float64)) - mean) < 1e-9 * mean
+
+
+def test_index_list_equals_all_pairs(small_scene):
+    s = small_scene
+    n = s["n"]
+    _, out, _ = ol.ecc(s["Ps"], s["dtrs"], s["n_u"], s["n_v"])
+    idx = np.array([(i, j, i, j) for i in range(n) for j in range(i + 1, n)], np.int32)
+    mean2, out2, _ = ol.ecc(s["Ps"], s["dtrs"], s["n_u"], s["n_v"], idx4=idx)
+    ref = np.array([out[j, i] for i, j, _, _ in idx])
+    assert np.array_equal(out2, ref)
+    # same view twice: the reference zeroes the record -> no samples, value 0
+    _, out3, ks3 = ol.ecc(s["Ps"], s["dtrs"], s["n_u"], s["n_v"], idx4=np.array([[1, 1, 1, 1]], np.int32),
+                          want_ksamples=True)
+    assert out3[0] == 0 and ks3[0] == 0
+
+
+def test_fixed_dkappa_sample_counts(small_scene):
+    s = small_scene
+    dk = np.deg2rad(0.05)
+    _, _, ks = ol.ecc(s["Ps"], s["dtrs"], s["n_u"], s["n_v"], dkappa=dk, want_ksamples=True)
+    r = ol.object_radius(s["Ps"][0], s["n_u"], s["n_v"])
+    assert ks.max() <= int(np.pi / 2 / dk) + 1
+    assert ks.min() >= 1 and r > 0
+
+
+def test_trajectory_geometry():
+    Ps = ol.circular_trajectory(12, 750, 1200, 320, 256, 360, 1.0)
+    for k, P in enumerate(Ps):
+        Cc = ol.source_position(P).astype(np.float64)
+        assert abs(np.linalg.norm(Cc[:3]) - 750) < 1e-3  # source on the circle of radius sid
+        Pm = P.reshape(4, 3).T
+        x = Pm @ np.array([0, 0, 0, 1.0])
+        assert np.allclose(x[:2] / x[2], [160, 128], atol=1e-6)  # origin projects to the principal point
+        assert abs(np.linalg.norm(Pm[2, :3]) - 1) < 1e-12  # normalised
