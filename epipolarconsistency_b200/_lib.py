@@ -26,6 +26,8 @@ SIGNATURES = {
     "ecc_set_radon_intermediates": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
     "ecc_set_projection_matrices": (C.c_int, [c_ctx, c_vp, C.c_int]),
     "ecc_update_projection_matrix": (C.c_int, [c_ctx, C.c_int, c_vp]),
+    "ecc_get_derived_views": (C.c_int, [c_ctx, c_vp, c_vp]),
+    "ecc_derive_views_host": (None, [c_vp, C.c_int, c_vp, c_vp]),
     "ecc_set_object_radius": (C.c_int, [c_ctx, C.c_double]),
     "ecc_get_object_radius": (C.c_int, [c_ctx, C.POINTER(C.c_double)]),
     "ecc_set_epipolar_plane_step": (C.c_int, [c_ctx, C.c_double]),

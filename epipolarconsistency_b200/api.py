@@ -43,7 +43,10 @@ def _ptr(x):
 class Context:
     """One GPU + one stream (ecc_context).  Thin, explicit wrapper of the C ABI."""
 
-    def __init__(self, device=-1, stream=None):
+    def __init__(self, device=-1, stream="torch"):
+        """stream: "torch" (default) issues all work on torch's current CUDA stream of the device, so that
+        tensors produced or consumed by torch ops are ordered with the library's kernels; None keeps the
+        context's own non-blocking stream; or pass a torch.cuda.Stream / raw cudaStream_t."""
         self.lib = _lib.load()
         h = _lib.c_ctx()
         rc = self.lib.ecc_create(int(device), C.byref(h))
@@ -51,7 +54,10 @@ class Context:
             raise EccError(f"ecc_create(device={device}) failed with {rc}: no usable CUDA device? "
                            "(this library has no CPU fallback)")
         self.h = h
-        if stream is not None:
+        if isinstance(stream, str) and stream == "torch":
+            import torch
+            self.set_stream(torch.cuda.current_stream(device if device >= 0 else None))
+        elif stream is not None:
             self.set_stream(stream)
 
     def close(self):
@@ -73,6 +79,8 @@ class Context:
     def set_stream(self, stream):
         """stream: torch.cuda.Stream, raw cudaStream_t int, or None for the context's own."""
         raw = None if stream is None else int(getattr(stream, "cuda_stream", stream))
+        if raw == 0:
+            raw = 1  # cudaStreamLegacy: torch's default stream, spelled so that it is not "NULL = own stream"
         self._check(self.lib.ecc_set_stream(self.h, raw))
 
     def synchronize(self):
@@ -116,6 +124,12 @@ class Context:
     def update_projection_matrix(self, index, P):
         P = np.ascontiguousarray(P, np.float64).reshape(12)
         self._check(self.lib.ecc_update_projection_matrix(self.h, int(index), _ptr(P)))
+
+    def get_derived_views(self, n_views):
+        A = np.zeros((n_views, 12), np.float32)
+        Cs = np.zeros((n_views, 4), np.float32)
+        self._check(self.lib.ecc_get_derived_views(self.h, _ptr(A), _ptr(Cs)))
+        return A, Cs
 
     def set_object_radius(self, r):
         self._check(self.lib.ecc_set_object_radius(self.h, float(r)))
@@ -196,6 +210,15 @@ def make_circular_trajectory(n_proj, sid, sdd, n_u, n_v, max_angle_deg, pixel_sp
     Ps = np.zeros((n_proj, 12), np.float64)
     _lib.load().ecc_make_circular_trajectory(n_proj, sid, sdd, n_u, n_v, max_angle_deg, pixel_spacing, _ptr(Ps))
     return Ps
+
+
+def derive_views_host(Ps):
+    """(P^+)^T and source positions as the metric uses them (fp32), computed on the host."""
+    Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
+    A = np.zeros((Ps.shape[0], 12), np.float32)
+    Cs = np.zeros((Ps.shape[0], 4), np.float32)
+    _lib.load().ecc_derive_views_host(_ptr(Ps), Ps.shape[0], _ptr(A), _ptr(Cs))
+    return A, Cs
 
 
 _default_ctx = None

@@ -150,6 +150,7 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
     L.image_diagonal = ctx->n_t * ctx->step_t * 2.f;
     L.radius = (float)radius;
     L.dkappa = (float)ctx->dkappa;
+    L.radii_d = nullptr;
     const int max_samples = (L.dkappa <= 0.f) ? (int)L.image_diagonal : (int)(ECC_PI_F * 0.5f / L.dkappa);
     L.sample_cap = (max_samples + 255) / 256 * 256;
     L.is_derivative = ctx->is_derivative;
@@ -160,7 +161,7 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
 }
 
 int upload_and_derive(ecc_context* ctx, const double* Ps, size_t count, double** Ps_d, float** Cs_d,
-                      float** A_d, size_t* cap)
+                      float** A_d, size_t* cap, int views_per_set = 0, float* radii_d = nullptr)
 {
     if (*cap < count) {
         ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -174,7 +175,8 @@ int upload_and_derive(ecc_context* ctx, const double* Ps, size_t count, double**
         *cap = count;
     }
     ECC_CUDA(ctx, cudaMemcpyAsync(*Ps_d, Ps, sizeof(double) * 12 * count, cudaMemcpyDefault, ctx->stream));
-    return launch_derive_views(ctx, *Ps_d, (int)count, *A_d, *Cs_d);
+    return launch_derive_views(ctx, *Ps_d, (int)count, *A_d, *Cs_d, views_per_set, ctx->n_u, ctx->n_v,
+                               ctx->object_radius, radii_d);
 }
 
 // Batch-mode buffers live outside the context struct's main set so that the current matrices stay valid.
@@ -183,6 +185,8 @@ struct BatchBuffers {
     float* Cs_d = nullptr;
     float* A_d = nullptr;
     size_t cap = 0;
+    float* radii_d = nullptr;
+    size_t radii_cap = 0;
 };
 std::map<ecc_context*, BatchBuffers>& batch_buffers()
 {
@@ -227,7 +231,7 @@ void ecc_destroy(ecc_context* ctx)
     free_image_pool(ctx);
     auto it = batch_buffers().find(ctx);
     if (it != batch_buffers().end()) {
-        cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d);
+        cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d); cudaFree(it->second.radii_d);
         batch_buffers().erase(it);
     }
     void* bufs[] = {ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, ctx->vals_d,
@@ -411,6 +415,27 @@ int ecc_update_projection_matrix(ecc_context* ctx, int index, const double* P)
                                ctx->Cs_d + (size_t)4 * index);
 }
 
+int ecc_get_derived_views(ecc_context* ctx, float* PinvTs, float* Cs)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (ctx->n_views == 0) return ECC_OK;
+    if (PinvTs) ECC_CUDA(ctx, cudaMemcpyAsync(PinvTs, ctx->PinvTs_d, sizeof(float) * 12 * ctx->n_views, cudaMemcpyDeviceToHost, ctx->stream));
+    if (Cs) ECC_CUDA(ctx, cudaMemcpyAsync(Cs, ctx->Cs_d, sizeof(float) * 4 * ctx->n_views, cudaMemcpyDeviceToHost, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ECC_OK;
+}
+
+void ecc_derive_views_host(const double* Ps, int n, float* PinvTs, float* Cs)
+{
+    for (int v = 0; v < n; v++) {
+        float A[12], C[4];
+        derive_view(Ps + (size_t)12 * v, A, C);
+        if (PinvTs) std::memcpy(PinvTs + (size_t)12 * v, A, sizeof(A));
+        if (Cs) std::memcpy(Cs + (size_t)4 * v, C, sizeof(C));
+    }
+}
+
 int ecc_set_object_radius(ecc_context* ctx, double r)
 {
     if (!ctx) return ECC_ERR_INVALID;
@@ -429,35 +454,8 @@ int ecc_get_object_radius(ecc_context* ctx, double* radius)
         *radius = 0;
         return ECC_OK;
     }
-    // estimateObjectRadius on the first matrix: focal lengths from the rows of the left 3x3 block,
-    // field of view from the image size, times the source's distance to the origin.
-    const double* P = ctx->Ps_h.data();
-    const double m1[3] = {P[0], P[3], P[6]}, m2[3] = {P[1], P[4], P[7]}, m3[3] = {P[2], P[5], P[8]};
-    auto cross = [](const double* a, const double* b, double* c) {
-        c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
-    };
-    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
-    double U[3], V[3], t[3];
-    cross(m3, m2, U);
-    cross(m3, m1, V);
-    const double nU = std::sqrt(dot(U, U)), nV = std::sqrt(dot(V, V));
-    for (int k = 0; k < 3; k++) { U[k] /= nU; V[k] /= nV; }
-    cross(V, m3, t);
-    const double fu = dot(m1, t);
-    cross(U, m3, t);
-    const double fv = dot(m2, t);
-    const double fov = std::fmax(std::fabs(std::atan(0.5 * ctx->n_u / fu)), std::fabs(std::atan(0.5 * ctx->n_v / fv)));
-    double m[4];
-    for (int k = 0; k < 4; k++) {
-        int c[3], q = 0;
-        for (int j = 0; j < 4; j++)
-            if (j != k) c[q++] = j;
-        m[k] = det3d(P[0 + 3 * c[0]], P[0 + 3 * c[1]], P[0 + 3 * c[2]], P[1 + 3 * c[0]], P[1 + 3 * c[1]],
-                     P[1 + 3 * c[2]], P[2 + 3 * c[0]], P[2 + 3 * c[1]], P[2 + 3 * c[2]]);
-        if (k & 1) m[k] = -m[k];
-    }
-    const double C[3] = {m[0] / m[3], m[1] / m[3], m[2] / m[3]};
-    *radius = std::sin(fov) * std::sqrt(dot(C, C));
+    // estimateObjectRadius on the first matrix (EpipolarConsistency.cpp:35-47)
+    *radius = object_radius_from_view(ctx->Ps_h.data(), ctx->n_u, ctx->n_v);
     return ECC_OK;
 }
 
@@ -636,7 +634,16 @@ int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, cons
         L.n_pairs = n * (n - 1) / 2;
     }
     BatchBuffers& B = batch_buffers()[ctx];
-    if ((rc = upload_and_derive(ctx, Ps_sets, (size_t)n_sets * n, &B.Ps_d, &B.Cs_d, &B.A_d, &B.cap))) return rc;
+    // every set gets the object radius the reference would derive from that set's first matrix
+    if (B.radii_cap < (size_t)n_sets) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (B.radii_d) cudaFree(B.radii_d);
+        B.radii_d = nullptr;
+        ECC_CUDA(ctx, cudaMalloc(&B.radii_d, sizeof(float) * n_sets));
+        B.radii_cap = n_sets;
+    }
+    if ((rc = upload_and_derive(ctx, Ps_sets, (size_t)n_sets * n, &B.Ps_d, &B.Cs_d, &B.A_d, &B.cap, (int)n, B.radii_d))) return rc;
+    L.radii_d = B.radii_d;
     L.Cs_d = B.Cs_d;
     L.PinvTs_d = B.A_d;
     L.n_sets = n_sets;

@@ -136,45 +136,169 @@ __host__ __device__ inline double det3d(double a, double b, double c, double d, 
     return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
 }
 
+// ---- pseudo-inverse transpose and source position, bit-faithful to the reference ------------------------
+// The reference derives both on the host in fp64 with a Householder QR (culaut::xsqqr / xgeinv,
+// LibUtilsCuda/culaut/xgeinv.hxx:40-168, used by xprojectionmatrix.hxx:20-52,93-105) and rounds to fp32.  The
+// metric is a sum of squared interpolation residuals, so a one-ulp change of these floats can move a pair value
+// at the 1e-3 level (DESIGN.md "conditioning"); we therefore reproduce the same sequence of IEEE operations.
+// R2 keeps every product and sum separately rounded (no fused multiply-add), on the device via the _rn intrinsics,
+// so host and device give the same bits as the reference's host code.
+struct R2 {
+    __host__ __device__ static inline double mul(double a, double b)
+    {
+#ifdef __CUDA_ARCH__
+        return __dmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
+    __host__ __device__ static inline double add(double a, double b)
+    {
+#ifdef __CUDA_ARCH__
+        return __dadd_rn(a, b);
+#else
+        return a + b;
+#endif
+    }
+    __host__ __device__ static inline double sub(double a, double b) { return add(a, -b); }
+    __host__ __device__ static inline double div(double a, double b)
+    {
+#ifdef __CUDA_ARCH__
+        return __ddiv_rn(a, b);
+#else
+        return a / b;
+#endif
+    }
+    __host__ __device__ static inline double root(double a)
+    {
+#ifdef __CUDA_ARCH__
+        return __dsqrt_rn(a);
+#else
+        return sqrt(a);
+#endif
+    }
+};
+
+// Householder QR of a column-major N x N matrix, A = Q R.  On return the strict upper triangle of A holds R's,
+// diag holds R's diagonal, and Q is explicit.  Quirk kept from the reference: the column scale is a running
+// maximum over all columns processed so far, and the last column is processed too.
+template <int N>
+__host__ __device__ inline void householder_qr(double* A, double* Q, double* diag)
+{
+    double coef[N];
+    double scale = 0.0;
+    for (int k = 0; k < N; k++) {
+        double* col = A + N * k;
+        for (int i = k; i < N; i++) {
+            const double m = fabs(col[i]);
+            if (scale < m) scale = m;
+        }
+        if (scale == 0.0) {
+            coef[k] = diag[k] = 0.0;
+            continue;
+        }
+        for (int i = k; i < N; i++) col[i] = R2::div(col[i], scale);
+        double nrm = 0.0;
+        for (int i = k; i < N; i++) nrm = R2::add(nrm, R2::mul(col[i], col[i]));
+        const double sigma = col[k] > 0.0 ? R2::root(nrm) : -R2::root(nrm);
+        col[k] = R2::add(col[k], sigma);
+        coef[k] = R2::mul(sigma, col[k]);
+        diag[k] = R2::mul(-scale, sigma);
+        for (int j = k + 1; j < N; j++) {
+            double* other = A + N * j;
+            double dot = 0.0;
+            for (int i = k; i < N; i++) dot = R2::add(dot, R2::mul(col[i], other[i]));
+            const double tau = R2::div(dot, coef[k]);
+            for (int i = k; i < N; i++) other[i] = R2::sub(other[i], R2::mul(tau, col[i]));
+        }
+    }
+    diag[N - 1] = -diag[N - 1];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) Q[i + N * j] = (i == j) ? 1.0 : 0.0;
+    for (int k = 0; k < N - 1; k++) {
+        if (coef[k] == 0.0) continue;
+        const double* col = A + N * k;
+        for (int j = 0; j < N; j++) {
+            double dot = 0.0;
+            for (int i = k; i < N; i++) dot = R2::add(dot, R2::mul(col[i], Q[j + N * i]));
+            dot = R2::div(dot, coef[k]);
+            for (int i = k; i < N; i++) Q[j + N * i] = R2::sub(Q[j + N * i], R2::mul(dot, col[i]));
+        }
+    }
+}
+
 // A = (P P^T)^-1 P as 3x4 col-major floats; C = null vector of P with C[3]==1.
 __host__ __device__ inline void derive_view(const double* P, float* A, float* C)
 {
+    // Gram matrix P P^T (symmetric 3x3); each entry is a left-to-right sum over the four columns
     double G[9];
     for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) {
-            double s = 0;
-            for (int k = 0; k < 4; k++) s += P[r + 3 * k] * P[c + 3 * k];
-            G[r + 3 * c] = s;
+        for (int c = r; c < 3; c++) {
+            double s = R2::mul(P[r], P[c]);
+            for (int k = 1; k < 4; k++) s = R2::add(s, R2::mul(P[r + 3 * k], P[c + 3 * k]));
+            G[c + 3 * r] = G[r + 3 * c] = s;
         }
-    const double det = det3d(G[0], G[3], G[6], G[1], G[4], G[7], G[2], G[5], G[8]);
-    const double id = 1.0 / det;
-    double Gi[9];
-    Gi[0] = (G[4] * G[8] - G[7] * G[5]) * id;
-    Gi[3] = -(G[3] * G[8] - G[6] * G[5]) * id;
-    Gi[6] = (G[3] * G[7] - G[6] * G[4]) * id;
-    Gi[1] = -(G[1] * G[8] - G[7] * G[2]) * id;
-    Gi[4] = (G[0] * G[8] - G[6] * G[2]) * id;
-    Gi[7] = -(G[0] * G[7] - G[6] * G[1]) * id;
-    Gi[2] = (G[1] * G[5] - G[4] * G[2]) * id;
-    Gi[5] = -(G[0] * G[5] - G[3] * G[2]) * id;
-    Gi[8] = (G[0] * G[4] - G[3] * G[1]) * id;
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 4; c++) {
-            double s = 0;
-            for (int k = 0; k < 3; k++) s += Gi[r + 3 * k] * P[k + 3 * c];
-            A[r + 3 * c] = (float)s;
+    // inverse through QR: solve R x = Q^T e_i by back substitution, one unit vector at a time
+    double Qm[9], dg[3], Gi[9];
+    householder_qr<3>(G, Qm, dg);
+    for (int i = 0; i < 3; i++) {
+        double rhs[3], x[3];
+        for (int j = 0; j < 3; j++) {
+            double s = 0.0;
+            for (int q = 0; q < 3; q++) s = R2::add(s, R2::mul(q == i ? 1.0 : 0.0, Qm[q + 3 * j]));
+            rhs[j] = s;
         }
+        x[2] = R2::div(rhs[2], dg[2]);
+        for (int r = 1; r >= 0; r--) {
+            double v = rhs[r];
+            for (int j = r + 1; j < 3; j++) v = R2::sub(v, R2::mul(G[r + 3 * j], x[j]));
+            x[r] = R2::div(v, dg[r]);
+        }
+        for (int r = 0; r < 3; r++) Gi[r + 3 * i] = x[r];
+    }
+    // PinvT(r,c) = sum_k P(k,c) * Gi(k,r)
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 3; r++) {
+            const double* p = P + 3 * c;
+            const double* g = Gi + 3 * r;
+            A[r + 3 * c] = (float)R2::add(R2::add(R2::mul(p[0], g[0]), R2::mul(p[1], g[1])), R2::mul(p[2], g[2]));
+        }
+    // source position: last column of Q in the QR decomposition of [P^T | 0] (4x4), de-homogenised
+    double M4[16], Q4[16], d4[4];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 4; j++) M4[j + 4 * i] = P[i + 3 * j];
+    for (int j = 0; j < 4; j++) M4[j + 12] = 0.0;
+    householder_qr<4>(M4, Q4, d4);
+    for (int i = 0; i < 4; i++) C[i] = (float)R2::div(Q4[i + 12], Q4[15]);
+}
+
+// Automatic object radius from one projection matrix (what Metric::getObjectRadius derives from the first
+// matrix of the set): focal lengths from the rows of the left 3x3 block, the larger half field of view of the
+// n_u x n_v detector, times the source's distance to the origin.
+__host__ __device__ inline double object_radius_from_view(const double* P, int n_u, int n_v)
+{
+    const double m1[3] = {P[0], P[3], P[6]}, m2[3] = {P[1], P[4], P[7]}, m3[3] = {P[2], P[5], P[8]};
+    double U[3] = {m3[1] * m2[2] - m3[2] * m2[1], m3[2] * m2[0] - m3[0] * m2[2], m3[0] * m2[1] - m3[1] * m2[0]};
+    double V[3] = {m3[1] * m1[2] - m3[2] * m1[1], m3[2] * m1[0] - m3[0] * m1[2], m3[0] * m1[1] - m3[1] * m1[0]};
+    const double nU = sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
+    const double nV = sqrt(V[0] * V[0] + V[1] * V[1] + V[2] * V[2]);
+    for (int k = 0; k < 3; k++) { U[k] /= nU; V[k] /= nV; }
+    const double t1[3] = {V[1] * m3[2] - V[2] * m3[1], V[2] * m3[0] - V[0] * m3[2], V[0] * m3[1] - V[1] * m3[0]};
+    const double t2[3] = {U[1] * m3[2] - U[2] * m3[1], U[2] * m3[0] - U[0] * m3[2], U[0] * m3[1] - U[1] * m3[0]};
+    const double fu = m1[0] * t1[0] + m1[1] * t1[1] + m1[2] * t1[2];
+    const double fv = m2[0] * t2[0] + m2[1] * t2[1] + m2[2] * t2[2];
+    const double fov = fmax(fabs(atan(0.5 * n_u / fu)), fabs(atan(0.5 * n_v / fv)));
     double m[4];
     for (int k = 0; k < 4; k++) {
         int c[3], q = 0;
         for (int j = 0; j < 4; j++)
             if (j != k) c[q++] = j;
-        m[k] = det3d(P[0 + 3 * c[0]], P[0 + 3 * c[1]], P[0 + 3 * c[2]], P[1 + 3 * c[0]],
-                     P[1 + 3 * c[1]], P[1 + 3 * c[2]], P[2 + 3 * c[0]], P[2 + 3 * c[1]],
-                     P[2 + 3 * c[2]]);
+        m[k] = det3d(P[0 + 3 * c[0]], P[0 + 3 * c[1]], P[0 + 3 * c[2]], P[1 + 3 * c[0]], P[1 + 3 * c[1]],
+                     P[1 + 3 * c[2]], P[2 + 3 * c[0]], P[2 + 3 * c[1]], P[2 + 3 * c[2]]);
         if (k & 1) m[k] = -m[k];
     }
-    for (int k = 0; k < 4; k++) C[k] = (float)(m[k] / m[3]);
+    const double C0 = m[0] / m[3], C1 = m[1] / m[3], C2 = m[2] / m[3];
+    return sin(fov) * sqrt(C0 * C0 + C1 * C1 + C2 * C2);
 }
 
 }  // namespace eccb200

@@ -125,6 +125,7 @@ struct PairLaunch {
     int n_dtrs, n_alpha, n_t;
     float half_nu, half_nv, range_t, image_diagonal;
     float radius, dkappa;
+    const float* radii_d;  // batched mode: one object radius per matrix set (device) or null
     int sample_cap;
     int is_derivative;
     int interp;
@@ -136,7 +137,11 @@ int launch_pairs(ecc_context* ctx, const PairLaunch& L);
 int launch_pair_counts(ecc_context* ctx, const PairLaunch& L, int* counts_d);
 int launch_sum_sets(ecc_context* ctx, const float* vals_d, long long n_pairs, int n_sets,
                     double* sums_d);
-int launch_derive_views(ecc_context* ctx, const double* Ps_d, int n, float* PinvTs_d, float* Cs_d);
+// radii_d (nullable): entry s receives the automatic object radius of set s (views_per_set matrices per set),
+// or fixed_radius when that is > 0.
+int launch_derive_views(ecc_context* ctx, const double* Ps_d, int n, float* PinvTs_d, float* Cs_d,
+                        int views_per_set = 0, int n_u = 0, int n_v = 0, double fixed_radius = 0.0,
+                        float* radii_d = nullptr);
 
 // ---- launchers (ecc_radon.cu) ----
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,

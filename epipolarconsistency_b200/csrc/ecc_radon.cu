@@ -10,6 +10,8 @@
 // image side by side (coherent texture footprints, no divergence), and the 8 warps of a CTA are
 // 8 neighbouring angles over the same strip of the image (L1 reuse).  Sample positions follow the
 // reference exactly (clipped entry point, t += 0.66f accumulation, +-1/2 px derivative lines).
+#include <cstdlib>
+
 #include "ecc_geometry.cuh"
 #include "ecc_internal.h"
 
@@ -88,13 +90,26 @@ __device__ __forceinline__ float sample_img(cudaTextureObject_t tex, float x, fl
     return sample_exact(tex, x, y);
 }
 
+// Bin tiling of a CTA.  Lanes: a quad of four consecutive lanes covers qa x 4/qa (angle x t) bins, the eight
+// quads of a warp are arranged ga along the angle axis x 8/ga along t, so a warp covers
+// la = qa*ga angles x lt = 32/la t bins.  The warps of the CTA (blockDim.y) are arranged wa along the angle axis
+// x blockDim.y/wa along t.  Examples: qa=1,ga=1: 32 parallel lines 2 px apart; qa=4,ga=8: a fan of 32 lines
+// through one t (the reference's arrangement); qa=2,ga=1: quads of 2 angles x 2 t, 16 t bins per warp.
+struct Tiling {
+    int qa, ga, wa;
+};
+
 template <bool DERIV, int INTERP>
-__global__ void __launch_bounds__(kLanesT* kAngles)
+__global__ void __launch_bounds__(256)
 radon_kernel(const cudaTextureObject_t* __restrict__ images, int n_u_i, int n_v_i, int n_alpha,
-             int n_t, int post, float* __restrict__ out)
+             int n_t, int post, Tiling tl, float* __restrict__ out)
 {
-    const int iy = blockIdx.x * kLanesT + threadIdx.x;  // t bin: lanes
-    const int ix = blockIdx.y * kAngles + threadIdx.y;  // angle bin: warps
+    const int la = tl.qa * tl.ga, lt = 32 / la, qt = 4 / tl.qa, wt = blockDim.y / tl.wa;
+    const int lane = threadIdx.x, warp = threadIdx.y, quad = lane >> 2, ql = lane & 3;
+    const int da = (quad % tl.ga) * tl.qa + ql % tl.qa;  // angle offset inside the warp tile
+    const int dt = (quad / tl.ga) * qt + ql / tl.qa;     // t offset inside the warp tile
+    const int ix = (blockIdx.x * tl.wa + warp % tl.wa) * la + da;  // angle bin
+    const int iy = (blockIdx.y * wt + warp / tl.wa) * lt + dt;     // t bin
     if (ix >= n_alpha || iy >= n_t) return;
     const cudaTextureObject_t tex = images[blockIdx.z];
     float* dst = out + (size_t)blockIdx.z * n_t * n_alpha + (size_t)iy * n_alpha + ix;
@@ -122,6 +137,44 @@ radon_kernel(const cudaTextureObject_t* __restrict__ images, int n_u_i, int n_v_
         sumo += sample_img<INTERP>(tex, o0 + t * d0 + d1, o1 + t * d1 - d0);
     }
     *dst = post_process((sum - sumo) * kStep, post);
+}
+
+// Derivative filter with the two lines of a bin on neighbouring lanes: a warp is 16 adjacent t bins x 2 lines,
+// i.e. 32 parallel lines about one pixel apart.
+template <int INTERP>
+__global__ void __launch_bounds__(256)
+radon_kernel_split(const cudaTextureObject_t* __restrict__ images, int n_u_i, int n_v_i, int n_alpha,
+                   int n_t, int post, float* __restrict__ out)
+{
+    const int lane_global = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iy = lane_global >> 1;                              // t bin
+    const int which = lane_global & 1;                            // 0: line at +1/2, 1: the line one pixel further
+    const int ix = blockIdx.y * blockDim.y + threadIdx.y;         // angle bin
+    if (ix >= n_alpha) return;
+    const bool in_range = iy < n_t;
+    const cudaTextureObject_t tex = images[blockIdx.z];
+    float sum = 0.f;
+    bool valid = false;
+    if (in_range) {
+        BinLine L = bin_line(ix, iy, n_alpha, n_t, (float)n_u_i, (float)n_v_i);
+        valid = L.valid;
+        if (valid) {
+            float o0 = L.o0 + 0.5f, o1 = L.o1 + 0.5f;
+            const float d0 = L.d0, d1 = L.d1, t_max = L.t_max;
+            o0 -= 0.5f * d1;
+            o1 += 0.5f * d0;
+            if (which == 0) {
+                for (float t = L.t; t <= t_max; t += kStep) sum += sample_img<INTERP>(tex, o0 + t * d0, o1 + t * d1);
+            } else {
+                for (float t = L.t; t <= t_max; t += kStep) sum += sample_img<INTERP>(tex, o0 + t * d0 + d1, o1 + t * d1 - d0);
+            }
+        }
+    }
+    const float other = __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (in_range && which == 0) {
+        float* dst = out + (size_t)blockIdx.z * n_t * n_alpha + (size_t)iy * n_alpha + ix;
+        *dst = valid ? post_process((sum - other) * kStep, post) : 0.f;
+    }
 }
 
 int ensure_pool(ecc_context* ctx, int n_u, int n_v, int count)
@@ -185,16 +238,32 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
                                                    sizeof(float) * n_u, sizeof(float) * n_u, n_v,
                                                    cudaMemcpyDeviceToDevice, ctx->stream));
         }
-        dim3 block(kLanesT, kAngles);
-        dim3 grid((n_t + kLanesT - 1) / kLanesT, (n_alpha + kAngles - 1) / kAngles, n);
+        // development knobs (environment): ECC_RADON_QA/GA lane tiling (QA=0: split-line kernel), ECC_RADON_WA warps
+        // along alpha, ECC_RADON_BY warps per CTA
+        static const int qa = getenv("ECC_RADON_QA") ? atoi(getenv("ECC_RADON_QA")) : 2;
+        static const int ga = getenv("ECC_RADON_GA") ? atoi(getenv("ECC_RADON_GA")) : 1;
+        static const int by = getenv("ECC_RADON_BY") ? atoi(getenv("ECC_RADON_BY")) : 8;
+        static const int wa_env = getenv("ECC_RADON_WA") ? atoi(getenv("ECC_RADON_WA")) : 4;
+        const int la = qa;
+        dim3 block(kLanesT, by);
         float* dst = out_d + (size_t)first * n_t * n_alpha;
+        const cudaTextureObject_t* texs = ctx->pool.tex_d;
         const int slot = prof_begin(ctx, FAM_RADON);
-        if (interp == ECC_INTERP_TEXTURE) {
-            if (deriv) radon_kernel<true, ECC_INTERP_TEXTURE><<<grid, block, 0, ctx->stream>>>(ctx->pool.tex_d, n_u, n_v, n_alpha, n_t, post, dst);
-            else radon_kernel<false, ECC_INTERP_TEXTURE><<<grid, block, 0, ctx->stream>>>(ctx->pool.tex_d, n_u, n_v, n_alpha, n_t, post, dst);
+        if (la == 0 && deriv) {
+            dim3 grid((2 * n_t + kLanesT - 1) / kLanesT, (n_alpha + by - 1) / by, n);
+            if (interp == ECC_INTERP_TEXTURE) radon_kernel_split<ECC_INTERP_TEXTURE><<<grid, block, 0, ctx->stream>>>(texs, n_u, n_v, n_alpha, n_t, post, dst);
+            else radon_kernel_split<ECC_INTERP_EXACT><<<grid, block, 0, ctx->stream>>>(texs, n_u, n_v, n_alpha, n_t, post, dst);
         } else {
-            if (deriv) radon_kernel<true, ECC_INTERP_EXACT><<<grid, block, 0, ctx->stream>>>(ctx->pool.tex_d, n_u, n_v, n_alpha, n_t, post, dst);
-            else radon_kernel<false, ECC_INTERP_EXACT><<<grid, block, 0, ctx->stream>>>(ctx->pool.tex_d, n_u, n_v, n_alpha, n_t, post, dst);
+            Tiling tl;
+            tl.qa = qa > 0 ? qa : 4;
+            tl.ga = ga;
+            tl.wa = wa_env;
+            const int tile_a = tl.qa * tl.ga * tl.wa, tile_t = (32 / (tl.qa * tl.ga)) * (by / tl.wa);
+            dim3 grid((n_alpha + tile_a - 1) / tile_a, (n_t + tile_t - 1) / tile_t, n);
+#define ECC_LAUNCH(K) K<<<grid, block, 0, ctx->stream>>>(texs, n_u, n_v, n_alpha, n_t, post, tl, dst)
+            if (interp == ECC_INTERP_TEXTURE) { if (deriv) ECC_LAUNCH((radon_kernel<true, ECC_INTERP_TEXTURE>)); else ECC_LAUNCH((radon_kernel<false, ECC_INTERP_TEXTURE>)); }
+            else { if (deriv) ECC_LAUNCH((radon_kernel<true, ECC_INTERP_EXACT>)); else ECC_LAUNCH((radon_kernel<false, ECC_INTERP_EXACT>)); }
+#undef ECC_LAUNCH
         }
         prof_end(ctx, slot);
         ECC_CUDA(ctx, cudaGetLastError());

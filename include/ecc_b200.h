@@ -102,6 +102,13 @@ int ecc_set_projection_matrices(ecc_context* ctx, const double* Ps, int n);
  * Gui/SingleImageMotion.h:84-90). */
 int ecc_update_projection_matrix(ecc_context* ctx, int index, const double* P);
 
+/* The fp32 pseudo-inverse transposes (n*12, 3x4 col-major) and source positions (n*4, C[3]==1) the metric
+ * works with, read back from the device (either pointer may be NULL). */
+int ecc_get_derived_views(ecc_context* ctx, float* PinvTs, float* Cs);
+/* The same derivation on the host (no GPU needed): bit-identical to the device path and to the reference's
+ * culaut routines (LibUtilsCuda/culaut/xprojectionmatrix.hxx:20-52,93-105). */
+void ecc_derive_views_host(const double* Ps, int n, float* PinvTs, float* Cs);
+
 /* Metric::setObjectRadius / getObjectRadius (EpipolarConsistency.cpp:70-84), 0 = automatic. */
 int ecc_set_object_radius(ecc_context* ctx, double radius_mm);
 int ecc_get_object_radius(ecc_context* ctx, double* radius_mm);

@@ -1,0 +1,244 @@
+// ref_cuda_harness.cu -- drives the REFERENCE's own CUDA launchers (compiled unchanged from
+// /root/reference/code/LibEpipolarConsistency/{RadonIntermediate,EpipolarConsistencyRadonIntermediate}.cu
+// by oracle/Makefile) so that tests and bench.py can run "the reference CUDA path" on the GPU box.
+// Ours: this harness only.  It re-creates, without Eigen/GetSet, the ~100 lines of host logic that sit
+// between the reference's class API and its two launchers:
+//   RadonIntermediate ctor + compute      RadonIntermediate.cpp:17-31,198-211
+//   BindlessTexture2D ctor                LibUtilsCuda/CudaBindlessTexture.cpp:17-44 (array, linear, clamp)
+//   setProjectionMatrices                 EpipolarConsistencyRadonIntermediate.cpp:134-163 (culaut, included verbatim)
+//   evaluate / evaluate(indices)          EpipolarConsistencyRadonIntermediate.cpp:166-225,267-322
+// Test infrastructure only; the product never links this.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+using std::abs;
+#include <LibUtilsCuda/culaut/xprojectionmatrix.hxx>
+
+// the reference's launchers (C++ linkage, defined in the reference .cu files)
+void computeDerivLineIntegrals(cudaTextureObject_t in, int n_x, int n_y, int n_alpha, int n_t, int filter,
+                               int post_process, float* out_d);
+void epipolarConsistency(int n_x, int n_y, int num_dtrs, char* dtrs_d, int n_alpha, int n_t, float step_alpha,
+                         float step_t, int num_Ps, float* Cs_d, float* PinvTs_d, int num_pairs, int* indices_d,
+                         float* K01s_d, float* out_d, float object_radius_mm, float dkappa, bool isDerivative,
+                         bool use_corr, float* out_corr_d);
+
+namespace {
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            fprintf(stderr, "ref harness CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return -1;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+struct ArrayTex {
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+};
+
+// Same settings as the reference's BindlessTexture2D(w,h,buffer,device,interpolate=true,normalized)
+int make_array_texture(const float* src_d, int w, int h, bool normalized, ArrayTex& out)
+{
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+    CK(cudaMallocArray(&out.arr, &desc, w, h));
+    CK(cudaMemcpy2DToArray(out.arr, 0, 0, src_d, sizeof(float) * w, sizeof(float) * w, h, cudaMemcpyDeviceToDevice));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = out.arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.normalizedCoords = normalized;
+    td.filterMode = cudaFilterModeLinear;
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.addressMode[1] = cudaAddressModeClamp;
+    td.readMode = cudaReadModeElementType;
+    CK(cudaCreateTextureObject(&out.tex, &res, &td, NULL));
+    return 0;
+}
+
+void free_array_texture(ArrayTex& t)
+{
+    if (t.tex) cudaDestroyTextureObject(t.tex);
+    if (t.arr) cudaFreeArray(t.arr);
+    t = ArrayTex();
+}
+
+struct RefMetric {
+    int n_views = 0, n_dtrs = 0, n_alpha = 0, n_t = 0, n_u = 0, n_v = 0;
+    float step_alpha = 0, step_t = 0;
+    bool is_derivative = true;
+    std::vector<ArrayTex> dtrs;
+    cudaTextureObject_t* tex_d = nullptr;
+    float *Cs_d = nullptr, *PinvTs_d = nullptr, *K01s_d = nullptr, *out_d = nullptr, *corr_d = nullptr;
+    int* idx_d = nullptr;
+    size_t k01_cap = 0, out_cap = 0, corr_cap = 0, idx_cap = 0;
+};
+
+}  // namespace
+
+extern "C" {
+
+// Radon intermediates of n images with the reference kernel.  Host pointers.  ms (nullable): GPU time of
+// the launcher calls only (texture set-up excluded), via CUDA events.
+int ref_cuda_radon(const float* images_h, int n_images, int n_u, int n_v, int n_alpha, int n_t, int filter,
+                   int post, float* dtrs_h, float* ms)
+{
+    const size_t img = (size_t)n_u * n_v, dtr = (size_t)n_alpha * n_t;
+    float *img_d = nullptr, *out_d = nullptr;
+    CK(cudaMalloc(&img_d, sizeof(float) * img));
+    CK(cudaMalloc(&out_d, sizeof(float) * dtr));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float total = 0.f;
+    for (int k = 0; k < n_images; k++) {
+        CK(cudaMemcpy(img_d, images_h + img * k, sizeof(float) * img, cudaMemcpyHostToDevice));
+        ArrayTex t;
+        if (make_array_texture(img_d, n_u, n_v, false, t)) return -1;
+        CK(cudaEventRecord(e0));
+        computeDerivLineIntegrals(t.tex, n_u, n_v, n_alpha, n_t, filter, post, out_d);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, e0, e1));
+        total += m;
+        CK(cudaMemcpy(dtrs_h + dtr * k, out_d, sizeof(float) * dtr, cudaMemcpyDeviceToHost));
+        free_array_texture(t);
+    }
+    if (ms) *ms = total;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(img_d);
+    cudaFree(out_d);
+    return 0;
+}
+
+// Metric object: dtrs become array textures exactly like RadonIntermediate::getTexture() (normalised).
+void* ref_cuda_metric_create(const float* dtrs_h, int n_dtrs, int n_alpha, int n_t, float step_alpha, float step_t,
+                             int n_u, int n_v, int is_derivative)
+{
+    RefMetric* M = new RefMetric();
+    M->n_dtrs = n_dtrs; M->n_alpha = n_alpha; M->n_t = n_t; M->n_u = n_u; M->n_v = n_v;
+    M->step_alpha = step_alpha; M->step_t = step_t; M->is_derivative = is_derivative != 0;
+    const size_t dtr = (size_t)n_alpha * n_t;
+    float* tmp_d = nullptr;
+    if (cudaMalloc(&tmp_d, sizeof(float) * dtr) != cudaSuccess) return nullptr;
+    std::vector<cudaTextureObject_t> handles(n_dtrs);
+    M->dtrs.resize(n_dtrs);
+    for (int k = 0; k < n_dtrs; k++) {
+        cudaMemcpy(tmp_d, dtrs_h + dtr * k, sizeof(float) * dtr, cudaMemcpyHostToDevice);
+        if (make_array_texture(tmp_d, n_alpha, n_t, true, M->dtrs[k])) return nullptr;
+        handles[k] = M->dtrs[k].tex;
+    }
+    cudaFree(tmp_d);
+    cudaMalloc(&M->tex_d, sizeof(cudaTextureObject_t) * n_dtrs);
+    cudaMemcpy(M->tex_d, handles.data(), sizeof(cudaTextureObject_t) * n_dtrs, cudaMemcpyHostToDevice);
+    return M;
+}
+
+void ref_cuda_metric_destroy(void* h)
+{
+    RefMetric* M = (RefMetric*)h;
+    if (!M) return;
+    for (auto& t : M->dtrs) free_array_texture(t);
+    cudaFree(M->tex_d); cudaFree(M->Cs_d); cudaFree(M->PinvTs_d); cudaFree(M->K01s_d); cudaFree(M->out_d);
+    cudaFree(M->corr_d); cudaFree(M->idx_d);
+    delete M;
+}
+
+// setProjectionMatrices with the reference's culaut routines (double -> float), then upload.
+int ref_cuda_metric_set_matrices(void* h, const double* Ps, int n)
+{
+    RefMetric* M = (RefMetric*)h;
+    std::vector<float> A((size_t)12 * n), Cs((size_t)4 * n);
+    for (int i = 0; i < n; i++) {
+        culaut::projection_matrix_pseudoinverse_transpose<double, float>(Ps + 12 * i, &A[12 * i]);
+        culaut::projection_matrix_source_position<double, float>(Ps + 12 * i, &Cs[4 * i]);
+    }
+    if (n != M->n_views) {
+        cudaFree(M->Cs_d); cudaFree(M->PinvTs_d);
+        CK(cudaMalloc(&M->Cs_d, sizeof(float) * 4 * n));
+        CK(cudaMalloc(&M->PinvTs_d, sizeof(float) * 12 * n));
+        M->n_views = n;
+    }
+    CK(cudaMemcpy(M->PinvTs_d, A.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(M->Cs_d, Cs.data(), sizeof(float) * 4 * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int grow(float** p, size_t* cap, size_t n)
+{
+    if (*cap >= n) return 0;
+    cudaFree(*p);
+    CK(cudaMalloc(p, sizeof(float) * n));
+    *cap = n;
+    return 0;
+}
+
+// evaluate(): all pairs (idx4 == NULL; out_h = n*n cost image, pre-zeroed by the caller if wanted) or a
+// pair list (out_h = n_pairs).  `out` is zeroed on the device before the launch: the reference zeroes it
+// inside the accumulating kernel, which races -- the in-kernel store then writes
+// zero over zero or over a partial sum; see tests for how the comparison copes.  Returns the mean.
+// ms (nullable): GPU time of the launcher call (both kernels + its two device syncs).
+double ref_cuda_metric_evaluate(void* h, const int* idx4, int n_pairs, float radius, float dkappa, float* out_h,
+                                float* ms)
+{
+    RefMetric* M = (RefMetric*)h;
+    const int n = M->n_views;
+    const bool all = (idx4 == nullptr);
+    const int pairs = all ? n * (n - 1) / 2 : n_pairs;
+    const size_t out_len = all ? (size_t)n * n : (size_t)pairs;
+    if (grow(&M->K01s_d, &M->k01_cap, (size_t)pairs * 16)) return -1;
+    if (grow(&M->out_d, &M->out_cap, out_len)) return -1;
+    if (grow(&M->corr_d, &M->corr_cap, (size_t)pairs)) return -1;
+    cudaMemset(M->out_d, 0, sizeof(float) * out_len);
+    cudaMemset(M->corr_d, 0, sizeof(float) * pairs);
+    if (!all) {
+        if (M->idx_cap < (size_t)pairs * 4) {
+            cudaFree(M->idx_d);
+            cudaMalloc(&M->idx_d, sizeof(int) * 4 * pairs);
+            M->idx_cap = (size_t)pairs * 4;
+        }
+        cudaMemcpy(M->idx_d, idx4, sizeof(int) * 4 * pairs, cudaMemcpyHostToDevice);
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    epipolarConsistency(M->n_u, M->n_v, M->n_dtrs, (char*)M->tex_d, M->n_alpha, M->n_t, M->step_alpha, M->step_t, n,
+                        M->Cs_d, M->PinvTs_d, all ? 0 : pairs, all ? nullptr : M->idx_d, M->K01s_d, M->out_d, radius,
+                        dkappa, M->is_derivative, false, M->corr_d);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float m = 0.f;
+    cudaEventElapsedTime(&m, e0, e1);
+    if (ms) *ms = m;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    std::vector<float> out(out_len);
+    cudaMemcpy(out.data(), M->out_d, sizeof(float) * out_len, cudaMemcpyDeviceToHost);
+    double sum = 0;
+    if (all) {
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++) {
+                const float v = out[(size_t)i + (size_t)j * n];
+                sum += v;
+                if (out_h) out_h[(size_t)i + (size_t)j * n] = v;
+            }
+    } else {
+        for (int k = 0; k < pairs; k++) {
+            sum += out[k];
+            if (out_h) out_h[k] = out[k];
+        }
+    }
+    return pairs ? sum / pairs : 0.0;
+}
+
+}  // extern "C"

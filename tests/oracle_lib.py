@@ -180,3 +180,79 @@ def ref_host():
     L.ref_line_to_sample.restype = C.c_int
     _ref_host = L
     return L
+
+
+_ref_cuda = None
+
+
+def ref_cuda():
+    """The reference's own CUDA kernels (sm_100 build) behind oracle/ref_cuda_harness.cu; None if not built.
+    Needs a GPU to call."""
+    global _ref_cuda
+    if _ref_cuda is not None:
+        return _ref_cuda
+    path = os.path.join(ORACLE_DIR, "_ref", "libecc_ref_cuda.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_cuda_radon.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p,
+                                 C.POINTER(C.c_float)]
+    L.ref_cuda_metric_create.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.ref_cuda_metric_create.restype = C.c_void_p
+    L.ref_cuda_metric_destroy.argtypes = [C.c_void_p]
+    L.ref_cuda_metric_set_matrices.argtypes = [C.c_void_p, _f64p, C.c_int]
+    L.ref_cuda_metric_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                           C.POINTER(C.c_float)]
+    L.ref_cuda_metric_evaluate.restype = C.c_double
+    _ref_cuda = L
+    return L
+
+
+def ref_cuda_radon(images, n_alpha, n_t, filter=0, post=0):
+    """Radon intermediates by the reference CUDA kernel.  Returns (dtrs, gpu_ms)."""
+    L = ref_cuda()
+    images = np.ascontiguousarray(images, np.float32)
+    n, n_v, n_u = images.shape
+    out = np.zeros((n, n_t, n_alpha), np.float32)
+    ms = C.c_float()
+    rc = L.ref_cuda_radon(images, n, n_u, n_v, n_alpha, n_t, filter, post, out, C.byref(ms))
+    assert rc == 0
+    return out, ms.value
+
+
+class RefCudaMetric:
+    """The reference MetricRadonIntermediate's device path (its launcher + kernels)."""
+
+    def __init__(self, Ps, dtrs, n_u, n_v, is_derivative=True):
+        self.L = ref_cuda()
+        dtrs = np.ascontiguousarray(dtrs, np.float32)
+        m, n_t, n_alpha = dtrs.shape
+        diag = np.sqrt(float(n_u) ** 2 + float(n_v) ** 2)
+        self.h = self.L.ref_cuda_metric_create(dtrs, m, n_alpha, n_t, np.float32(np.pi / n_alpha),
+                                               np.float32(diag / n_t), n_u, n_v, int(is_derivative))
+        assert self.h
+        self.set_matrices(Ps)
+
+    def set_matrices(self, Ps):
+        Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
+        self.n = Ps.shape[0]
+        assert self.L.ref_cuda_metric_set_matrices(self.h, Ps, self.n) == 0
+
+    def evaluate(self, radius, dkappa=0.0, idx4=None):
+        """Returns (mean, out, gpu_ms); out is the n*n cost image or the per-pair list."""
+        ms = C.c_float()
+        if idx4 is None:
+            out = np.zeros((self.n, self.n), np.float32)
+            mean = self.L.ref_cuda_metric_evaluate(self.h, None, 0, radius, dkappa, out.ctypes.data_as(C.c_void_p),
+                                                   C.byref(ms))
+        else:
+            idx4 = np.ascontiguousarray(idx4, np.int32).reshape(-1, 4)
+            out = np.zeros(idx4.shape[0], np.float32)
+            mean = self.L.ref_cuda_metric_evaluate(self.h, idx4.ctypes.data_as(C.c_void_p), idx4.shape[0], radius,
+                                                   dkappa, out.ctypes.data_as(C.c_void_p), C.byref(ms))
+        return mean, out, ms.value
+
+    def close(self):
+        if self.h:
+            self.L.ref_cuda_metric_destroy(self.h)
+            self.h = None
