@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ECC hot path (BASELINE.json): full all-pairs ECC for 496 projections of
+1240x960 (config C3: Radon intermediates 768x768, dkappa 0.01 deg, 200 deg short scan, ~122k pairs).
+
+One STEP = one pass of the hot path over the synthetic data set:
+    Radon intermediates of all projections (sharded by projection) -> all-gather -> set matrices ->
+    all-pairs ECC (pairs partitioned by equal work) -> reduce -> mean on the host.
+`value`   whole-job pairs/s with the projection images already resident in HBM.
+`e2e`     the same through the public C ABI with HOST (pinned) image buffers: H2D of the images and D2H of the
+          n x n cost image + mean are inside the timed region.
+Usage:  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+        torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, NCCL)
+--impl reference times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on a bounded
+sample of the same workload; the reference ships no CPU implementation of this path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload (BASELINE.json configs[2]) -------------------------------------------
+WORKLOADS = {
+    "c3": dict(n=496, n_u=1240, n_v=960, n_alpha=768, n_t=768, sid=750.0, sdd=1200.0, px=0.308, arc=200.0,
+               dkappa_deg=0.01, name="C3: all-pairs ECC, 496 proj 1240x960 -> 768x768 dtr, dkappa 0.01 deg, 200 deg arc"),
+    "c1": dict(n=100, n_u=512, n_v=512, n_alpha=256, n_t=256, sid=750.0, sdd=1200.0, px=0.616, arc=360.0,
+               dkappa_deg=0.0, name="C1: all-pairs ECC, 100 proj 512x512 -> 256x256 dtr, dkappa auto, 360 deg"),
+    "tiny": dict(n=16, n_u=320, n_v=256, n_alpha=192, n_t=192, sid=750.0, sdd=1200.0, px=1.2, arc=200.0,
+                 dkappa_deg=0.05, name="tiny (debug)"),
+}
+# phantom: 5 ellipsoids, seed-1234 style fixed list (centre xyz, semi-axes xyz, density)
+ELLIPSOIDS = np.array([
+    [0.0, 0.0, 0.0, 80.0, 60.0, 70.0, 1.0],
+    [20.0, -10.0, 5.0, 25.0, 30.0, 20.0, 0.6],
+    [-25.0, 15.0, -10.0, 20.0, 22.0, 28.0, -0.5],
+    [5.0, 30.0, 20.0, 22.0, 20.0, 24.0, 0.8],
+    [-10.0, -30.0, -25.0, 30.0, 21.0, 20.0, -0.7],
+])
+MEASURED_PEAKS = os.path.join(ROOT, "MEASURED_PEAKS.json")
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    try:
+        with open(MEASURED_PEAKS) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+# ===========================================================================================================
+# own arm
+# ===========================================================================================================
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from epipolarconsistency_b200 import api
+    from epipolarconsistency_b200.distributed import ShardedPipeline, shard_bounds
+
+    W = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, n_u, n_v, n_a, n_t = W["n"], W["n_u"], W["n_v"], W["n_alpha"], W["n_t"]
+    ctx = api.Context(local_rank)  # bound to torch's current stream
+    Ps = api.make_circular_trajectory(n, W["sid"], W["sdd"], n_u, n_v, W["arc"], W["px"])
+    bounds = shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    # synthetic data: this rank's projections, generated on the device (resident), plus a pinned host copy for e2e
+    images = torch.empty((hi - lo, n_v, n_u), dtype=torch.float32, device=dev)
+    ctx.synth_projections(Ps[lo:hi], n_u, n_v, ELLIPSOIDS, images)
+    images_host = torch.empty((hi - lo, n_v, n_u), dtype=torch.float32, pin_memory=True)
+    images_host.copy_(images)
+    cost_dev = torch.zeros((n, n), dtype=torch.float32, device=dev)
+    cost_host = torch.zeros((n, n), dtype=torch.float32, pin_memory=True)
+    pipe = ShardedPipeline(ctx, rank, world, device=dev)
+    ctx.set_interpolation(api.INTERP_TEXTURE)
+    ctx.set_object_radius(0.0)
+    ctx.set_epipolar_plane_step(float(np.deg2rad(W["dkappa_deg"])))
+
+    def step(src_images, want_cost_on_host):
+        full = pipe.radon_allgather(src_images, n, n_a, n_t)
+        ctx.set_radon_intermediates(full, n_u, n_v, True)
+        ctx.set_projection_matrices(Ps)
+        cost_dev.zero_()
+        mean = pipe.evaluate_all_pairs(n, cost_dev)
+        if want_cost_on_host:
+            cost_host.copy_(cost_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return mean
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize, timed with CUDA events on the launching stream; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(max(args.warmup, 1)):
+        mean = step(images, False)
+    # ---- device-resident timing, with per-kernel event profile and clock sampling
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    ms_total, mean = timed(lambda: step(images, False), args.steps)
+    prof = {fam: ctx.profile_get(fam) for fam in ("radon", "pairs", "geometry", "reduce")}
+    ctx.profile_enable(False)
+    clocks = sampler.summary()
+    # ---- end to end through the C ABI with host buffers
+    for _ in range(1):
+        step(images_host, True)
+    ms_e2e, mean_e2e = timed(lambda: step(images_host, True), args.steps)
+
+    n_pairs = n * (n - 1) // 2
+    ms_step = ms_total / args.steps
+    ms_step_e2e = ms_e2e / args.steps
+    # ---- rooflines (DESIGN.md section "Rooflines"): algorithmic bytes = 16 B per bilinear sample (Radon kernel),
+    # 64 B per kappa sample (pair kernel), SURVEY.md section 8d
+    samples_per_proj = ctx.radon_num_samples(n_u, n_v, n_a, n_t)
+    counts = ctx.pair_sample_counts(n)
+    peak, peak_src = hbm_peak()
+    radon_ms, radon_launches = prof["radon"]
+    pairs_ms, pairs_launches = prof["pairs"]
+    radon_bytes_per_launch = 16.0 * samples_per_proj * (hi - lo) * args.steps / max(radon_launches, 1)
+    radon_gbs = radon_bytes_per_launch / (radon_ms / max(radon_launches, 1) * 1e-3) / 1e9 if radon_ms > 0 else 0.0
+    my_lo, my_hi = (pipe.c.partition_pairs(world)[rank:rank + 2] if world > 1 else (0, n_pairs))
+    pair_bytes = 64.0 * float(counts[int(my_lo):int(my_hi)].sum())
+    pairs_gbs = pair_bytes / (pairs_ms / max(pairs_launches, 1) * 1e-3) / 1e9 if pairs_ms > 0 else 0.0
+    launches = sum(v[1] for v in prof.values())
+
+    if rank == 0:
+        line = {
+            "metric": "all-pairs ECC image-pairs/s, end of Radon intermediates included (C3)",
+            "value": n_pairs / (ms_step * 1e-3),
+            "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": ms_step,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic: analytic 5-ellipsoid phantom, circular cone-beam trajectory, cosine weighted; generated on device",
+            "config": {"workload": W["name"], "projections": n, "pairs": n_pairs, "interpolation": "texture (reference CUDA numerics)",
+                       "sharding": f"projections block-sharded over {world} GPU(s), pairs partitioned by equal kappa samples",
+                       "l2": "inputs larger than L2 (%.2f GB images + %.2f GB dtrs per step)" % (n * n_u * n_v * 4 / 1e9, n * n_a * n_t * 4 / 1e9)},
+            "stages": {"radon_intermediates_per_s": world * (hi - lo) / ((radon_ms / args.steps) * 1e-3) if radon_ms > 0 else None,
+                       "radon_kernel_ms_per_step_rank0": radon_ms / args.steps,
+                       "pairs_per_s_metric_only_rank0": float(my_hi - my_lo) / ((pairs_ms / args.steps) * 1e-3) if pairs_ms > 0 else None,
+                       "pair_kernel_ms_per_step_rank0": pairs_ms / args.steps,
+                       "mean_ecc": mean},
+            "e2e": {"value": n_pairs / (ms_step_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_step_e2e,
+                    "h2d_bytes_per_step": int(n) * n_u * n_v * 4 + n * 96, "d2h_bytes_per_step": n * n * 4 + 8 * world,
+                    "mean_ecc": mean_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "radon_kernel (texture-unit bound; algorithmic tap bytes vs HBM copy peak)",
+                         "achieved": radon_gbs, "peak": peak, "unit": "GB/s", "frac": radon_gbs / peak, "peak_source": peak_src,
+                         "traffic": None,
+                         "samples_per_s": radon_gbs * 1e9 / 16.0,
+                         "tex_rate_frac": (radon_gbs * 1e9 / 16.0) / 1.09e12,
+                         "note": "16 B per bilinear sample x %.4g samples per projection; tex_rate_frac = samples/s over the measured "
+                                 "tex2D rate of this GPU (1.09e12/s at 1965 MHz, profiles/tex_probe_r01.txt)" % samples_per_proj},
+            "roofline_pairs": {"bound": "hbm", "kernel": "pairs_kernel (L1/texture gather bound)", "achieved": pairs_gbs, "peak": peak,
+                               "unit": "GB/s", "frac": pairs_gbs / peak, "kappa_samples": float(counts.sum())},
+        }
+        if args.cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(W, Ps, full_dtrs=pipe._full)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ===========================================================================================================
+# CPU baseline / reference arm: the oracle (CPU restatement), timed on a bounded sample of the same workload
+# ===========================================================================================================
+def cpu_sample(W, Ps, dtrs_host, n_radon=1, n_pairs_sample=1500, seed=5):
+    """Times the oracle on n_radon full-size projections and n_pairs_sample random pairs of the enumeration.
+    Returns (seconds radon per projection, seconds per pair, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    n, n_u, n_v, n_a, n_t = W["n"], W["n_u"], W["n_v"], W["n_alpha"], W["n_t"]
+    cores = ol.oracle().oracle_max_threads()
+    imgs = [ol.project_ellipsoids(Ps[k], n_u, n_v, ELLIPSOIDS) for k in range(n_radon)]
+    t0 = time.perf_counter()
+    for im in imgs:
+        ol.radon(im, n_a, n_t, interp=ol.INTERP_EXACT)
+    t_radon = (time.perf_counter() - t0) / n_radon
+    rng = np.random.default_rng(seed)
+    total = n * (n - 1) // 2
+    ks = rng.choice(total, size=min(n_pairs_sample, total), replace=False)
+    idx = np.array([ol.get_ij(int(k), n) * 2 for k in ks], np.int32)  # (P0, P1, dtr0, dtr1)
+    if dtrs_host is None:
+        # no GPU-computed dtrs at hand (reference arm): 64 stand-in dtrs (scaled copies of one oracle dtr, 151 MB at
+        # C3) addressed modulo 64, so that the memory footprint of the lookups is realistic; timing is data independent
+        base = ol.radon(imgs[0], n_a, n_t, interp=ol.INTERP_EXACT)
+        m = min(64, n)
+        dtrs_host = np.stack([base * np.float32(1.0 + 0.01 * k) for k in range(m)])
+        idx[:, 2] %= m
+        idx[:, 3] %= m
+    t0 = time.perf_counter()
+    ol.ecc(Ps, dtrs_host, n_u, n_v, dkappa=float(np.deg2rad(W["dkappa_deg"])), interp=ol.INTERP_EXACT, idx4=idx, want_out=False)
+    t_pair = (time.perf_counter() - t0) / len(ks)
+    return t_radon, t_pair, cores, len(ks)
+
+
+def cpu_baseline(W, Ps, full_dtrs=None):
+    n = W["n"]
+    n_pairs = n * (n - 1) // 2
+    dtrs_host = full_dtrs.cpu().numpy() if full_dtrs is not None else None
+    t_radon, t_pair, cores, k = cpu_sample(W, Ps, dtrs_host)
+    est = n * t_radon + n_pairs * t_pair
+    return {"value": n_pairs / est, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"oracle (CPU restatement, OpenMP): Radon of 1 of {n} projections ({t_radon:.2f} s) + {k} of {n_pairs} pairs "
+                      f"({t_pair * 1e3:.3f} ms/pair), scaled linearly to the whole job ({est:.0f} s)",
+            "radon_intermediates_per_s": 1.0 / t_radon, "pairs_per_s_metric_only": 1.0 / t_pair}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    W = WORKLOADS[args.workload]
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    n = W["n"]
+    n_pairs = n * (n - 1) // 2
+    Ps = ol.circular_trajectory(n, W["sid"], W["sdd"], W["n_u"], W["n_v"], W["arc"], W["px"])
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(W, Ps, None, n_radon=1, n_pairs_sample=200)
+    t0 = time.perf_counter()
+    acc = []
+    for _ in range(args.steps):
+        acc.append(cpu_sample(W, Ps, None))
+    wall = time.perf_counter() - t0
+    t_radon = float(np.mean([a[0] for a in acc]))
+    t_pair = float(np.mean([a[1] for a in acc]))
+    cores, k = acc[0][2], acc[0][3]
+    est = n * t_radon + n_pairs * t_pair
+    value = n_pairs / est
+    line = {
+        "impl": "reference",
+        "metric": "all-pairs ECC image-pairs/s, end of Radon intermediates included (C3)",
+        "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic: analytic 5-ellipsoid phantom, circular cone-beam trajectory, cosine weighted",
+        "config": {"workload": W["name"], "projections": n, "pairs": n_pairs, "interpolation": "exact fp32 (CPU float path)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"per step: Radon of 1 of {n} projections + {k} of {n_pairs} pairs on {cores} host threads, scaled "
+                                   f"linearly to the whole job; measured {t_radon:.2f} s/projection, {t_pair * 1e3:.3f} ms/pair; "
+                                   f"wall time of the {args.steps} sampled steps {wall:.1f} s"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference ships no CPU implementation of this path (its Radon transform exists only as a CUDA kernel); "
+                "this arm times oracle/ = the CPU restatement pinned against the reference's own headers and CUDA kernels",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

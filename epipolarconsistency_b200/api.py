@@ -102,6 +102,11 @@ class Context:
                                                interp, _ptr(out)))
         return out
 
+    def radon_num_samples(self, n_u, n_v, n_alpha, n_t, filter=FILTER_DERIVATIVE):
+        c = C.c_double()
+        self._check(self.lib.ecc_radon_num_samples(self.h, n_u, n_v, n_alpha, n_t, filter, C.byref(c)))
+        return c.value
+
     @staticmethod
     def radon_bin_sizes(n_u, n_v, n_alpha, n_t):
         a, t = C.c_double(), C.c_double()

@@ -307,6 +307,14 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
     return ECC_OK;
 }
 
+int ecc_radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count)
+{
+    if (!ctx || !count) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (n_u < 2 || n_v < 2 || n_alpha < 1 || n_t < 1) return fail(ctx, ECC_ERR_INVALID, "ecc_radon_num_samples: bad argument");
+    return radon_num_samples(ctx, n_u, n_v, n_alpha, n_t, filter, count);
+}
+
 int ecc_set_radon_intermediates(ecc_context* ctx, const float* dtrs, int n_dtrs, int n_alpha, int n_t,
                                 double step_alpha, double step_t, int n_u, int n_v, int is_derivative)
 {

@@ -147,6 +147,7 @@ int launch_derive_views(ecc_context* ctx, const double* Ps_d, int n, float* Pinv
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
                 int n_alpha, int n_t, int filter, int post, int interp, float* out_d);
 void free_image_pool(ecc_context* ctx);
+int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
 
 // ---- launchers (ecc_synth.cu) ----
 int synth_projections(ecc_context* ctx, const double* Ps_h, int n, int n_u, int n_v,

@@ -177,6 +177,23 @@ radon_kernel_split(const cudaTextureObject_t* __restrict__ images, int n_u_i, in
     }
 }
 
+// Work counter: the number of bilinear samples the Radon kernel takes per projection for this geometry (same
+// clipping and the same t += 0.66f walk, no fetches).
+__global__ void radon_count_kernel(int n_u_i, int n_v_i, int n_alpha, int n_t, int lines_per_bin,
+                                   unsigned long long* total)
+{
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+    unsigned long long cnt = 0;
+    if (ix < n_alpha && iy < n_t) {
+        BinLine L = bin_line(ix, iy, n_alpha, n_t, (float)n_u_i, (float)n_v_i);
+        if (L.valid)
+            for (float t = L.t; t <= L.t_max; t += kStep) cnt += lines_per_bin;
+    }
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && cnt) atomicAdd(total, cnt);
+}
+
 int ensure_pool(ecc_context* ctx, int n_u, int n_v, int count)
 {
     ImagePool& P = ctx->pool;
@@ -210,6 +227,21 @@ int ensure_pool(ecc_context* ctx, int n_u, int n_v, int count)
 }
 
 }  // namespace
+
+int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count)
+{
+    unsigned long long* total_d = nullptr;
+    ECC_CUDA(ctx, cudaMalloc(&total_d, sizeof(unsigned long long)));
+    ECC_CUDA(ctx, cudaMemsetAsync(total_d, 0, sizeof(unsigned long long), ctx->stream));
+    dim3 block(32, 8), grid((n_alpha + 31) / 32, (n_t + 7) / 8);
+    radon_count_kernel<<<grid, block, 0, ctx->stream>>>(n_u, n_v, n_alpha, n_t, filter == ECC_FILTER_DERIVATIVE ? 2 : 1, total_d);
+    unsigned long long total = 0;
+    ECC_CUDA(ctx, cudaMemcpyAsync(&total, total_d, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(total_d);
+    *count = (double)total;
+    return ECC_OK;
+}
 
 void free_image_pool(ecc_context* ctx)
 {

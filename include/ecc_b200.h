@@ -85,6 +85,11 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
 void ecc_radon_bin_sizes(int n_u, int n_v, int n_alpha, int n_t, double* step_alpha,
                          double* step_t);
 
+/* Work counter for benchmarks: bilinear image samples per projection for this geometry (exactly what the
+ * kernel takes: clipped lines, step 0.66 px, two lines per bin for the derivative filter). */
+int ecc_radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter,
+                          double* count);
+
 /* ---- Metric state (MetricRadonIntermediate) ------------------------------------------------ */
 
 /* setRadonIntermediates (EpipolarConsistencyRadonIntermediate.cpp:87-106).  dtrs [h|d]:

@@ -1,0 +1,93 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size 2 over gloo, with a stub compute object in place of
+the CUDA context (the product kernels need a GPU; what is tested here is sharding, exchange and reduction)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from epipolarconsistency_b200.distributed import ShardedPipeline, shard_bounds
+
+
+class StubCompute:
+    """Deterministic stand-in for api.Context: 'Radon' of an image is its mean broadcast over the bins; pair (i,j)
+    costs 1000*i + j."""
+
+    def __init__(self, n_views, world):
+        self.n, self.world = n_views, world
+
+    def radon_compute(self, images, n_alpha, n_t, out=None, **kw):
+        out.copy_(images.mean(dim=(1, 2))[:, None, None].expand(-1, n_t, n_alpha))
+        return out
+
+    def partition_pairs(self, n_parts):
+        total = self.n * (self.n - 1) // 2
+        return np.array(shard_bounds(total, n_parts), np.int64)[::1]
+
+    def evaluate_range(self, lo, hi, cost_image=None, want_sum=True):
+        pairs = [(i, j) for i in range(self.n) for j in range(i + 1, self.n)][lo:hi]
+        s = 0.0
+        for i, j in pairs:
+            v = 1000.0 * i + j
+            s += v
+            if cost_image is not None:
+                cost_image[j, i] = v
+        return s
+
+
+def _worker(rank, world, port, n_total, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bounds = shard_bounds(n_total, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        local = torch.stack([torch.full((6, 8), float(k)) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 6, 8))
+        pipe = ShardedPipeline(StubCompute(n_total, world), rank, world, device="cpu")
+        full = pipe.radon_allgather(local, n_total, 5, 4)
+        cost = torch.zeros((n_total, n_total))
+        mean = pipe.evaluate_all_pairs(n_total, cost)
+        results[rank] = (full[:, 0, 0].tolist(), mean, cost.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(n_total, world=2):
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_total, results), nprocs=world, join=True)
+    return dict(results)
+
+
+def test_shard_bounds():
+    assert shard_bounds(496, 8) == [0, 62, 124, 186, 248, 310, 372, 434, 496]
+    assert shard_bounds(5, 2) == [0, 3, 5]
+    assert shard_bounds(1, 4) == [0, 1, 1, 1, 1]
+
+
+def _check(n_total):
+    res = _run(n_total)
+    pairs = [(i, j) for i in range(n_total) for j in range(i + 1, n_total)]
+    want_mean = np.mean([1000.0 * i + j for i, j in pairs])
+    for rank in (0, 1):
+        dtr_vals, mean, cost = res[rank]
+        assert dtr_vals == [float(k) for k in range(n_total)]  # every rank ends with all dtrs, in order
+        assert abs(mean - want_mean) < 1e-9
+        for i, j in pairs:
+            assert cost[j, i] == 1000.0 * i + j  # every pair written exactly once across the ranks
+
+
+def test_world2_even_shards():
+    _check(6)
+
+
+def test_world2_ragged_shards():
+    _check(5)
