@@ -25,6 +25,10 @@ SIGNATURES = {
     "ecc_radon_bin_sizes": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ecc_radon_num_samples": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "ecc_set_radon_intermediates": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "ecc_set_radon_intermediate_pointers": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "ecc_device_alloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(c_vp)]),
+    "ecc_device_free": (C.c_int, [c_ctx, c_vp]),
+    "ecc_copy": (C.c_int, [c_ctx, c_vp, c_vp, C.c_size_t]),
     "ecc_set_projection_matrices": (C.c_int, [c_ctx, c_vp, C.c_int]),
     "ecc_update_projection_matrix": (C.c_int, [c_ctx, C.c_int, c_vp]),
     "ecc_get_derived_views": (C.c_int, [c_ctx, c_vp, c_vp]),

@@ -125,7 +125,7 @@ void destroy_dtr_textures(ecc_context* ctx)
 int fill_launch(ecc_context* ctx, PairLaunch& L)
 {
     if (ctx->n_views <= 0) return fail(ctx, ECC_ERR_STATE, "projection matrices not set");
-    if (ctx->n_dtrs <= 0 || !ctx->dtrs_d) return fail(ctx, ECC_ERR_STATE, "Radon intermediates not set");
+    if (ctx->n_dtrs <= 0 || !ctx->dtr_ptrs_d) return fail(ctx, ECC_ERR_STATE, "Radon intermediates not set");
     double radius = 0;
     int rc = ecc_get_object_radius(ctx, &radius);
     if (rc) return rc;
@@ -137,9 +137,8 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
     L.Cs_d = ctx->Cs_d;
     L.PinvTs_d = ctx->PinvTs_d;
     L.tex_d = ctx->dtr_tex_d;
-    L.dtrs_d = ctx->dtrs_d;
+    L.dtr_ptrs_d = ctx->dtr_ptrs_d;
     L.dtr_pitch = ctx->dtr_pitch;
-    L.dtr_stride = ctx->dtr_stride;
     L.n_dtrs = ctx->n_dtrs;
     L.n_alpha = ctx->n_alpha;
     L.n_t = ctx->n_t;
@@ -234,7 +233,7 @@ void ecc_destroy(ecc_context* ctx)
         cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d); cudaFree(it->second.radii_d);
         batch_buffers().erase(it);
     }
-    void* bufs[] = {ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, ctx->vals_d,
+    void* bufs[] = {ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, (void*)ctx->dtr_ptrs_d, ctx->vals_d,
                     ctx->sums_d, ctx->idx_d, ctx->counts_d, ctx->img_stage_d, ctx->out_stage_d, ctx->cost_d};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -315,6 +314,60 @@ int ecc_radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n
     return radon_num_samples(ctx, n_u, n_v, n_alpha, n_t, filter, count);
 }
 
+// Installs n_dtrs device-resident dtrs given by one pointer each (row pitch `pitch` floats): texture objects over
+// the caller's memory (zero copy) + the pointer table for the exact-interpolation path.
+static int install_dtrs(ecc_context* ctx, const std::vector<const float*>& ptrs, size_t pitch, int n_alpha, int n_t,
+                        double step_alpha, double step_t, int n_u, int n_v, int is_derivative)
+{
+    const int n_dtrs = (int)ptrs.size();
+    const bool same = (ptrs == ctx->dtr_ptrs_h && n_alpha == ctx->n_alpha && n_t == ctx->n_t && pitch == ctx->dtr_pitch &&
+                       (int)ctx->dtr_tex_h.size() == n_dtrs);
+    if (!same) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        destroy_dtr_textures(ctx);
+        ctx->dtr_tex_h.resize(n_dtrs, 0);
+        for (int k = 0; k < n_dtrs; k++) {
+            cudaResourceDesc res = {};
+            res.resType = cudaResourceTypePitch2D;
+            res.res.pitch2D.devPtr = const_cast<float*>(ptrs[k]);
+            res.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+            res.res.pitch2D.width = n_alpha;
+            res.res.pitch2D.height = n_t;
+            res.res.pitch2D.pitchInBytes = sizeof(float) * pitch;
+            cudaTextureDesc td = {};
+            td.normalizedCoords = 1;  // as the reference's dtr textures (RadonIntermediate.cpp:192)
+            td.filterMode = cudaFilterModeLinear;
+            td.addressMode[0] = cudaAddressModeClamp;
+            td.addressMode[1] = cudaAddressModeClamp;
+            td.readMode = cudaReadModeElementType;
+            ECC_CUDA(ctx, cudaCreateTextureObject(&ctx->dtr_tex_h[k], &res, &td, nullptr));
+        }
+        size_t cap_bytes = ctx->dtr_tex_cap * sizeof(cudaTextureObject_t);
+        int rc = ensure_bytes(ctx, (void**)&ctx->dtr_tex_d, &cap_bytes, sizeof(cudaTextureObject_t) * n_dtrs);
+        ctx->dtr_tex_cap = cap_bytes / sizeof(cudaTextureObject_t);
+        if (rc) return rc;
+        size_t pcap = ctx->dtr_ptrs_cap * sizeof(float*);
+        rc = ensure_bytes(ctx, (void**)&ctx->dtr_ptrs_d, &pcap, sizeof(float*) * n_dtrs);
+        ctx->dtr_ptrs_cap = pcap / sizeof(float*);
+        if (rc) return rc;
+        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->dtr_tex_d, ctx->dtr_tex_h.data(), sizeof(cudaTextureObject_t) * n_dtrs,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->dtr_ptrs_d, ptrs.data(), sizeof(float*) * n_dtrs, cudaMemcpyHostToDevice, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->dtr_ptrs_h = ptrs;
+    }
+    ctx->dtr_pitch = pitch;
+    ctx->n_dtrs = n_dtrs;
+    ctx->n_alpha = n_alpha;
+    ctx->n_t = n_t;
+    ctx->n_u = n_u;
+    ctx->n_v = n_v;
+    ctx->step_alpha = (float)step_alpha;
+    ctx->step_t = (float)step_t;
+    ctx->is_derivative = is_derivative ? 1 : 0;
+    return ECC_OK;
+}
+
 int ecc_set_radon_intermediates(ecc_context* ctx, const float* dtrs, int n_dtrs, int n_alpha, int n_t,
                                 double step_alpha, double step_t, int n_u, int n_v, int is_derivative)
 {
@@ -348,47 +401,54 @@ int ecc_set_radon_intermediates(ecc_context* ctx, const float* dtrs, int n_dtrs,
         }
         base = ctx->dtrs_owned;
     }
-    const bool same_layout = (base == ctx->dtrs_d && n_dtrs == ctx->n_dtrs && n_alpha == ctx->n_alpha && n_t == ctx->n_t &&
-                              pitch == ctx->dtr_pitch && stride == ctx->dtr_stride && (int)ctx->dtr_tex_h.size() == n_dtrs);
-    if (!same_layout) {
-        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        destroy_dtr_textures(ctx);
-        ctx->dtr_tex_h.resize(n_dtrs, 0);
-        for (int k = 0; k < n_dtrs; k++) {
-            cudaResourceDesc res = {};
-            res.resType = cudaResourceTypePitch2D;
-            res.res.pitch2D.devPtr = const_cast<float*>(base + stride * k);
-            res.res.pitch2D.desc = cudaCreateChannelDesc<float>();
-            res.res.pitch2D.width = n_alpha;
-            res.res.pitch2D.height = n_t;
-            res.res.pitch2D.pitchInBytes = sizeof(float) * pitch;
-            cudaTextureDesc td = {};
-            td.normalizedCoords = 1;  // as the reference's dtr textures (RadonIntermediate.cpp:192)
-            td.filterMode = cudaFilterModeLinear;
-            td.addressMode[0] = cudaAddressModeClamp;
-            td.addressMode[1] = cudaAddressModeClamp;
-            td.readMode = cudaReadModeElementType;
-            ECC_CUDA(ctx, cudaCreateTextureObject(&ctx->dtr_tex_h[k], &res, &td, nullptr));
-        }
-        size_t cap_bytes = ctx->dtr_tex_cap * sizeof(cudaTextureObject_t);
-        int rc = ensure_bytes(ctx, (void**)&ctx->dtr_tex_d, &cap_bytes, sizeof(cudaTextureObject_t) * n_dtrs);
-        ctx->dtr_tex_cap = cap_bytes / sizeof(cudaTextureObject_t);
-        if (rc) return rc;
-        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->dtr_tex_d, ctx->dtr_tex_h.data(), sizeof(cudaTextureObject_t) * n_dtrs,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    std::vector<const float*> ptrs(n_dtrs);
+    for (int k = 0; k < n_dtrs; k++) ptrs[k] = base + stride * k;
     ctx->dtrs_d = base;
-    ctx->dtr_pitch = pitch;
     ctx->dtr_stride = stride;
-    ctx->n_dtrs = n_dtrs;
-    ctx->n_alpha = n_alpha;
-    ctx->n_t = n_t;
-    ctx->n_u = n_u;
-    ctx->n_v = n_v;
-    ctx->step_alpha = (float)step_alpha;
-    ctx->step_t = (float)step_t;
-    ctx->is_derivative = is_derivative ? 1 : 0;
+    return install_dtrs(ctx, ptrs, pitch, n_alpha, n_t, step_alpha, step_t, n_u, n_v, is_derivative);
+}
+
+int ecc_set_radon_intermediate_pointers(ecc_context* ctx, const float* const* dtrs, int n_dtrs, int n_alpha, int n_t,
+                                        double step_alpha, double step_t, int n_u, int n_v, int is_derivative)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!dtrs || n_dtrs < 1 || n_alpha < 1 || n_t < 1 || n_u < 1 || n_v < 1)
+        return fail(ctx, ECC_ERR_INVALID, "ecc_set_radon_intermediate_pointers: bad argument");
+    if (n_alpha % 8 != 0) return fail(ctx, ECC_ERR_INVALID, "zero-copy dtrs need n_alpha to be a multiple of 8 (32-byte texture pitch)");
+    std::vector<const float*> ptrs(dtrs, dtrs + n_dtrs);
+    for (int k = 0; k < n_dtrs; k++)
+        if (!is_device_pointer(ptrs[k]) || (uintptr_t)ptrs[k] % 512 != 0)
+            return fail(ctx, ECC_ERR_INVALID, "every dtr must be device memory aligned to 512 bytes (use ecc_device_alloc)");
+    ctx->dtrs_d = nullptr;
+    ctx->dtr_stride = 0;
+    return install_dtrs(ctx, ptrs, (size_t)n_alpha, n_alpha, n_t, step_alpha, step_t, n_u, n_v, is_derivative);
+}
+
+int ecc_device_alloc(ecc_context* ctx, size_t bytes, void** ptr)
+{
+    if (!ctx || !ptr) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    ECC_CUDA(ctx, cudaMalloc(ptr, bytes ? bytes : 16));  // cudaMalloc returns at least 512-byte aligned memory
+    return ECC_OK;
+}
+
+int ecc_device_free(ecc_context* ctx, void* ptr)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!ptr) return ECC_OK;
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ECC_CUDA(ctx, cudaFree(ptr));
+    return ECC_OK;
+}
+
+int ecc_copy(ecc_context* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx || (bytes && (!dst || !src))) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    ECC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ECC_OK;
 }
 

@@ -47,7 +47,10 @@ struct ecc_context {
     // ---- radon intermediates ----
     int n_dtrs = 0, n_alpha = 0, n_t = 0, n_u = 0, n_v = 0, is_derivative = 1;
     float step_alpha = 0.f, step_t = 0.f;
-    const float* dtrs_d = nullptr;  // [n_dtrs][n_t][dtr_pitch]
+    const float* dtrs_d = nullptr;  // [n_dtrs][n_t][dtr_pitch] when set from one block, else null
+    std::vector<const float*> dtr_ptrs_h;  // one device pointer per dtr
+    const float** dtr_ptrs_d = nullptr;    // the same table on the device
+    size_t dtr_ptrs_cap = 0;
     size_t dtr_pitch = 0;           // floats per row
     size_t dtr_stride = 0;          // floats per dtr
     float* dtrs_owned = nullptr;    // non-null when the context owns the storage
@@ -120,8 +123,8 @@ struct PairLaunch {
     const float* PinvTs_d; // n_sets*n_views*12
     // dtrs
     const cudaTextureObject_t* tex_d;
-    const float* dtrs_d;
-    size_t dtr_pitch, dtr_stride;
+    const float* const* dtr_ptrs_d;  // one device pointer per dtr
+    size_t dtr_pitch;
     int n_dtrs, n_alpha, n_t;
     float half_nu, half_nv, range_t, image_diagonal;
     float radius, dkappa;

@@ -1,0 +1,209 @@
+// EpipolarConsistencyRadonIntermediate.h -- facade of EpipolarConsistency::MetricRadonIntermediate with the
+// reference's public interface (LibEpipolarConsistency/EpipolarConsistencyRadonIntermediate.h:21-106,
+// .cpp:41-322) on top of libecc_b200's C ABI.  New capability beyond the reference: evaluateBatch().
+#ifndef ECC_FACADE_METRIC_RADON_INTERMEDIATE_H
+#define ECC_FACADE_METRIC_RADON_INTERMEDIATE_H
+
+#include <set>
+#include <vector>
+
+#include "EpipolarConsistency.h"
+#include "RadonIntermediate.h"
+
+namespace EpipolarConsistency {
+
+/// Compute Epipolar Consistency on the GPU
+class MetricRadonIntermediate : public Metric {
+    std::vector<RadonIntermediate*> dtrs;  //< Radon intermediate functions (not owned).
+    bool use_corr;
+    ecc_context* ctx;
+
+    void chk(int rc, const char* what) const { detail::check(rc, ctx, what); }
+    void pushSettings()
+    {
+        chk(ecc_set_object_radius(ctx, userObjectRadius()), "ecc_set_object_radius");
+        chk(ecc_set_epipolar_plane_step(ctx, dkappa), "ecc_set_epipolar_plane_step");
+    }
+
+public:
+    MetricRadonIntermediate() : Metric(), use_corr(false), ctx(0x0) { detail::check(ecc_create(-1, &ctx), 0x0, "ecc_create"); }
+
+    MetricRadonIntermediate(const std::vector<ProjectionMatrix>& Ps, const std::vector<RadonIntermediate*>& _dtrs)
+        : Metric(), use_corr(false), ctx(0x0)
+    {
+        detail::check(ecc_create(-1, &ctx), 0x0, "ecc_create");
+        setProjectionMatrices(Ps);
+        setRadonIntermediates(_dtrs);
+    }
+
+    ~MetricRadonIntermediate() { ecc_destroy(ctx); }
+
+    /// Deprecated.
+    MetricRadonIntermediate& setdKappa(float _dkappa)
+    {
+        dkappa = _dkappa;
+        return *this;
+    }
+
+    /// Tell Metric to compute correlation instead of SSD.  Not part of the hot path.
+    MetricRadonIntermediate& useCorrelation(bool corr = true)
+    {
+        if (corr) detail::check(ECC_ERR_UNSUPPORTED, 0x0, "useCorrelation(true): correlation mode");
+        use_corr = corr;
+        return *this;
+    }
+
+    /// Interpolation flavour: ECC_INTERP_TEXTURE (reference CUDA numerics, default) or ECC_INTERP_EXACT.
+    MetricRadonIntermediate& setInterpolation(int interp)
+    {
+        chk(ecc_set_interpolation(ctx, interp), "ecc_set_interpolation");
+        return *this;
+    }
+
+    /// Register the Radon intermediates (zero copy).  DO NOT delete or change _dtrs during lifetime of Metric.
+    MetricRadonIntermediate& setRadonIntermediates(const std::vector<RadonIntermediate*>& _dtrs)
+    {
+        dtrs = _dtrs;
+        if (dtrs.empty()) return *this;
+        // size and parameters of dtrs (assumed to be identical), EpipolarConsistencyRadonIntermediate.cpp:89-98
+        RadonIntermediate* d0 = dtrs[0];
+        n_u = d0->getOriginalImageSize(0);
+        n_v = d0->getOriginalImageSize(1);
+        std::vector<const float*> ptrs(dtrs.size());
+        for (size_t i = 0; i < dtrs.size(); i++) {
+            dtrs[i]->getTexture();  // "make resident"
+            ptrs[i] = dtrs[i]->devicePointer();
+        }
+        const int n_alpha = d0->getRadonBinNumber(0), n_t = d0->getRadonBinNumber(1);
+        if (n_alpha % 8 == 0) {
+            chk(ecc_set_radon_intermediate_pointers(ctx, ptrs.data(), (int)ptrs.size(), n_alpha, n_t, d0->getRadonBinSize(0),
+                                                    d0->getRadonBinSize(1), n_u, n_v, d0->isDerivative()),
+                "ecc_set_radon_intermediate_pointers");
+        } else {
+            // widths that cannot be a texture pitch: gather into one block, the library repacks it
+            const size_t len = (size_t)n_alpha * n_t;
+            void* block = 0x0;
+            chk(ecc_device_alloc(ctx, sizeof(float) * len * ptrs.size(), &block), "ecc_device_alloc");
+            for (size_t i = 0; i < ptrs.size(); i++)
+                chk(ecc_copy(ctx, (float*)block + len * i, ptrs[i], sizeof(float) * len), "ecc_copy");
+            chk(ecc_set_radon_intermediates(ctx, (const float*)block, (int)ptrs.size(), n_alpha, n_t, d0->getRadonBinSize(0),
+                                            d0->getRadonBinSize(1), n_u, n_v, d0->isDerivative()),
+                "ecc_set_radon_intermediates");
+            chk(ecc_device_free(ctx, block), "ecc_device_free");
+        }
+        return *this;
+    }
+
+    /// Access Radon intermediate functions (for visualization and debugging)
+    const std::vector<RadonIntermediate*>& getRadonIntermediates() const { return dtrs; }
+
+    /// Declared but never defined in the reference (EpipolarConsistencyRadonIntermediate.h:52); a no-op here.
+    Metric& setRadonIntermediateBinning(int, int) { return *this; }
+
+    /// A TODO no-op in the reference as well (EpipolarConsistencyRadonIntermediate.cpp:121-125).
+    virtual Metric& setProjectionImages(const std::vector<UtilsCuda::BindlessTexture2D<float>*>&) { return *this; }
+
+    /// Compute null space and pseudoinverse of projection matrices and convert to float.
+    virtual Metric& setProjectionMatrices(const std::vector<ProjectionMatrix>& _Ps)
+    {
+        Metric::setProjectionMatrices(_Ps);
+        if (Ps.empty()) return *this;
+        std::vector<double> flat(12 * Ps.size());
+        for (size_t i = 0; i < Ps.size(); i++) std::memcpy(&flat[12 * i], Ps[i].data(), sizeof(double) * 12);
+        chk(ecc_set_projection_matrices(ctx, flat.data(), (int)Ps.size()), "ecc_set_projection_matrices");
+        return *this;
+    }
+
+    /// Radius of the object: the user's value, or the automatic estimate from the first matrix.
+    virtual double getObjectRadius() const
+    {
+        ecc_set_object_radius(ctx, userObjectRadius());
+        double r = 0;
+        chk(ecc_get_object_radius(ctx, &r), "ecc_get_object_radius");
+        return r;
+    }
+
+    /// Evaluates metric without any transformation of the geometry. Out is n*n and mean is returned.
+    virtual double evaluate(float* out = 0x0)
+    {
+        pushSettings();
+        double mean = 0;
+        chk(ecc_evaluate(ctx, out, &mean), "ecc_evaluate");
+        return mean;
+    }
+
+    /// The number of projections. The number of evaluations will be n*(n-1)/2
+    virtual int getNumberOfProjetions() { return (int)Ps.size(); }
+
+    /// Evaluates metric for just specific views
+    double evaluate(const std::set<int>& views, float* _out = 0x0)
+    {
+        std::vector<Eigen::Vector4i> indices;
+        for (auto i = views.begin(); i != views.end(); ++i)
+            for (auto j = i; j != views.end(); ++j) {
+                if (i == j) continue;
+                indices.push_back(Eigen::Vector4i(*i, *j, *i, *j));
+            }
+        std::vector<float> tmp;
+        if (!_out) {
+            tmp.resize(indices.size());
+            _out = tmp.data();
+        }
+        return evaluate(indices, _out);
+    }
+
+    /// Evaluates metric for explicit (P0,P1,dtr0,dtr1) tuples; writes indices.size() floats to out.
+    double evaluate(const std::vector<Eigen::Vector4i>& _indices, float* _out)
+    {
+        if (_indices.empty()) return 0.0;
+        pushSettings();
+        std::vector<int> flat(4 * _indices.size());
+        for (size_t i = 0; i < _indices.size(); i++)
+            for (int k = 0; k < 4; k++) flat[4 * i + k] = _indices[i].data()[k];
+        double mean = 0;
+        chk(ecc_evaluate_indices(ctx, flat.data(), (int)_indices.size(), _out, &mean), "ecc_evaluate_indices");
+        return mean;
+    }
+
+    /// NEW: score K complete projection-matrix sets against the same dtrs in one launch; returns the K means.
+    std::vector<double> evaluateBatch(const std::vector<std::vector<ProjectionMatrix> >& sets,
+                                      const std::vector<Eigen::Vector4i>* _indices = 0x0, float* out = 0x0)
+    {
+        std::vector<double> means(sets.size(), 0.0);
+        if (sets.empty()) return means;
+        pushSettings();
+        const size_t n = Ps.size();
+        std::vector<double> flat(12 * n * sets.size());
+        for (size_t s = 0; s < sets.size(); s++)
+            for (size_t i = 0; i < n; i++) std::memcpy(&flat[12 * (s * n + i)], sets[s][i].data(), sizeof(double) * 12);
+        std::vector<int> idx;
+        if (_indices) {
+            idx.resize(4 * _indices->size());
+            for (size_t i = 0; i < _indices->size(); i++)
+                for (int k = 0; k < 4; k++) idx[4 * i + k] = (*_indices)[i].data()[k];
+        }
+        chk(ecc_evaluate_batch(ctx, flat.data(), (int)sets.size(), _indices ? idx.data() : 0x0, _indices ? (int)_indices->size() : 0, out,
+                               means.data()),
+            "ecc_evaluate_batch");
+        return means;
+    }
+
+    /// Visualisation helper of the reference (EpipolarConsistencyRadonIntermediate.cpp:324-393): that code samples on
+    /// the CPU with its own texel mapping.  Here: the pair's metric value from the GPU path; sample vectors are not filled.
+    virtual double evaluateForImagePair(int i, int j, std::vector<float>* redundant_samples0 = 0x0,
+                                        std::vector<float>* redundant_samples1 = 0x0, std::vector<float>* kappas = 0x0)
+    {
+        (void)redundant_samples0; (void)redundant_samples1; (void)kappas;
+        std::vector<Eigen::Vector4i> one(1, Eigen::Vector4i(i, j, i, j));
+        float v = 0;
+        evaluate(one, &v);
+        return v;
+    }
+
+protected:
+    MetricRadonIntermediate(const MetricRadonIntermediate&);
+};
+
+}  // namespace EpipolarConsistency
+
+#endif

@@ -100,6 +100,19 @@ int ecc_set_radon_intermediates(ecc_context* ctx, const float* dtrs, int n_dtrs,
                                 int n_t, double step_alpha, double step_t, int n_u, int n_v,
                                 int is_derivative);
 
+/* The same for dtrs that live in separate device allocations, one pointer each (the reference keeps a
+ * std::vector<RadonIntermediate*>, EpipolarConsistencyRadonIntermediate.h:23): zero copy, every pointer must be
+ * 512-byte aligned device memory (ecc_device_alloc) and n_alpha a multiple of 8. dtrs: host array of n_dtrs pointers. */
+int ecc_set_radon_intermediate_pointers(ecc_context* ctx, const float* const* dtrs, int n_dtrs, int n_alpha,
+                                        int n_t, double step_alpha, double step_t, int n_u, int n_v,
+                                        int is_derivative);
+
+/* Device memory for callers without a CUDA toolchain of their own (the C++ facade): allocate / free / copy in
+ * any direction (host<->device, device<->device); ecc_copy synchronises. */
+int ecc_device_alloc(ecc_context* ctx, size_t bytes, void** ptr);
+int ecc_device_free(ecc_context* ctx, void* ptr);
+int ecc_copy(ecc_context* ctx, void* dst, const void* src, size_t bytes);
+
 /* setProjectionMatrices (EpipolarConsistencyRadonIntermediate.cpp:134-163): pseudo-inverse
  * transposes and source positions are derived on the device in fp64 and stored as fp32. */
 int ecc_set_projection_matrices(ecc_context* ctx, const double* Ps, int n);

@@ -41,3 +41,37 @@ int ref_line_to_sample(float* line, float range_t)
 }
 
 }  // extern "C"
+
+// ---- the reference's own NRRD reader / writer (HeaderOnly/NRRD/nrrd_image.hxx), to cross-check the file layout
+#include <NRRD/nrrd_image.hxx>
+#include <cstring>
+
+extern "C" {
+
+// Loads `path` with the reference's NRRD::Image<float>.  Returns 0 on failure, else the number of pixels; fills
+// sizes and the value of one meta key.
+int ref_nrrd_load(const char* path, float* out, int max_len, int* w, int* h, const char* key, char* value, int value_cap)
+{
+    NRRD::Image<float> img;
+    if (!img.load(path)) return 0;
+    *w = img.size(0);
+    *h = img.size(1);
+    const int n = img.length();
+    if (n > max_len) return 0;
+    for (int i = 0; i < n; i++) out[i] = img[i];
+    std::string v = img.meta_info[key];
+    std::strncpy(value, v.c_str(), value_cap - 1);
+    value[value_cap - 1] = 0;
+    return n;
+}
+
+// Saves a w x h float image with one meta key using the reference's writer.
+int ref_nrrd_save(const char* path, const float* data, int w, int h, const char* key, const char* value)
+{
+    NRRD::Image<float> img(w, h);
+    for (int i = 0; i < w * h; i++) img[i] = data[i];
+    img.meta_info[key] = value;
+    return img.save(path) ? 1 : 0;
+}
+
+}  // extern "C"

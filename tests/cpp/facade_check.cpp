@@ -1,0 +1,155 @@
+// facade_check.cpp -- exercises the C++ facade (include/EpipolarConsistency/*.h) the way the reference's tools use
+// the reference classes.  "cpu": file-format and API-surface checks without a GPU.  "gpu": Radon intermediates +
+// metric through the facade on a small synthetic scene; prints numbers that tests/test_facade.py compares with
+// the Python mirror of the same ABI.
+#define ECC_FACADE_THROW
+#include <EpipolarConsistency/EpipolarConsistencyRadonIntermediate.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+using namespace EpipolarConsistency;
+
+static int fail(const char* what)
+{
+    std::printf("FAIL %s\n", what);
+    return 1;
+}
+
+static int run_cpu(const char* tmpdir)
+{
+    // NRRD round trip with the dtr meta keys (RadonIntermediate.cpp:96-103)
+    NRRD::Image<float> img(7, 5);
+    for (int i = 0; i < img.length(); i++) ((float*)img)[i] = 0.25f * i - 3.f;
+    img.meta_info["Bin Size/Angle"] = toString(3.14159265358979 / 7);
+    img.meta_info["Bin Size/Distance"] = toString(12.5);
+    img.meta_info["Original Image/Width"] = toString(160);
+    img.meta_info["Original Image/Height"] = toString(128);
+    img.meta_info["Filter"] = "Derivative";
+    const std::string path = std::string(tmpdir) + "/facade_dtr.nrrd";
+    if (!img.save(path)) return fail("save");
+    // header layout: magic, fields in lexical order, keys, offset comment, blank line
+    std::ifstream f(path.c_str(), std::ios::binary);
+    std::string line;
+    const char* expect[] = {"NRRD0004", "dimension: 2", "encoding: raw", "endian: little", "sizes: 7 5", "spacings: 1 1", "type: float",
+                            "Bin Size/Angle:=0.448799", "Bin Size/Distance:=12.5", "Filter:=Derivative", "Original Image/Height:=128",
+                            "Original Image/Width:=160"};
+    for (const char* e : expect) {
+        std::getline(f, line);
+        if (line != e) {
+            std::printf("header line '%s' != '%s'\n", line.c_str(), e);
+            return fail("header");
+        }
+    }
+    std::getline(f, line);
+    if (line.compare(0, 22, "# Offset to raw data: ") != 0) return fail("offset comment");
+    const int offset = std::atoi(line.c_str() + 22);
+    std::getline(f, line);
+    if (!line.empty()) return fail("blank line");
+    if ((int)f.tellg() != offset) return fail("offset value");
+    f.close();
+    NRRD::Image<float> back(path);
+    if (!back || back.size(0) != 7 || back.size(1) != 5) return fail("load sizes");
+    for (int i = 0; i < img.length(); i++)
+        if (((float*)back)[i] != ((float*)img)[i]) return fail("load data");
+    if (back.meta_info["Filter"] != "Derivative" || stringTo<int>(back.meta_info["Original Image/Width"]) != 160) return fail("load meta");
+    // API surface of the compat types
+    Geometry::ProjectionMatrix P;
+    P(2, 3) = 5.0;
+    if (P.data()[2 + 3 * 3] != 5.0) return fail("column-major");
+    Eigen::Vector4i v(1, 2, 3, 4);
+    if (v.data()[2] != 3) return fail("Vector4i");
+    // a file with a single key, for the byte-for-byte comparison with the reference's writer
+    NRRD::Image<float> one(7, 5);
+    for (int i = 0; i < one.length(); i++) ((float*)one)[i] = 0.25f * i - 3.f;
+    one.meta_info["Filter"] = "Derivative";
+    if (!one.save(std::string(tmpdir) + "/facade_same.nrrd")) return fail("save same");
+    std::printf("OK cpu\n");
+    return 0;
+}
+
+static int run_load(const char* path)
+{
+    NRRD::Image<float> img(path);
+    if (!img) return fail("load");
+    double sum = 0;
+    for (int i = 0; i < img.length(); i++) sum += ((float*)img)[i];
+    std::printf("loaded %d %d %.9g %s\n", img.size(0), img.size(1), sum, img.meta_info["Filter"].c_str());
+    return 0;
+}
+
+static int run_gpu(const char* tmpdir)
+{
+    const int n = 6, n_u = 160, n_v = 128, n_a = 128, n_t = 128;
+    std::vector<double> flat(12 * n);
+    ecc_make_circular_trajectory(n, 750.0, 1200.0, n_u, n_v, 200.0, 2.0, flat.data());
+    std::vector<ProjectionMatrix> Ps(n);
+    for (int i = 0; i < n; i++) std::memcpy(Ps[i].data(), &flat[12 * i], sizeof(double) * 12);
+    // synthetic projections through the C ABI, copied to host images
+    ecc_context* ctx = detail::shared_context();
+    const double ell[14] = {0, 0, 0, 60, 40, 50, 1.0, 20, -10, 5, 20, 25, 15, 0.5};
+    void* dev = 0x0;
+    detail::check(ecc_device_alloc(ctx, sizeof(float) * (size_t)n * n_u * n_v, &dev), ctx, "alloc");
+    detail::check(ecc_synth_projections(ctx, flat.data(), n, n_u, n_v, ell, 2, 1, 1, (float*)dev), ctx, "synth");
+    std::vector<NRRD::Image<float> > images(n);
+    std::vector<RadonIntermediate*> dtrs(n);
+    for (int i = 0; i < n; i++) {
+        images[i].set(n_u, n_v);
+        detail::check(ecc_copy(ctx, (float*)images[i], (float*)dev + (size_t)i * n_u * n_v, sizeof(float) * n_u * n_v), ctx, "copy");
+        dtrs[i] = new RadonIntermediate(images[i], n_a, n_t, RadonIntermediate::Derivative, RadonIntermediate::Identity);
+    }
+    ecc_device_free(ctx, dev);
+    if (!dtrs[0]->isDerivative() || dtrs[0]->getRadonBinNumber(1) != n_t || dtrs[0]->getOriginalImageSize(0) != n_u) return fail("dtr props");
+    // save / reload a dtr: identical data and properties
+    dtrs[2]->readback();
+    const std::string path = std::string(tmpdir) + "/facade_dtr2.nrrd";
+    if (!dtrs[2]->data().save(path)) return fail("dtr save");
+    RadonIntermediate reloaded(path);
+    reloaded.readback();
+    for (int k = 0; k < n_a * n_t; k++)
+        if (((const float*)reloaded.data())[k] != ((const float*)dtrs[2]->data())[k]) return fail("dtr reload data");
+    if (std::fabs(reloaded.getRadonBinSize(1) - dtrs[2]->getRadonBinSize(1)) > 1e-5 * dtrs[2]->getRadonBinSize(1)) return fail("dtr reload props");
+
+    MetricRadonIntermediate ecc(Ps, dtrs);
+    std::vector<float> cost(n * n, -1.f);
+    const double mean = ecc.evaluate(cost.data());
+    std::printf("radius %.9g\n", ecc.getObjectRadius());
+    std::printf("mean %.9g\n", mean);
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) std::printf("pair %d %d %.9g\n", i, j, cost[i + j * n]);
+    if (cost[0] != -1.f) return fail("untouched entries");
+    std::set<int> views;
+    views.insert(1); views.insert(3); views.insert(4);
+    std::printf("subset %.9g\n", ecc.evaluate(views));
+    std::vector<Eigen::Vector4i> idx;
+    idx.push_back(Eigen::Vector4i(0, 5, 0, 5));
+    idx.push_back(Eigen::Vector4i(2, 1, 2, 1));
+    float out2[2];
+    std::printf("list %.9g %.9g %.9g\n", ecc.evaluate(idx, out2), out2[0], out2[1]);
+    std::vector<std::vector<ProjectionMatrix> > sets(2, Ps);
+    sets[1][3](0, 3) += 3.0 * sets[1][3](2, 3);  // detector shift of view 3 by 3 px in u
+    for (int c = 0; c < 3; c++) sets[1][3](0, c) += 3.0 * sets[1][3](2, c);
+    std::vector<double> means = ecc.evaluateBatch(sets);
+    std::printf("batch %.9g %.9g\n", means[0], means[1]);
+    ecc.setObjectRadius(50.0).setEpipolarPlaneStep(0.002);
+    std::printf("fixed %.9g\n", ecc.evaluate());
+    for (auto d : dtrs) delete d;
+    std::printf("OK gpu\n");
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    const char* mode = argc > 1 ? argv[1] : "cpu";
+    const char* tmpdir = argc > 2 ? argv[2] : "/tmp";
+    try {
+        if (std::strcmp(mode, "load") == 0) return run_load(tmpdir);
+        return std::strcmp(mode, "gpu") == 0 ? run_gpu(tmpdir) : run_cpu(tmpdir);
+    } catch (const std::exception& e) {
+        std::printf("EXCEPTION %s\n", e.what());
+        return 2;
+    }
+}

@@ -256,3 +256,14 @@ class RefCudaMetric:
         if self.h:
             self.L.ref_cuda_metric_destroy(self.h)
             self.h = None
+
+
+def ref_nrrd():
+    """The reference's own NRRD reader/writer (via oracle/_ref/libecc_ref_host.so); None if not built."""
+    L = ref_host()
+    if L is None or not hasattr(L, "ref_nrrd_load"):
+        return None
+    L.ref_nrrd_load.argtypes = [C.c_char_p, _f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p,
+                                C.c_char_p, C.c_int]
+    L.ref_nrrd_save.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+    return L

@@ -1,0 +1,91 @@
+"""The C++ facade (include/EpipolarConsistency/*.h): builds with plain g++ against libecc_b200.so, keeps the
+reference's file layout (checked against the reference's own NRRD reader/writer when oracle/_ref is present), and on
+the GPU gives the same numbers as the Python mirror of the same ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "facade_check")
+
+
+def build():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp")], check=True, stdout=subprocess.DEVNULL)
+
+
+def test_facade_builds_and_cpu_checks(tmp_path):
+    build()
+    r = subprocess.run([EXE, "cpu", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK cpu" in r.stdout, r.stdout + r.stderr
+
+
+def test_nrrd_layout_against_reference_reader_and_writer(tmp_path):
+    R = ol.ref_nrrd()
+    if R is None:
+        pytest.skip("oracle/_ref/libecc_ref_host.so (with the reference's NRRD code) not built")
+    build()
+    subprocess.run([EXE, "cpu", str(tmp_path)], check=True, stdout=subprocess.DEVNULL)
+    # (1) a file written by the facade loads in the reference's reader
+    out = np.zeros(64, np.float32)
+    w, h = C.c_int(), C.c_int()
+    val = C.create_string_buffer(64)
+    n = R.ref_nrrd_load(str(tmp_path / "facade_dtr.nrrd").encode(), out, 64, C.byref(w), C.byref(h), b"Filter", val, 64)
+    assert n == 35 and (w.value, h.value) == (7, 5) and val.value == b"Derivative"
+    assert np.array_equal(out[:35], 0.25 * np.arange(35, dtype=np.float32) - 3)
+    # (2) a file written by the reference's writer is byte-identical to the facade's for the same content
+    data = (0.25 * np.arange(35, dtype=np.float32) - 3).astype(np.float32)
+    assert R.ref_nrrd_save(str(tmp_path / "ref.nrrd").encode(), data, 7, 5, b"Filter", b"Derivative") == 1
+    ref_bytes = open(tmp_path / "ref.nrrd", "rb").read()
+    head, raw = ref_bytes.split(b"\n\n", 1)
+    assert raw == data.tobytes()
+    assert head.startswith(b"NRRD0004\ndimension: 2\nencoding: raw\nendian: little\nsizes: 7 5\n")
+    assert ref_bytes == open(tmp_path / "facade_same.nrrd", "rb").read()
+    # (3) and it loads in the facade's reader
+    r = subprocess.run([EXE, "load", str(tmp_path / "ref.nrrd")], capture_output=True, text=True)
+    assert r.stdout.split() == ["loaded", "7", "5", "%.9g" % float(data.astype(np.float64).sum()), "Derivative"], r.stdout
+
+
+@pytest.mark.gpu
+def test_facade_gpu_matches_python_mirror(tmp_path):
+    from epipolarconsistency_b200 import api
+    build()
+    r = subprocess.run([EXE, "gpu", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK gpu" in r.stdout, r.stdout + r.stderr
+    vals = {}
+    pairs = {}
+    for line in r.stdout.splitlines():
+        t = line.split()
+        if t[0] == "pair":
+            pairs[(int(t[1]), int(t[2]))] = float(t[3])
+        elif t[0] in ("radius", "mean", "subset", "fixed"):
+            vals[t[0]] = float(t[1])
+        elif t[0] in ("list", "batch"):
+            vals[t[0]] = [float(x) for x in t[1:]]
+    # the same scene through the Python mirror
+    import torch
+    n, n_u, n_v, n_a, n_t = 6, 160, 128, 128, 128
+    ell = np.array([[0, 0, 0, 60, 40, 50, 1.0], [20, -10, 5, 20, 25, 15, 0.5]])
+    ctx = api.Context()
+    Ps = api.make_circular_trajectory(n, 750.0, 1200.0, n_u, n_v, 200.0, 2.0)
+    imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
+    ctx.synth_projections(Ps, n_u, n_v, ell, imgs)
+    dtrs = ctx.radon_compute(imgs, n_a, n_t)
+    ctx.set_projection_matrices(Ps)
+    ctx.set_radon_intermediates(dtrs, n_u, n_v, True)
+    cost = np.zeros((n, n), np.float32)
+    mean = ctx.evaluate(cost)
+    assert abs(vals["radius"] - ctx.get_object_radius()) < 1e-6
+    assert abs(vals["mean"] - mean) <= 1e-7 * mean
+    for (i, j), v in pairs.items():
+        assert abs(v - cost[j, i]) <= 1e-6 * abs(cost[j, i]) + 1e-12
+    idx = np.array([(1, 3, 1, 3), (1, 4, 1, 4), (3, 4, 3, 4)], np.int32)
+    assert abs(vals["subset"] - ctx.evaluate_indices(idx)) <= 1e-7 * vals["subset"]
+    assert vals["batch"][1] > 2 * vals["batch"][0] and abs(vals["batch"][0] - mean) <= 1e-7 * mean
+    ctx.set_object_radius(50.0)
+    ctx.set_epipolar_plane_step(0.002)
+    assert abs(vals["fixed"] - ctx.evaluate(None)) <= 1e-7 * vals["fixed"]
