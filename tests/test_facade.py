@@ -85,7 +85,16 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
         assert abs(v - cost[j, i]) <= 1e-6 * abs(cost[j, i]) + 1e-12
     idx = np.array([(1, 3, 1, 3), (1, 4, 1, 4), (3, 4, 3, 4)], np.int32)
     assert abs(vals["subset"] - ctx.evaluate_indices(idx)) <= 1e-7 * vals["subset"]
-    assert vals["batch"][1] > 2 * vals["batch"][0] and abs(vals["batch"][0] - mean) <= 1e-7 * mean
+    # the same two matrix sets through the mirror: set 1 = view 3 shifted by 3 px in u (row0 += 3*row2; Ps are
+    # column-major 3x4: entry (r,c) at r + 3c)
+    sets = np.stack([Ps, Ps]).reshape(2, n, 12).copy()
+    for c in range(4):
+        sets[1, 3, 0 + 3 * c] += 3.0 * sets[1, 3, 2 + 3 * c]
+    want_batch = ctx.evaluate_batch(sets)
+    assert abs(vals["batch"][0] - mean) <= 1e-7 * mean
+    assert abs(vals["batch"][0] - want_batch[0]) <= 1e-7 * mean
+    assert abs(vals["batch"][1] - want_batch[1]) <= 1e-7 * want_batch[1]
+    assert vals["batch"][1] > 1.1 * vals["batch"][0]
     ctx.set_object_radius(50.0)
     ctx.set_epipolar_plane_step(0.002)
     assert abs(vals["fixed"] - ctx.evaluate(None)) <= 1e-7 * vals["fixed"]
