@@ -228,6 +228,7 @@ void ecc_destroy(ecc_context* ctx)
     prof_collect(ctx);
     destroy_dtr_textures(ctx);
     free_image_pool(ctx);
+    free_hybrid(ctx);
     auto it = batch_buffers().find(ctx);
     if (it != batch_buffers().end()) {
         cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d); cudaFree(it->second.radii_d);
@@ -279,7 +280,7 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
         return fail(ctx, ECC_ERR_UNSUPPORTED, "ramp filter is not part of the hot path (SURVEY.md row N4)");
     if (filter != ECC_FILTER_DERIVATIVE && filter != ECC_FILTER_NONE) return fail(ctx, ECC_ERR_INVALID, "bad filter");
     if (post < 0 || post > 2) return fail(ctx, ECC_ERR_INVALID, "bad post_process");
-    if (interp != ECC_INTERP_TEXTURE && interp != ECC_INTERP_EXACT) return fail(ctx, ECC_ERR_INVALID, "bad interp");
+    if (interp != ECC_INTERP_TEXTURE && interp != ECC_INTERP_EXACT && interp != ECC_INTERP_HYBRID) return fail(ctx, ECC_ERR_INVALID, "bad interp");
     if (n_images == 0) return ECC_OK;
     const bool in_dev = is_device_pointer(images), out_dev = is_device_pointer(dtrs_out);
     const size_t img_elems = (size_t)n_u * n_v, dtr_elems = (size_t)n_alpha * n_t;

@@ -27,6 +27,18 @@ struct ImagePool {
     cudaTextureObject_t* tex_d = nullptr;
 };
 
+// Staging of the hybrid Radon kernel's shared-memory path: padded and transposed-padded image copies, their TMA
+// tensor maps (CUtensorMap, kept as raw bytes so that this header does not need cuda.h) and the work-queue word.
+struct HybridStage {
+    int n_u = 0, n_v = 0, count = 0;
+    float* pad_n = nullptr;
+    float* pad_t = nullptr;
+    unsigned* queue = nullptr;  // [2 counters][one claim word per item]
+    size_t queue_words = 0;
+    alignas(64) unsigned char map_n[128] = {};
+    alignas(64) unsigned char map_t[128] = {};
+};
+
 }  // namespace eccb200
 
 struct ecc_context {
@@ -83,6 +95,7 @@ struct ecc_context {
     size_t cost_cap = 0;
 
     eccb200::ImagePool pool;
+    eccb200::HybridStage hybrid;
 
     // ---- profiling ----
     bool profiling = false;
@@ -150,6 +163,10 @@ int launch_derive_views(ecc_context* ctx, const double* Ps_d, int n, float* Pinv
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
                 int n_alpha, int n_t, int filter, int post, int interp, float* out_d);
 void free_image_pool(ecc_context* ctx);
+// ---- launchers (ecc_radon_hybrid.cu) ----
+int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, const float* images_d, int n, int n_u,
+                        int n_v, int n_alpha, int n_t, int post, float* out_d);
+void free_hybrid(ecc_context* ctx);
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
 
 // ---- launchers (ecc_synth.cu) ----

@@ -280,10 +280,15 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
         dim3 block(kLanesT, by);
         float* dst = out_d + (size_t)first * n_t * n_alpha;
         const cudaTextureObject_t* texs = ctx->pool.tex_d;
+        if (interp == ECC_INTERP_HYBRID && deriv) {
+            const int rc2 = radon_hybrid_launch(ctx, texs, images_d + (size_t)first * n_u * n_v, n, n_u, n_v, n_alpha, n_t, post, dst);
+            if (rc2) return rc2;
+            continue;
+        }
         const int slot = prof_begin(ctx, FAM_RADON);
         if (la == 0 && deriv) {
             dim3 grid((2 * n_t + kLanesT - 1) / kLanesT, (n_alpha + by - 1) / by, n);
-            if (interp == ECC_INTERP_TEXTURE) radon_kernel_split<ECC_INTERP_TEXTURE><<<grid, block, 0, ctx->stream>>>(texs, n_u, n_v, n_alpha, n_t, post, dst);
+            if (interp != ECC_INTERP_EXACT) radon_kernel_split<ECC_INTERP_TEXTURE><<<grid, block, 0, ctx->stream>>>(texs, n_u, n_v, n_alpha, n_t, post, dst);
             else radon_kernel_split<ECC_INTERP_EXACT><<<grid, block, 0, ctx->stream>>>(texs, n_u, n_v, n_alpha, n_t, post, dst);
         } else {
             Tiling tl;
@@ -293,7 +298,7 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
             const int tile_a = tl.qa * tl.ga * tl.wa, tile_t = (32 / (tl.qa * tl.ga)) * (by / tl.wa);
             dim3 grid((n_alpha + tile_a - 1) / tile_a, (n_t + tile_t - 1) / tile_t, n);
 #define ECC_LAUNCH(K) K<<<grid, block, 0, ctx->stream>>>(texs, n_u, n_v, n_alpha, n_t, post, tl, dst)
-            if (interp == ECC_INTERP_TEXTURE) { if (deriv) ECC_LAUNCH((radon_kernel<true, ECC_INTERP_TEXTURE>)); else ECC_LAUNCH((radon_kernel<false, ECC_INTERP_TEXTURE>)); }
+            if (interp != ECC_INTERP_EXACT) { if (deriv) ECC_LAUNCH((radon_kernel<true, ECC_INTERP_TEXTURE>)); else ECC_LAUNCH((radon_kernel<false, ECC_INTERP_TEXTURE>)); }
             else { if (deriv) ECC_LAUNCH((radon_kernel<true, ECC_INTERP_EXACT>)); else ECC_LAUNCH((radon_kernel<false, ECC_INTERP_EXACT>)); }
 #undef ECC_LAUNCH
         }

@@ -1,0 +1,581 @@
+// ecc_radon_hybrid.cu -- Radon-intermediate kernel that feeds BOTH sampling pipes of an SM (sm_100a).
+//
+// WHAT (reference, code/LibEpipolarConsistency/RadonIntermediate.cu:31-143): per (alpha,t) bin the difference of two
+// line integrals one pixel apart, sample step 0.66 px, bilinear image lookups through the texture unit.
+// WHY a second path: the texture-only kernel (ecc_radon.cu) sits at 98 % of the L1TEX texture data pipe with 86 % of
+// the issue slots idle (profiles/ncu_radon_r01.txt).  The texture filter's arithmetic is known exactly
+// (profiles/tex_probe_r01.txt: position rounded to 1/256, w11 = (a*b+128)>>8, ...), so the idle issue slots can
+// take the same samples from shared memory (profiles/radon_lsu_probe_r01.txt: within 7e-6 of the peak of the
+// texture result, 1.66x the texture-only rate with both running side by side).
+// HOW:
+//   * persistent CTAs of 8 "window" warps + NT texture warps; work = items of 8 angles x 32 t bins per image, drawn
+//     from a two-ended queue: window groups take items from the front, texture warps take 32-bin sub-tiles from the
+//     back, so the split between the two pipes balances itself.
+//   * a window group walks its 256 lines (two per bin) in lock step through 28-pixel chunks of the image along the
+//     lines' primary axis; the band of rows all lines need inside a chunk is fetched by TMA (cp.async.bulk.tensor,
+//     36-column x 32-row boxes, zero fill outside) into shared memory, double buffered behind an mbarrier.  Near-
+//     vertical angles read a transposed copy of the image, so the code path is the same.
+//   * sample positions are the reference's, bit for bit (clipped entry, t += 0.66f in fp32, +-1/2 px lines).
+#include <cuda.h>
+
+#include <climits>
+#include <cstdlib>
+
+#include "ecc_geometry.cuh"
+#include "ecc_internal.h"
+
+namespace eccb200 {
+
+namespace {
+
+constexpr float kStep = 0.66f;
+constexpr int kWindowWarps = 8;      // warps of a window group = threads / 32 that share one item
+constexpr int kItemAngles = 8;       // angles per item
+constexpr int kItemT = 32;           // t bins per item
+constexpr int kSubTiles = 8;         // 32-bin sub-tiles per item (2 angles x 16 t each)
+constexpr int kChunk = 28;           // pixels of the primary axis per chunk
+constexpr int kBoxW = 36;            // window columns [28j-4, 28j+32): chunk + 2 either side, start a multiple of 4
+                                     // (TMA: the innermost start coordinate must be 16-byte aligned, tools/tma_probe.cu)
+constexpr int kBoxLead = 4;          // columns in front of the chunk
+constexpr int kBoxR = 32;            // rows per TMA box
+constexpr int kMaxChunks = 64;       // primary axis up to ~1790 px; longer -> the item goes through the texture unit
+
+struct BinLine {
+    float o0, o1, d0, d1, t, t_max;
+    bool valid, swapped;
+};
+
+// Bin (ix,iy) -> line, clipped against the image inset by one pixel (RadonIntermediate.cu:44-92).  "swapped": the
+// line misses the inset box (its "middle two" intersections come in the other order) but still passes the
+// reference's entry-point test; only such lines can sample outside the image (clamp addressing).
+__device__ __forceinline__ BinLine bin_line(int ix, int iy, int n_alpha, int n_t, float n_u, float n_v)
+{
+    BinLine L;
+    const float x_rel = ix / (float)n_alpha - 0.5f;
+    const float y_rel = iy / (float)n_t - 0.5f;
+    const float diag = sqrtf(n_u * n_u + n_v * n_v);
+    const float alpha = x_rel * ECC_PI_F;
+    const float tau = y_rel * diag;
+    const float l0 = -sinf(alpha);
+    const float l1 = cosf(alpha);
+    float l2 = -tau;
+    l2 += -0.5f * n_u * l0 - 0.5f * n_v * l1;
+    L.o0 = -l2 * l0;
+    L.o1 = -l2 * l1;
+    L.d0 = l1;
+    L.d1 = -l0;
+    float ta = (1.f - L.o0) / L.d0, tb = (n_u - 1.f - L.o0) / L.d0;
+    float tc = (1.f - L.o1) / L.d1, td = (n_v - 1.f - L.o1) / L.d1;
+    if (L.d0 * L.d0 < 1e-12f) { ta = -1e10f; tb = 1e10f; }
+    if (L.d1 * L.d1 < 1e-12f) { tc = -1e10f; td = 1e10f; }
+    const float lo1 = fminf(ta, tb), hi1 = fmaxf(ta, tb);
+    const float lo2 = fminf(tc, td), hi2 = fmaxf(tc, td);
+    L.t = fmaxf(lo1, lo2);
+    L.t_max = fminf(hi1, hi2);
+    L.swapped = fminf(hi1, hi2) < fmaxf(lo1, lo2);
+    if (L.swapped) { L.t = fminf(hi1, hi2); L.t_max = fmaxf(lo1, lo2); }
+    const float pu = L.o0 + L.t * L.d0, pv = L.o1 + L.t * L.d1;
+    const bool inside = (pu <= n_u && pv <= n_v && pu >= 0.f && pv >= 0.f);
+    L.valid = inside && !(L.t_max <= L.t);
+    return L;
+}
+
+__device__ __forceinline__ float post_process(float r, int post)
+{
+    if (post == ECC_POST_SQRT) return r < 0.f ? -sqrtf(-r) : sqrtf(r);
+    if (post == ECC_POST_LOG) return r < 0.f ? -logf(-r + 1.f) : logf(r + 1.f);
+    return r;
+}
+
+// The whole bin through the texture unit, four steps in flight (the adds of t and of the sums happen in the
+// reference's order; a sample past t_max contributes an exact 0).
+__device__ __forceinline__ float bin_texture(cudaTextureObject_t tex, const BinLine& L)
+{
+    float o0 = L.o0 + 0.5f, o1 = L.o1 + 0.5f;  // texel centres
+    const float d0 = L.d0, d1 = L.d1, t_max = L.t_max;
+    o0 -= 0.5f * d1;
+    o1 += 0.5f * d0;
+    float sum = 0.f, sumo = 0.f;
+    float t = L.t;
+    while (t <= t_max) {
+        const float t1 = t + kStep, t2 = t1 + kStep, t3 = t2 + kStep;
+        const float a0 = tex2D<float>(tex, o0 + t * d0, o1 + t * d1);
+        const float b0 = tex2D<float>(tex, o0 + t * d0 + d1, o1 + t * d1 - d0);
+        float a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f, a3 = 0.f, b3 = 0.f;
+        if (t1 <= t_max) {
+            a1 = tex2D<float>(tex, o0 + t1 * d0, o1 + t1 * d1);
+            b1 = tex2D<float>(tex, o0 + t1 * d0 + d1, o1 + t1 * d1 - d0);
+        }
+        if (t2 <= t_max) {
+            a2 = tex2D<float>(tex, o0 + t2 * d0, o1 + t2 * d1);
+            b2 = tex2D<float>(tex, o0 + t2 * d0 + d1, o1 + t2 * d1 - d0);
+        }
+        if (t3 <= t_max) {
+            a3 = tex2D<float>(tex, o0 + t3 * d0, o1 + t3 * d1);
+            b3 = tex2D<float>(tex, o0 + t3 * d0 + d1, o1 + t3 * d1 - d0);
+        }
+        sum += a0; sumo += b0;
+        sum += a1; sumo += b1;
+        sum += a2; sumo += b2;
+        sum += a3; sumo += b3;
+        t = t3 + kStep;
+    }
+    return (sum - sumo) * kStep;
+}
+
+// One bilinear sample from the shared-memory window, reproducing the texture unit (profiles/tex_probe_r01.txt):
+// (coordinate - 1/2) rounded to 1/256 half up -> cell index and 8-bit fractions a, b; weights
+// w11 = (a*b + 128) >> 8, w10 = a - w11, w01 = b - w11, w00 = 256 - a - b + w11, all /256.
+// pri/sec: texel-space coordinates along the window's column / row axis.  base: byte address (shared window) such
+// that cell (ipri, isec) sits at base + 4*((isec + M)*kBoxW + ipri + M) with M = 0x4B0000 (the exponent bits of the
+// rounding constant are left in the index and folded into base).
+__device__ __forceinline__ float sample_window(unsigned base, float pri, float sec)
+{
+    const float Ps = fmaf(pri, 256.f, -127.5f);  // exact: 256*(pri - 1/2) + 1/2
+    const float Ss = fmaf(sec, 256.f, -127.5f);
+    const unsigned Pi = __float_as_uint(__fadd_rd(Ps, 8388608.f));  // 0x4B000000 + floor(Ps)
+    const unsigned Si = __float_as_uint(__fadd_rd(Ss, 8388608.f));
+    const unsigned a = Pi & 255u, b = Si & 255u;
+    const unsigned addr = base + (((Si >> 8) * kBoxW + (Pi >> 8)) << 2);
+    float v00, v10, v01, v11;
+    asm volatile(
+        "ld.shared.f32 %0, [%4];\n"
+        "ld.shared.f32 %1, [%4+4];\n"
+        "ld.shared.f32 %2, [%4+144];\n"
+        "ld.shared.f32 %3, [%4+148];\n"
+        : "=f"(v00), "=f"(v10), "=f"(v01), "=f"(v11)
+        : "r"(addr));
+    const unsigned w11 = (a * b + 128u) >> 8;
+    const unsigned w10 = a - w11, w01 = b - w11, w00 = 256u + w11 - a - b;
+    float s = __uint2float_rn(w11) * v11;
+    s = fmaf(__uint2float_rn(w01), v01, s);
+    s = fmaf(__uint2float_rn(w10), v10, s);
+    s = fmaf(__uint2float_rn(w00), v00, s);
+    return s;  // times 256
+}
+static_assert(kBoxW * 4 == 144, "sample_window hard-codes the row pitch");
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned mbar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(mbar)
+        : "memory");
+}
+__device__ __forceinline__ void group_sync()  // the window warps only (named barrier 1)
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(kWindowWarps * 32) : "memory");
+}
+
+// ---- two-ended work queue ----------------------------------------------------------------------------------------
+// counters[0]: items handed out from the front (window groups), counters[1]: 32-bin sub-tiles handed out from the back
+// (texture warps); both only ever fetch-add.  claim[item]: 0 free, 1 window group, 2 texture warps -- set by the first
+// taker with a compare-and-swap on the item's own word.  Fronts claim in increasing, backs in decreasing item order, so
+// whoever finds an item claimed by the other side has met it and stops; every item is claimed exactly once.
+constexpr unsigned kClaimWindow = 1u, kClaimTexture = 2u;
+__device__ __forceinline__ int take_front(unsigned* counters, unsigned* claim, unsigned total_items)
+{
+    const unsigned f = atomicAdd(&counters[0], 1u);
+    if (f >= total_items) return -1;
+    return atomicCAS(&claim[f], 0u, kClaimWindow) == 0u ? (int)f : -1;
+}
+// returns the sub-tile index b (item = total_items - 1 - b / kSubTiles) or -1
+__device__ __forceinline__ int take_back(unsigned* counters, unsigned* claim, unsigned total_items)
+{
+    const unsigned b = atomicAdd(&counters[1], 1u);
+    if (b >= total_items * kSubTiles) return -1;
+    const unsigned seen = atomicCAS(&claim[total_items - 1u - b / kSubTiles], 0u, kClaimTexture);
+    return seen == kClaimWindow ? -1 : (int)b;
+}
+
+struct HybridParams {
+    const cudaTextureObject_t* texs;
+    int n_img, n_u, n_v, n_alpha, n_t, post;
+    int groups_a, groups_t;  // items per image = groups_a * groups_t
+    int rmax, nbuf;          // window rows per buffer (multiple of kBoxR), buffers (1 or 2)
+    int mode;                // development: 0 both paths, 1 texture warps only, 2 window warps only
+    unsigned* counters;      // [2], zeroed before the launch
+    unsigned* claim;         // [items], zeroed before the launch
+    unsigned magic;          // 0x4B0000, kept out of the compiler's sight (see sample_window)
+    float* out;
+};
+
+struct ItemBins {
+    int img, ix, iy;
+};
+// item id -> image, and this warp-in-item's bin for the lane (quad tiling: 2 angles x 2 t per quad, 16 t per warp)
+__device__ __forceinline__ ItemBins item_bins(int item, int wi, int lane, const HybridParams& p)
+{
+    ItemBins r;
+    const int per_img = p.groups_a * p.groups_t;
+    r.img = item / per_img;
+    const int rem = item - r.img * per_img;
+    const int tg = rem / p.groups_a, ag = rem - tg * p.groups_a;
+    const int quad = lane >> 2, ql = lane & 3;
+    r.ix = ag * kItemAngles + (wi & 3) * 2 + (ql & 1);
+    r.iy = tg * kItemT + (wi >> 2) * 16 + quad * 2 + (ql >> 1);
+    return r;
+}
+
+template <int MAXTHREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
+radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_constant__ CUtensorMap map_t,
+                    const HybridParams p)
+{
+    extern __shared__ __align__(128) unsigned char window_raw[];
+    __shared__ __align__(8) unsigned long long mbar_store[2];
+    __shared__ int s_item, s_jmin, s_jmax, s_fallback;
+    __shared__ int win_lo[kMaxChunks], win_hi[kMaxChunks];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned total_items = (unsigned)(p.n_img * p.groups_a * p.groups_t);
+    const float n_u = (float)p.n_u, n_v = (float)p.n_v;
+    const size_t img_stride = (size_t)p.n_t * p.n_alpha;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar_store[0]), 1);
+        mbar_init(smem_u32(&mbar_store[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= kWindowWarps) {
+        if (p.mode == 2) return;
+        // ---------------- texture warps: 32-bin sub-tiles from the back of the queue ----------------
+        for (;;) {
+            int sub = 0;
+            if (lane == 0) sub = take_back(p.counters, p.claim, total_items);
+            sub = __shfl_sync(0xffffffffu, sub, 0);
+            if (sub < 0) break;
+            const int item = (int)total_items - 1 - sub / kSubTiles;
+            const ItemBins B = item_bins(item, sub % kSubTiles, lane, p);
+            if (B.ix >= p.n_alpha || B.iy >= p.n_t) continue;
+            const BinLine L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
+            float r = 0.f;
+            if (L.valid) r = post_process(bin_texture(p.texs[B.img], L), p.post);
+            p.out[B.img * img_stride + (size_t)B.iy * p.n_alpha + B.ix] = r;
+        }
+        return;
+    }
+
+    // ---------------- window warps: whole items from the front of the queue ----------------
+    if (p.mode == 1) return;
+    const unsigned window_base = smem_u32(window_raw);
+    const unsigned buf_bytes = (unsigned)p.rmax * kBoxW * 4u;
+    const unsigned mbar0 = smem_u32(&mbar_store[0]);
+    unsigned phase0 = 0, phase1 = 0;
+    for (;;) {
+        if (tid == 0) {
+            s_item = take_front(p.counters, p.claim, total_items);
+            s_jmin = INT_MAX;
+            s_jmax = INT_MIN;
+            s_fallback = 0;
+        }
+        if (tid < kMaxChunks) { win_lo[tid] = INT_MAX; win_hi[tid] = INT_MIN; }
+        group_sync();
+        const int item = s_item;
+        if (item < 0) break;
+        const ItemBins B = item_bins(item, warp, lane, p);
+        const bool in_range = B.ix < p.n_alpha && B.iy < p.n_t;
+        BinLine L;
+        L.valid = false;
+        L.swapped = false;
+        if (in_range) L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
+        // the window path has no clamp addressing: it takes the lines that stay inside the inset box (all but a few at
+        // the image border: lines that miss the box, and axis-parallel lines, which the reference does not clip)
+        bool safe = false;
+        if (in_range && L.valid) {
+            const float ax = L.o0 + L.t * L.d0, ay = L.o1 + L.t * L.d1, bx = L.o0 + L.t_max * L.d0, by = L.o1 + L.t_max * L.d1;
+            const float lo = 1.f - 1e-3f, hx = n_u - 1.f + 1e-3f, hy = n_v - 1.f + 1e-3f;
+            safe = !L.swapped && fminf(ax, bx) >= lo && fmaxf(ax, bx) <= hx && fminf(ay, by) >= lo && fmaxf(ay, by) <= hy;
+        }
+        const bool live = safe;
+
+        // orientation of the item: primary axis = the one the lines advance along fastest (from the item's middle angle)
+        const int per_img = p.groups_a * p.groups_t;
+        const int ag = (item % per_img) % p.groups_a;
+        const float alpha_mid = ((ag * kItemAngles + 0.5f * (kItemAngles - 1)) / (float)p.n_alpha - 0.5f) * ECC_PI_F;
+        const bool vertical = fabsf(sinf(alpha_mid)) > fabsf(cosf(alpha_mid));
+        const int dir = (vertical && alpha_mid < 0.f) ? -1 : 1;
+
+        // line A of the bin in texel space, exactly as the reference forms it; line B = A + (d1, -d0)
+        float oA0 = L.o0 + 0.5f, oA1 = L.o1 + 0.5f;
+        oA0 -= 0.5f * L.d1;
+        oA1 += 0.5f * L.d0;
+        const float op = vertical ? oA1 : oA0, dp = vertical ? L.d1 : L.d0;
+        const float os = vertical ? oA0 : oA1, ds = vertical ? L.d0 : L.d1;
+        const float offp = vertical ? -L.d0 : L.d1, offs = vertical ? L.d1 : -L.d0;
+        const float inv_dp = live ? 1.f / dp : 0.f;
+
+        // chunks this line touches (by line A's primary pixel coordinate), one spare either side
+        int jmin_l = INT_MAX, jmax_l = INT_MIN;
+        if (live) {
+            const float pa = fmaf(L.t, dp, op) - 0.5f, pb = fmaf(L.t_max, dp, op) - 0.5f;
+            const int ja = (int)floorf(fminf(pa, pb) * (1.f / kChunk)), jb = (int)floorf(fmaxf(pa, pb) * (1.f / kChunk));
+            jmin_l = ja - 1;
+            jmax_l = jb + 1;
+        }
+        {
+            const int wmin = __reduce_min_sync(0xffffffffu, jmin_l), wmax = __reduce_max_sync(0xffffffffu, jmax_l);
+            if (lane == 0 && wmin <= wmax) { atomicMin(&s_jmin, wmin + 1); atomicMax(&s_jmax, wmax - 1); }
+        }
+        group_sync();
+        const int jlo = s_jmin, jhi = s_jmax;
+        const int n_chunks = jhi - jlo + 1;  // <= 0: no live line in this item
+        const bool too_long = n_chunks > kMaxChunks;
+
+        // row window of every chunk: rows (secondary axis) any of the group's lines needs there
+        if (n_chunks > 0 && !too_long) {
+            for (int k = 0; k < n_chunks; k++) {
+                const int j = jlo + k;
+                int lo = INT_MAX, hi = INT_MIN;
+                if (live && j >= jmin_l && j <= jmax_l) {
+                    const float t0 = ((float)(j * kChunk - 2) + 0.5f - op) * inv_dp;
+                    const float t1 = ((float)(j * kChunk + kChunk + 2) + 0.5f - op) * inv_dp;
+                    const float s0 = fmaf(fmaxf(fminf(t0, t1), L.t - 2.f), ds, os);
+                    const float s1 = fmaf(fminf(fmaxf(t0, t1), L.t_max + 2.f), ds, os);
+                    // line B is within one pixel of line A; a sample at s reads rows floor(s - 1/2) and the next
+                    lo = (int)floorf(fminf(s0, s1) - 2.0f);
+                    hi = (int)floorf(fmaxf(s0, s1) + 1.0f) + 1;
+                }
+                const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+                if (lane == 0 && wlo <= whi) { atomicMin(&win_lo[k], wlo); atomicMax(&win_hi[k], whi); }
+            }
+        }
+        group_sync();
+        if (n_chunks > 0 && !too_long && tid < n_chunks) {
+            if (win_lo[tid] <= win_hi[tid] && win_hi[tid] - win_lo[tid] + 1 > p.rmax) s_fallback = 1;
+        }
+        if (tid == 0 && too_long) s_fallback = 1;
+        group_sync();
+        const bool fallback = s_fallback != 0;
+
+        float result = 0.f;
+        if (n_chunks > 0 && !fallback) {
+            const CUtensorMap* map = vertical ? &map_t : &map_n;
+            float t = live ? L.t : 3.0e38f;
+            const float t_max = live ? L.t_max : -3.0e38f;
+            float sum = 0.f, sumo = 0.f;
+            // issue the loads of chunk k (traversal order) into buffer k % nbuf
+            auto issue = [&](int k) {
+                const int kk = dir > 0 ? k : n_chunks - 1 - k;
+                const int lo = win_lo[kk], hi = win_hi[kk];
+                if (lo > hi) return;
+                const int boxes = (hi - lo + kBoxR) / kBoxR;
+                const unsigned b = (p.nbuf == 2) ? (unsigned)(k & 1) : 0u;
+                const unsigned mb = mbar0 + 8u * b;
+                mbar_expect_tx(mb, (unsigned)boxes * kBoxR * kBoxW * 4u);
+                for (int q = 0; q < boxes; q++)
+                    tma_load_3d(window_base + b * buf_bytes + (unsigned)q * kBoxR * kBoxW * 4u, map,
+                                (jlo + kk) * kChunk - kBoxLead, lo + q * kBoxR, B.img, mb);
+            };
+            if (p.nbuf == 2 && tid == 0) issue(0);
+            for (int k = 0; k < n_chunks; k++) {
+                const int kk = dir > 0 ? k : n_chunks - 1 - k;
+                const int j = jlo + kk;
+                const int lo = win_lo[kk], hi = win_hi[kk];
+                if (p.nbuf == 2) {
+                    group_sync();  // everybody is done with the buffer chunk k+1 will overwrite
+                    if (tid == 0 && k + 1 < n_chunks) issue(k + 1);
+                } else {
+                    group_sync();
+                    if (tid == 0) issue(k);
+                }
+                if (lo > hi) continue;  // nobody samples in this chunk
+                const unsigned b = (p.nbuf == 2) ? (unsigned)(k & 1) : 0u;
+                if (b == 0) { mbar_wait(mbar0, phase0); phase0 ^= 1u; }
+                else { mbar_wait(mbar0 + 8u, phase1); phase1 ^= 1u; }
+                // this chunk's samples: t up to where line A leaves the chunk (the last chunk takes the rest)
+                float lim = t_max;
+                if (k + 1 < n_chunks) {
+                    const float edge = (float)(dir > 0 ? (j + 1) * kChunk : j * kChunk) + 0.5f;
+                    lim = fminf(t_max, (edge - op) * inv_dp);
+                }
+                const unsigned base = window_base + b * buf_bytes -
+                                      4u * ((p.magic + (unsigned)lo) * kBoxW + p.magic + (unsigned)(j * kChunk - kBoxLead));
+                for (; t <= lim; t += kStep) {
+                    const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
+                    sum = fmaf(sample_window(base, pri, sec), 0.00390625f, sum);
+                    sumo = fmaf(sample_window(base, pri + offp, sec + offs), 0.00390625f, sumo);
+                }
+            }
+            result = (sum - sumo) * kStep;
+        }
+        if (in_range) {
+            // the (rare) lines outside the window path: items too long / too tall for the window, and lines that miss
+            // the inset box (they may sample outside the image: clamp addressing)
+            if (L.valid && (fallback || !safe)) result = bin_texture(p.texs[B.img], L);
+            p.out[B.img * img_stride + (size_t)B.iy * p.n_alpha + B.ix] = L.valid ? post_process(result, p.post) : 0.f;
+        }
+        group_sync();  // s_item / tables are rewritten at the top
+    }
+}
+
+// ---- image staging for the window path ------------------------------------------------------------------------------
+// padded copy [n][n_v+1][pitch_n] (pixel (x,y) at [y][x]) and transposed padded copy [n][n_u+1][pitch_t] ([x][y]);
+// entries past the last row / column replicate the edge (clamp addressing of the reference's texture).
+__global__ void pad_kernel(const float* __restrict__ src, int n_u, int n_v, int pitch, float* __restrict__ dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= pitch) return;
+    const float* s = src + (size_t)blockIdx.z * n_u * n_v;
+    dst[((size_t)blockIdx.z * (n_v + 1) + y) * pitch + x] = s[(size_t)min(y, n_v - 1) * n_u + min(x, n_u - 1)];
+}
+__global__ void pad_transpose_kernel(const float* __restrict__ src, int n_u, int n_v, int pitch, float* __restrict__ dst)
+{
+    __shared__ float tile[32][33];
+    const float* s = src + (size_t)blockIdx.z * n_u * n_v;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+        tile[r][threadIdx.x] = s[(size_t)min(y0 + r, n_v - 1) * n_u + min(x0 + threadIdx.x, n_u - 1)];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int x = x0 + r, y = y0 + threadIdx.x;  // output row = x, column = y
+        if (x <= n_u && y < pitch) dst[((size_t)blockIdx.z * (n_u + 1) + x) * pitch + y] = tile[threadIdx.x][r];
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(ecc_context* ctx, CUtensorMap* map, float* base, int pitch, int rows, int count)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ECC_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+        if (!sym || q != cudaDriverEntryPointSuccess) return fail(ctx, ECC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        fn = (EncodeTiledFn)sym;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)count};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4u, (cuuint64_t)pitch * rows * 4u};
+    const cuuint32_t box[3] = {kBoxW, kBoxR, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, ECC_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return ECC_OK;
+}
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+void free_hybrid(ecc_context* ctx)
+{
+    HybridStage& H = ctx->hybrid;
+    if (H.pad_n) cudaFree(H.pad_n);
+    if (H.pad_t) cudaFree(H.pad_t);
+    if (H.queue) cudaFree(H.queue);
+    H = HybridStage();
+}
+
+// One launch over n images whose texture objects are texs_d[0..n) and whose pixels are images_d (dense, device).
+int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, const float* images_d, int n, int n_u,
+                        int n_v, int n_alpha, int n_t, int post, float* out_d)
+{
+    HybridStage& H = ctx->hybrid;
+    const int pitch_n = (n_u + 1 + 3) & ~3, pitch_t = (n_v + 1 + 3) & ~3;
+    if (H.n_u != n_u || H.n_v != n_v || H.count < n) {
+        const int count = n > H.count ? n : H.count;
+        free_hybrid(ctx);
+        ECC_CUDA(ctx, cudaMalloc(&H.pad_n, sizeof(float) * (size_t)count * (n_v + 1) * pitch_n));
+        ECC_CUDA(ctx, cudaMalloc(&H.pad_t, sizeof(float) * (size_t)count * (n_u + 1) * pitch_t));
+        H.n_u = n_u;
+        H.n_v = n_v;
+        H.count = count;
+        static_assert(sizeof(CUtensorMap) == sizeof(H.map_n), "tensor map storage");
+        int rc = encode_map(ctx, (CUtensorMap*)H.map_n, H.pad_n, pitch_n, n_v + 1, count);
+        if (rc) return rc;
+        rc = encode_map(ctx, (CUtensorMap*)H.map_t, H.pad_t, pitch_t, n_u + 1, count);
+        if (rc) return rc;
+    }
+    pad_kernel<<<dim3((pitch_n + 127) / 128, n_v + 1, n), 128, 0, ctx->stream>>>(images_d, n_u, n_v, pitch_n, H.pad_n);
+    pad_transpose_kernel<<<dim3((n_u + 1 + 31) / 32, (pitch_t + 31) / 32, n), dim3(32, 8), 0, ctx->stream>>>(images_d, n_u, n_v, pitch_t, H.pad_t);
+
+    HybridParams P;
+    P.texs = texs_d;
+    P.n_img = n;
+    P.n_u = n_u;
+    P.n_v = n_v;
+    P.n_alpha = n_alpha;
+    P.n_t = n_t;
+    P.post = post;
+    P.groups_a = (n_alpha + kItemAngles - 1) / kItemAngles;
+    P.groups_t = (n_t + kItemT - 1) / kItemT;
+    // development knobs (environment): texture warps per CTA, window rows, buffers, CTAs per SM
+    static const int nt = env_int("ECC_HYBRID_NT", 4);
+    static const int rmax = (env_int("ECC_HYBRID_RMAX", 192) + kBoxR - 1) / kBoxR * kBoxR;
+    static const int nbuf = env_int("ECC_HYBRID_NBUF", 1) == 2 ? 2 : 1;
+    static const int ctas = env_int("ECC_HYBRID_CTAS", 4);
+    static const int mode = env_int("ECC_HYBRID_MODE", 0);
+    P.mode = mode;
+    P.rmax = rmax;
+    P.nbuf = nbuf;
+    const size_t queue_words = 2 + (size_t)n * P.groups_a * P.groups_t;
+    if (H.queue_words < queue_words) {
+        if (H.queue) cudaFree(H.queue);
+        H.queue = nullptr;
+        H.queue_words = 0;
+        ECC_CUDA(ctx, cudaMalloc(&H.queue, sizeof(unsigned) * queue_words));
+        H.queue_words = queue_words;
+    }
+    ECC_CUDA(ctx, cudaMemsetAsync(H.queue, 0, sizeof(unsigned) * queue_words, ctx->stream));
+    P.counters = H.queue;
+    P.claim = H.queue + 2;
+    P.magic = 0x4B0000u;
+    P.out = out_d;
+    const int threads = (kWindowWarps + nt) * 32;
+    const size_t smem = (size_t)rmax * kBoxW * 4 * nbuf;
+    const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;
+    const CUtensorMap& mt = *(const CUtensorMap*)H.map_t;
+    const int slot = prof_begin(ctx, FAM_RADON);
+    if (threads <= 384 && ctas >= 4) {
+        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid_kernel<384, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        radon_hybrid_kernel<384, 4><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
+    } else if (threads <= 512 && ctas >= 3) {
+        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid_kernel<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        radon_hybrid_kernel<512, 3><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
+    } else {
+        if (threads > 768) return fail(ctx, ECC_ERR_INVALID, "ECC_HYBRID_NT too large");
+        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid_kernel<768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        radon_hybrid_kernel<768, 2><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
+    }
+    prof_end(ctx, slot);
+    ECC_CUDA(ctx, cudaGetLastError());
+    return ECC_OK;
+}
+
+}  // namespace eccb200

@@ -58,8 +58,12 @@ enum { ECC_POST_IDENTITY = 0, ECC_POST_SQRT = 1, ECC_POST_LOG = 2 };
 /* Bilinear interpolation flavour.
  * ECC_INTERP_TEXTURE: the GPU's texture filter (1.8 fixed-point weights) exactly as the reference
  *   CUDA path uses it (LibUtilsCuda/CudaBindlessTexture.cpp:36-40) -- the drop-in default.
- * ECC_INTERP_EXACT: full fp32 weights (the "CPU float path" numerics). */
-enum { ECC_INTERP_TEXTURE = 0, ECC_INTERP_EXACT = 1 };
+ * ECC_INTERP_EXACT: full fp32 weights (the "CPU float path" numerics).
+ * ECC_INTERP_HYBRID (ecc_radon_compute only): the texture filter's arithmetic -- same sample positions, same 1.8
+ *   fixed-point weights -- with part of the bins sampled from shared memory instead of through the texture unit, so
+ *   that both sampling pipes of an SM work at once.  Bins differ from ECC_INTERP_TEXTURE by the rounding of the
+ *   filter's internal sum only (measured <= 1e-5 of the peak, tolerance 1e-4). */
+enum { ECC_INTERP_TEXTURE = 0, ECC_INTERP_EXACT = 1, ECC_INTERP_HYBRID = 2 };
 
 typedef struct ecc_context ecc_context;
 
