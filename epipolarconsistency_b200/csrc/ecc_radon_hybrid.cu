@@ -13,7 +13,7 @@
 //     back, so the split between the two pipes balances itself.
 //   * a window group walks its 256 lines (two per bin) in lock step through 28-pixel chunks of the image along the
 //     lines' primary axis; the band of rows all lines need inside a chunk is fetched by TMA (cp.async.bulk.tensor,
-//     36-column x 32-row boxes, zero fill outside) into shared memory, double buffered behind an mbarrier.  Near-
+//     one 200-row x 36-column box, zero fill outside) into shared memory, double buffered behind an mbarrier.  Near-
 //     vertical angles read a transposed copy of the image, so the code path is the same.
 //   * sample positions are the reference's, bit for bit (clipped entry, t += 0.66f in fp32, +-1/2 px lines).
 #include <cuda.h>
@@ -37,7 +37,8 @@ constexpr int kChunk = 28;           // pixels of the primary axis per chunk
 constexpr int kBoxW = 36;            // window columns [28j-4, 28j+32): chunk + 2 either side, start a multiple of 4
                                      // (TMA: the innermost start coordinate must be 16-byte aligned, tools/tma_probe.cu)
 constexpr int kBoxLead = 4;          // columns in front of the chunk
-constexpr int kBoxR = 32;            // rows per TMA box
+constexpr int kRows = 200;           // window rows (secondary axis) = the contiguous axis of the shared-memory window;
+                                     // 200 = 8 mod 32 words keeps neighbouring columns on different banks
 constexpr int kMaxChunks = 64;       // primary axis up to ~1790 px; longer -> the item goes through the texture unit
 
 struct BinLine {
@@ -127,8 +128,9 @@ __device__ __forceinline__ float bin_texture(cudaTextureObject_t tex, const BinL
 // (coordinate - 1/2) rounded to 1/256 half up -> cell index and 8-bit fractions a, b; weights
 // w11 = (a*b + 128) >> 8, w10 = a - w11, w01 = b - w11, w00 = 256 - a - b + w11, all /256.
 // pri/sec: texel-space coordinates along the window's column / row axis.  base: byte address (shared window) such
-// that cell (ipri, isec) sits at base + 4*((isec + M)*kBoxW + ipri + M) with M = 0x4B0000 (the exponent bits of the
-// rounding constant are left in the index and folded into base).
+// that cell (ipri, isec) sits at base + 4*((ipri + M)*kRows + isec + M) with M = 0x4B0000 (the exponent bits of the
+// rounding constant are left in the index and folded into base).  The secondary axis is the contiguous one: the lanes
+// of a warp are parallel lines 2..3 rows apart at (nearly) the same column, which spreads them over the banks.
 __device__ __forceinline__ float sample_window(unsigned base, float pri, float sec)
 {
     const float Ps = fmaf(pri, 256.f, -127.5f);  // exact: 256*(pri - 1/2) + 1/2
@@ -136,14 +138,14 @@ __device__ __forceinline__ float sample_window(unsigned base, float pri, float s
     const unsigned Pi = __float_as_uint(__fadd_rd(Ps, 8388608.f));  // 0x4B000000 + floor(Ps)
     const unsigned Si = __float_as_uint(__fadd_rd(Ss, 8388608.f));
     const unsigned a = Pi & 255u, b = Si & 255u;
-    const unsigned addr = base + (((Si >> 8) * kBoxW + (Pi >> 8)) << 2);
+    const unsigned addr = base + (((Pi >> 8) * kRows + (Si >> 8)) << 2);
     float v00, v10, v01, v11;
     asm volatile(
         "ld.shared.f32 %0, [%4];\n"
         "ld.shared.f32 %1, [%4+4];\n"
-        "ld.shared.f32 %2, [%4+144];\n"
-        "ld.shared.f32 %3, [%4+148];\n"
-        : "=f"(v00), "=f"(v10), "=f"(v01), "=f"(v11)
+        "ld.shared.f32 %2, [%4+800];\n"
+        "ld.shared.f32 %3, [%4+804];\n"
+        : "=f"(v00), "=f"(v01), "=f"(v10), "=f"(v11)
         : "r"(addr));
     const unsigned w11 = (a * b + 128u) >> 8;
     const unsigned w10 = a - w11, w01 = b - w11, w00 = 256u + w11 - a - b;
@@ -153,7 +155,7 @@ __device__ __forceinline__ float sample_window(unsigned base, float pri, float s
     s = fmaf(__uint2float_rn(w00), v00, s);
     return s;  // times 256
 }
-static_assert(kBoxW * 4 == 144, "sample_window hard-codes the row pitch");
+static_assert(kRows * 4 == 800, "sample_window hard-codes the column pitch");
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -217,7 +219,7 @@ struct HybridParams {
     const cudaTextureObject_t* texs;
     int n_img, n_u, n_v, n_alpha, n_t, post;
     int groups_a, groups_t;  // items per image = groups_a * groups_t
-    int rmax, nbuf;          // window rows per buffer (multiple of kBoxR), buffers (1 or 2)
+    int nbuf;                // window buffers (1 or 2)
     int mode;                // development: 0 both paths, 1 texture warps only, 2 window warps only
     unsigned* counters;      // [2], zeroed before the launch
     unsigned* claim;         // [items], zeroed before the launch
@@ -287,7 +289,7 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
     // ---------------- window warps: whole items from the front of the queue ----------------
     if (p.mode == 1) return;
     const unsigned window_base = smem_u32(window_raw);
-    const unsigned buf_bytes = (unsigned)p.rmax * kBoxW * 4u;
+    const unsigned buf_bytes = (unsigned)kRows * kBoxW * 4u;
     const unsigned mbar0 = smem_u32(&mbar_store[0]);
     unsigned phase0 = 0, phase1 = 0;
     for (;;) {
@@ -370,7 +372,11 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
         }
         group_sync();
         if (n_chunks > 0 && !too_long && tid < n_chunks) {
-            if (win_lo[tid] <= win_hi[tid] && win_hi[tid] - win_lo[tid] + 1 > p.rmax) s_fallback = 1;
+            // the window's first row must be a multiple of 4 (TMA: 16-byte aligned start along the contiguous axis)
+            if (win_lo[tid] <= win_hi[tid]) {
+                win_lo[tid] &= ~3;
+                if (win_hi[tid] - win_lo[tid] + 1 > kRows) s_fallback = 1;
+            }
         }
         if (tid == 0 && too_long) s_fallback = 1;
         group_sync();
@@ -378,7 +384,8 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
 
         float result = 0.f;
         if (n_chunks > 0 && !fallback) {
-            const CUtensorMap* map = vertical ? &map_t : &map_n;
+            // the copy whose contiguous axis is the window's secondary axis
+            const CUtensorMap* map = vertical ? &map_n : &map_t;
             float t = live ? L.t : 3.0e38f;
             const float t_max = live ? L.t_max : -3.0e38f;
             float sum = 0.f, sumo = 0.f;
@@ -387,13 +394,10 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
                 const int kk = dir > 0 ? k : n_chunks - 1 - k;
                 const int lo = win_lo[kk], hi = win_hi[kk];
                 if (lo > hi) return;
-                const int boxes = (hi - lo + kBoxR) / kBoxR;
                 const unsigned b = (p.nbuf == 2) ? (unsigned)(k & 1) : 0u;
                 const unsigned mb = mbar0 + 8u * b;
-                mbar_expect_tx(mb, (unsigned)boxes * kBoxR * kBoxW * 4u);
-                for (int q = 0; q < boxes; q++)
-                    tma_load_3d(window_base + b * buf_bytes + (unsigned)q * kBoxR * kBoxW * 4u, map,
-                                (jlo + kk) * kChunk - kBoxLead, lo + q * kBoxR, B.img, mb);
+                mbar_expect_tx(mb, buf_bytes);
+                tma_load_3d(window_base + b * buf_bytes, map, lo, (jlo + kk) * kChunk - kBoxLead, B.img, mb);
             };
             if (p.nbuf == 2 && tid == 0) issue(0);
             for (int k = 0; k < n_chunks; k++) {
@@ -418,7 +422,7 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
                     lim = fminf(t_max, (edge - op) * inv_dp);
                 }
                 const unsigned base = window_base + b * buf_bytes -
-                                      4u * ((p.magic + (unsigned)lo) * kBoxW + p.magic + (unsigned)(j * kChunk - kBoxLead));
+                                      4u * ((p.magic + (unsigned)(j * kChunk - kBoxLead)) * kRows + p.magic + (unsigned)lo);
                 for (; t <= lim; t += kStep) {
                     const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
                     sum = fmaf(sample_window(base, pri, sec), 0.00390625f, sum);
@@ -477,7 +481,7 @@ int encode_map(ecc_context* ctx, CUtensorMap* map, float* base, int pitch, int r
     }
     const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)count};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4u, (cuuint64_t)pitch * rows * 4u};
-    const cuuint32_t box[3] = {kBoxW, kBoxR, 1};
+    const cuuint32_t box[3] = {kRows, kBoxW, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -537,12 +541,10 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
     P.groups_t = (n_t + kItemT - 1) / kItemT;
     // development knobs (environment): texture warps per CTA, window rows, buffers, CTAs per SM
     static const int nt = env_int("ECC_HYBRID_NT", 4);
-    static const int rmax = (env_int("ECC_HYBRID_RMAX", 192) + kBoxR - 1) / kBoxR * kBoxR;
     static const int nbuf = env_int("ECC_HYBRID_NBUF", 1) == 2 ? 2 : 1;
     static const int ctas = env_int("ECC_HYBRID_CTAS", 4);
     static const int mode = env_int("ECC_HYBRID_MODE", 0);
     P.mode = mode;
-    P.rmax = rmax;
     P.nbuf = nbuf;
     const size_t queue_words = 2 + (size_t)n * P.groups_a * P.groups_t;
     if (H.queue_words < queue_words) {
@@ -558,7 +560,7 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
     P.magic = 0x4B0000u;
     P.out = out_d;
     const int threads = (kWindowWarps + nt) * 32;
-    const size_t smem = (size_t)rmax * kBoxW * 4 * nbuf;
+    const size_t smem = (size_t)kRows * kBoxW * 4 * nbuf;
     const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;
     const CUtensorMap& mt = *(const CUtensorMap*)H.map_t;
     const int slot = prof_begin(ctx, FAM_RADON);
