@@ -125,8 +125,10 @@ def run_b200(args):
     ctx.set_object_radius(0.0)
     ctx.set_epipolar_plane_step(float(np.deg2rad(W["dkappa_deg"])))
 
+    radon_interp = {"hybrid": api.INTERP_HYBRID, "texture": api.INTERP_TEXTURE, "exact": api.INTERP_EXACT}[args.radon]
+
     def step(src_images, want_cost_on_host):
-        full = pipe.radon_allgather(src_images, n, n_a, n_t)
+        full = pipe.radon_allgather(src_images, n, n_a, n_t, interp=radon_interp)
         ctx.set_radon_intermediates(full, n_u, n_v, True)
         ctx.set_projection_matrices(Ps)
         cost_dev.zero_()
@@ -201,7 +203,9 @@ def run_b200(args):
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic: analytic 5-ellipsoid phantom, circular cone-beam trajectory, cosine weighted; generated on device",
-            "config": {"workload": W["name"], "projections": n, "pairs": n_pairs, "interpolation": "texture (reference CUDA numerics)",
+            "config": {"workload": W["name"], "projections": n, "pairs": n_pairs, "interpolation": {"hybrid": "texture-filter arithmetic (reference CUDA numerics); Radon samples split between the texture unit and a shared-memory path with the same 1.8 fixed-point weights",
+                                         "texture": "texture unit (reference CUDA numerics, bit-identical Radon bins)",
+                                         "exact": "Radon with exact fp32 weights; metric through the texture unit"}[args.radon],
                        "sharding": f"projections block-sharded over {world} GPU(s), pairs partitioned by equal kappa samples",
                        "l2": "inputs larger than L2 (%.2f GB images + %.2f GB dtrs per step)" % (n * n_u * n_v * 4 / 1e9, n * n_a * n_t * 4 / 1e9)},
             "stages": {"radon_intermediates_per_s": world * (hi - lo) / ((radon_ms / args.steps) * 1e-3) if radon_ms > 0 else None,
@@ -214,7 +218,7 @@ def run_b200(args):
                     "mean_ecc": mean_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "radon_kernel (texture-unit bound; algorithmic tap bytes vs HBM copy peak)",
+            "roofline": {"bound": "hbm", "kernel": ("radon_hybrid_kernel (texture data pipe + issue-slot bound; " if args.radon == "hybrid" else "radon_kernel (texture-unit bound; ") + "algorithmic tap bytes vs HBM copy peak)",
                          "achieved": radon_gbs, "peak": peak, "unit": "GB/s", "frac": radon_gbs / peak, "peak_source": peak_src,
                          "traffic": None,
                          "samples_per_s": radon_gbs * 1e9 / 16.0,
@@ -325,6 +329,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--radon", default="hybrid", choices=["hybrid", "texture", "exact"],
+                    help="Radon engine: hybrid (texture unit + shared-memory path, default), texture (bit-identical to the reference kernel), exact")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

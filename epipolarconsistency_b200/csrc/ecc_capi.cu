@@ -229,6 +229,10 @@ void ecc_destroy(ecc_context* ctx)
     destroy_dtr_textures(ctx);
     free_image_pool(ctx);
     free_hybrid(ctx);
+    if (ctx->copy_stream) {
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int b = 0; b < 2; b++) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_consumed[b]); }
+    }
     auto it = batch_buffers().find(ctx);
     if (it != batch_buffers().end()) {
         cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d); cudaFree(it->second.radii_d);
@@ -285,23 +289,47 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
     const bool in_dev = is_device_pointer(images), out_dev = is_device_pointer(dtrs_out);
     const size_t img_elems = (size_t)n_u * n_v, dtr_elems = (size_t)n_alpha * n_t;
     if (in_dev && out_dev) return radon_batch(ctx, images, n_images, n_u, n_v, n_alpha, n_t, filter, post, interp, dtrs_out);
-    // Host memory on either side: stream the batch through device staging in chunks.
+    // Host memory on either side: stream the batch through device staging in chunks.  Host images go through two
+    // staging buffers on a copy stream of their own, so that the upload of chunk i+1 runs under the kernels of chunk i
+    // (the first chunk is small: its upload is the only one that is exposed).
     const int chunk = n_images < 32 ? n_images : 32;
+    const int first_chunk = (!in_dev && n_images > 8) ? 8 : chunk;
     int rc;
-    if (!in_dev && (rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * img_elems * chunk))) return rc;
+    if (!in_dev && (rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * img_elems * chunk * 2))) return rc;
     if (!out_dev && (rc = ensure_bytes(ctx, (void**)&ctx->out_stage_d, &ctx->out_stage_bytes, sizeof(float) * dtr_elems * chunk))) return rc;
-    for (int first = 0; first < n_images; first += chunk) {
-        const int n = (n_images - first < chunk) ? n_images - first : chunk;
+    if (!in_dev && !ctx->copy_stream) {
+        ECC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            ECC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+            ECC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming));
+        }
+    }
+    if (!in_dev) {
+        // the staging buffers may still be read by work queued earlier on the compute stream
+        ECC_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+        ECC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
+    }
+    int k = 0;
+    for (int first = 0; first < n_images; k++) {
+        const int want = (k == 0) ? first_chunk : chunk;
+        const int n = (n_images - first < want) ? n_images - first : want;
         const float* src = images + (size_t)first * img_elems;
+        const int b = k & 1;
         if (!in_dev) {
-            ECC_CUDA(ctx, cudaMemcpyAsync(ctx->img_stage_d, src, sizeof(float) * img_elems * n, cudaMemcpyHostToDevice, ctx->stream));
-            src = ctx->img_stage_d;
+            float* stage = ctx->img_stage_d + (size_t)b * img_elems * chunk;
+            if (k >= 2) ECC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+            ECC_CUDA(ctx, cudaMemcpyAsync(stage, src, sizeof(float) * img_elems * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ECC_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+            ECC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+            src = stage;
         }
         float* dst = out_dev ? dtrs_out + (size_t)first * dtr_elems : ctx->out_stage_d;
         rc = radon_batch(ctx, src, n, n_u, n_v, n_alpha, n_t, filter, post, interp, dst);
         if (rc) return rc;
+        if (!in_dev) ECC_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
         if (!out_dev)
             ECC_CUDA(ctx, cudaMemcpyAsync(dtrs_out + (size_t)first * dtr_elems, dst, sizeof(float) * dtr_elems * n, cudaMemcpyDeviceToHost, ctx->stream));
+        first += n;
     }
     ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ECC_OK;

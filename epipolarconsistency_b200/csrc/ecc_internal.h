@@ -45,6 +45,8 @@ struct ecc_context {
     int device = 0;
     cudaStream_t stream = nullptr;      // stream all work is issued on
     cudaStream_t own_stream = nullptr;  // created by ecc_create
+    cudaStream_t copy_stream = nullptr; // uploads of host images under the Radon kernels (created on first use)
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     int sm_count = 148;
     std::string last_error;
 

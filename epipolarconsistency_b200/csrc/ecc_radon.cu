@@ -257,7 +257,7 @@ void free_image_pool(ecc_context* ctx)
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
                 int n_alpha, int n_t, int filter, int post, int interp, float* out_d)
 {
-    constexpr int kPool = 32;
+    constexpr int kPool = 64;  // projections per launch
     const int pool = n_images < kPool ? n_images : kPool;
     int rc = ensure_pool(ctx, n_u, n_v, pool);
     if (rc) return rc;

@@ -88,8 +88,39 @@ __device__ __forceinline__ float post_process(float r, int post)
     return r;
 }
 
-// The whole bin through the texture unit, four steps in flight (the adds of t and of the sums happen in the
-// reference's order; a sample past t_max contributes an exact 0).
+// Which samples a bin takes.  The source loop is `for (t = t_min; t <= t_max; t += 0.66f)`, but what the reference's
+// kernel EXECUTES (nvcc 12.9 -O3, sm_100; ours in ecc_radon.cu compiles to the same control flow, which is why it is
+// bit-identical to it) is that loop unrolled by four with ONE test per block:
+//     if (t + 1.98f <= t_max) do { four samples; t += 4 steps } while (t <= t_max - 1.98f);
+//     if (t + 0.66f <= t_max) { two samples; t += 2 steps }     if (t <= t_max || nothing taken yet) one sample;
+// In exact arithmetic that is the source loop; in fp32 a block's fourth sample can lie an ulp past t_max where the
+// source loop would have stopped (about one bin in 10^4 on rough images, one sample of ~2300).  Both paths of this
+// kernel take exactly the samples of the executed reference: the texture path by having this shape, the window path
+// by walking t ahead once (ref_last_sample) and stopping at the last sample's t.
+__device__ __forceinline__ float ref_last_sample(float t, float t_max)
+{
+    float last = t;
+    bool none_yet = true;
+    if (!(t + 1.98f > t_max)) {
+        const float r3 = t_max - 1.98f;
+#pragma unroll 1
+        do {
+            last = ((t + kStep) + kStep) + kStep;
+            t = last + kStep;
+        } while (!(t > r3));
+        none_yet = false;
+    }
+    const float t1 = t + kStep;
+    if (!(t1 > t_max)) {
+        last = t1;
+        t = t1 + kStep;
+        none_yet = false;
+    }
+    if (t <= t_max || none_yet) last = t;
+    return last;
+}
+
+// The whole bin through the texture unit, in the executed reference's shape (see above); sums in sample order.
 __device__ __forceinline__ float bin_texture(cudaTextureObject_t tex, const BinLine& L)
 {
     float o0 = L.o0 + 0.5f, o1 = L.o1 + 0.5f;  // texel centres
@@ -98,29 +129,38 @@ __device__ __forceinline__ float bin_texture(cudaTextureObject_t tex, const BinL
     o1 += 0.5f * d0;
     float sum = 0.f, sumo = 0.f;
     float t = L.t;
-    while (t <= t_max) {
-        const float t1 = t + kStep, t2 = t1 + kStep, t3 = t2 + kStep;
-        const float a0 = tex2D<float>(tex, o0 + t * d0, o1 + t * d1);
-        const float b0 = tex2D<float>(tex, o0 + t * d0 + d1, o1 + t * d1 - d0);
-        float a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f, a3 = 0.f, b3 = 0.f;
-        if (t1 <= t_max) {
-            a1 = tex2D<float>(tex, o0 + t1 * d0, o1 + t1 * d1);
-            b1 = tex2D<float>(tex, o0 + t1 * d0 + d1, o1 + t1 * d1 - d0);
-        }
-        if (t2 <= t_max) {
-            a2 = tex2D<float>(tex, o0 + t2 * d0, o1 + t2 * d1);
-            b2 = tex2D<float>(tex, o0 + t2 * d0 + d1, o1 + t2 * d1 - d0);
-        }
-        if (t3 <= t_max) {
-            a3 = tex2D<float>(tex, o0 + t3 * d0, o1 + t3 * d1);
-            b3 = tex2D<float>(tex, o0 + t3 * d0 + d1, o1 + t3 * d1 - d0);
-        }
+    bool none_yet = true;
+#define ECC_TEX_A(tt) tex2D<float>(tex, o0 + (tt) * d0, o1 + (tt) * d1)
+#define ECC_TEX_B(tt) tex2D<float>(tex, o0 + (tt) * d0 + d1, o1 + (tt) * d1 - d0)
+    if (!(t + 1.98f > t_max)) {
+        const float r3 = t_max - 1.98f;
+#pragma unroll 1
+        do {
+            const float t1 = t + kStep, t2 = t1 + kStep, t3 = t2 + kStep;
+            const float a0 = ECC_TEX_A(t), b0 = ECC_TEX_B(t), a1 = ECC_TEX_A(t1), b1 = ECC_TEX_B(t1);
+            const float a2 = ECC_TEX_A(t2), b2 = ECC_TEX_B(t2), a3 = ECC_TEX_A(t3), b3 = ECC_TEX_B(t3);
+            sum += a0; sumo += b0;
+            sum += a1; sumo += b1;
+            sum += a2; sumo += b2;
+            sum += a3; sumo += b3;
+            t = t3 + kStep;
+        } while (!(t > r3));
+        none_yet = false;
+    }
+    const float t1 = t + kStep;
+    if (!(t1 > t_max)) {
+        const float a0 = ECC_TEX_A(t), b0 = ECC_TEX_B(t), a1 = ECC_TEX_A(t1), b1 = ECC_TEX_B(t1);
         sum += a0; sumo += b0;
         sum += a1; sumo += b1;
-        sum += a2; sumo += b2;
-        sum += a3; sumo += b3;
-        t = t3 + kStep;
+        t = t1 + kStep;
+        none_yet = false;
     }
+    if (t <= t_max || none_yet) {
+        sum += ECC_TEX_A(t);
+        sumo += ECC_TEX_B(t);
+    }
+#undef ECC_TEX_A
+#undef ECC_TEX_B
     return (sum - sumo) * kStep;
 }
 
@@ -387,7 +427,8 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
             // the copy whose contiguous axis is the window's secondary axis
             const CUtensorMap* map = vertical ? &map_n : &map_t;
             float t = live ? L.t : 3.0e38f;
-            const float t_max = live ? L.t_max : -3.0e38f;
+            // stop at the last sample the executed reference takes (an ulp past t_max at times, see ref_last_sample)
+            const float t_max = live ? ref_last_sample(L.t, L.t_max) : -3.0e38f;
             float sum = 0.f, sumo = 0.f;
             // issue the loads of chunk k (traversal order) into buffer k % nbuf
             auto issue = [&](int k) {
@@ -423,6 +464,7 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
                 }
                 const unsigned base = window_base + b * buf_bytes -
                                       4u * ((p.magic + (unsigned)(j * kChunk - kBoxLead)) * kRows + p.magic + (unsigned)lo);
+#pragma unroll 1  // one test per sample: the compiler's own unrolling of such a loop tests once per block (see ref_last_sample)
                 for (; t <= lim; t += kStep) {
                     const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
                     sum = fmaf(sample_window(base, pri, sec), 0.00390625f, sum);

@@ -119,6 +119,72 @@ def test_radon_batches_larger_than_pool(ctx):
     assert np.array_equal(got, again)
 
 
+# ---- hybrid engine: texture unit + shared-memory window path with the texture filter's arithmetic ----------------
+def test_radon_hybrid_vs_reference_cuda(ctx, scene):
+    if ol.ref_cuda() is None:
+        pytest.skip("oracle/_ref/libecc_ref_cuda.so not present")
+    ref, _ = ol.ref_cuda_radon(scene["imgs"][:4], scene["n_a"], scene["n_t"])
+    got = ctx.radon_compute(scene["imgs"][:4], scene["n_a"], scene["n_t"], interp=api.INTERP_HYBRID)
+    assert peak_err(got, ref) < RADON_TOL
+
+
+@pytest.mark.parametrize("shape", [(160, 128, 192, 192), (150, 100, 100, 90), (64, 200, 33, 47), (97, 31, 8, 130),
+                                   (203, 301, 100, 90), (40, 36, 64, 64)])
+def test_radon_hybrid_vs_texture_engine(ctx, shape):
+    """Same sample positions and the same 1.8 fixed-point weights: only the rounding of the filter's sum differs."""
+    n_u, n_v, n_a, n_t = shape
+    rng = np.random.default_rng(17)
+    img = rng.random((5, n_v, n_u), dtype=np.float32) * 10  # rough everywhere, also at the borders
+    tex = ctx.radon_compute(img, n_a, n_t, interp=api.INTERP_TEXTURE)
+    hyb = ctx.radon_compute(img, n_a, n_t, interp=api.INTERP_HYBRID)
+    assert hyb.shape == (5, n_t, n_a) and np.isfinite(hyb).all()
+    assert peak_err(hyb, tex) < RADON_TOL
+    # bins the lines of which miss the image are exactly 0 in both
+    assert np.array_equal(hyb == 0, tex == 0)
+
+
+@pytest.mark.parametrize("post", [1, 2])
+def test_radon_hybrid_postprocess(ctx, scene, post):
+    im = scene["imgs"][:3]
+    tex = ctx.radon_compute(im, 96, 80, post=post, interp=api.INTERP_TEXTURE)
+    hyb = ctx.radon_compute(im, 96, 80, post=post, interp=api.INTERP_HYBRID)
+    assert peak_err(hyb, tex) < 2e-3  # sqrt/log amplify rounding near zero
+
+
+def test_radon_hybrid_non_derivative_filter_uses_texture_engine(ctx, scene):
+    im = scene["imgs"][:2]
+    a = ctx.radon_compute(im, 96, 80, filter=api.FILTER_NONE, interp=api.INTERP_TEXTURE)
+    b = ctx.radon_compute(im, 96, 80, filter=api.FILTER_NONE, interp=api.INTERP_HYBRID)
+    assert np.array_equal(a, b)
+
+
+def test_radon_hybrid_long_axis_falls_back(ctx):
+    """An image wider than the window path's 64 chunks: those items go through the texture unit, same result."""
+    rng = np.random.default_rng(23)
+    img = rng.random((1, 48, 2100), dtype=np.float32)
+    tex = ctx.radon_compute(img, 64, 96, interp=api.INTERP_TEXTURE)
+    hyb = ctx.radon_compute(img, 64, 96, interp=api.INTERP_HYBRID)
+    assert peak_err(hyb, tex) < RADON_TOL
+
+
+def test_radon_hybrid_full_size_vs_texture_engine(ctx):
+    """BASELINE's full size (1240x960 -> 768x768), phantom + noise: every bin within 1e-4 of the peak."""
+    import torch
+    n, n_u, n_v = 3, 1240, 960
+    Ps = api.make_circular_trajectory(n, 750.0, 1200.0, n_u, n_v, 200.0, 0.308)
+    imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
+    ctx.synth_projections(Ps, n_u, n_v, ELL, imgs)
+    g = torch.Generator(device="cuda").manual_seed(29)
+    imgs += 0.05 * torch.rand(imgs.shape, device="cuda", generator=g)
+    tex = ctx.radon_compute(imgs, 768, 768, interp=api.INTERP_TEXTURE)
+    hyb = ctx.radon_compute(imgs, 768, 768, interp=api.INTERP_HYBRID)
+    err = float((hyb - tex).abs().max() / tex.abs().max())
+    assert err < RADON_TOL
+    # repeatable: the split between the two paths changes from run to run, the arithmetic of a bin is one of two
+    again = ctx.radon_compute(imgs, 768, 768, interp=api.INTERP_HYBRID)
+    assert float((hyb - again).abs().max() / tex.abs().max()) < RADON_TOL
+
+
 def test_radon_linearity_full_size(ctx):
     """Size-independent property at BASELINE's full size (1240x960 -> 768x768): R(a x + b y) = a R(x) + b R(y)."""
     import torch
