@@ -322,6 +322,12 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: anything native libraries write to file descriptor 1 (NCCL prints its
+    # version there) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
