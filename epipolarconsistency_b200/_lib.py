@@ -37,6 +37,7 @@ SIGNATURES = {
     "ecc_get_object_radius": (C.c_int, [c_ctx, C.POINTER(C.c_double)]),
     "ecc_set_epipolar_plane_step": (C.c_int, [c_ctx, C.c_double]),
     "ecc_set_interpolation": (C.c_int, [c_ctx, C.c_int]),
+    "ecc_use_correlation": (C.c_int, [c_ctx, C.c_int]),
     "ecc_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),
     "ecc_evaluate_range": (C.c_int, [c_ctx, C.c_longlong, C.c_longlong, c_vp, C.POINTER(C.c_double)]),
     "ecc_evaluate_indices": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.POINTER(C.c_double)]),

@@ -147,6 +147,9 @@ class Context:
     def set_epipolar_plane_step(self, dkappa):
         self._check(self.lib.ecc_set_epipolar_plane_step(self.h, float(dkappa)))
 
+    def use_correlation(self, on=True):
+        self._check(self.lib.ecc_use_correlation(self.h, int(bool(on))))
+
     def set_interpolation(self, interp):
         self._check(self.lib.ecc_set_interpolation(self.h, int(interp)))
 
@@ -361,8 +364,7 @@ class MetricRadonIntermediate:
         return self.Ps.shape[0]
 
     def useCorrelation(self, corr=True):
-        if corr:
-            raise EccError("correlation mode is not part of the hot path (SURVEY.md row N4)")
+        self.ctx.use_correlation(corr)
         return self
 
     def setInterpolation(self, interp):

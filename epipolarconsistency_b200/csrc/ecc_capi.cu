@@ -154,6 +154,7 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
     L.sample_cap = (max_samples + 255) / 256 * 256;
     L.is_derivative = ctx->is_derivative;
     L.interp = ctx->interp;
+    L.use_corr = ctx->use_corr;
     L.vals_d = nullptr;
     L.image_d = nullptr;
     return ECC_OK;
@@ -229,6 +230,7 @@ void ecc_destroy(ecc_context* ctx)
     destroy_dtr_textures(ctx);
     free_image_pool(ctx);
     free_hybrid(ctx);
+    if (ctx->ramp_g_d) cudaFree(ctx->ramp_g_d);
     if (ctx->copy_stream) {
         cudaStreamDestroy(ctx->copy_stream);
         for (int b = 0; b < 2; b++) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_consumed[b]); }
@@ -280,9 +282,7 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
     Guard g(ctx);
     if (!images || !dtrs_out || n_images < 0 || n_u < 2 || n_v < 2 || n_alpha < 1 || n_t < 1)
         return fail(ctx, ECC_ERR_INVALID, "ecc_radon_compute: bad argument");
-    if (filter == ECC_FILTER_RAMP)
-        return fail(ctx, ECC_ERR_UNSUPPORTED, "ramp filter is not part of the hot path (SURVEY.md row N4)");
-    if (filter != ECC_FILTER_DERIVATIVE && filter != ECC_FILTER_NONE) return fail(ctx, ECC_ERR_INVALID, "bad filter");
+    if (filter != ECC_FILTER_DERIVATIVE && filter != ECC_FILTER_NONE && filter != ECC_FILTER_RAMP) return fail(ctx, ECC_ERR_INVALID, "bad filter");
     if (post < 0 || post > 2) return fail(ctx, ECC_ERR_INVALID, "bad post_process");
     if (interp != ECC_INTERP_TEXTURE && interp != ECC_INTERP_EXACT && interp != ECC_INTERP_HYBRID) return fail(ctx, ECC_ERR_INVALID, "bad interp");
     if (n_images == 0) return ECC_OK;
@@ -560,6 +560,13 @@ int ecc_set_epipolar_plane_step(ecc_context* ctx, double dkappa)
 {
     if (!ctx) return ECC_ERR_INVALID;
     ctx->dkappa = dkappa;
+    return ECC_OK;
+}
+
+int ecc_use_correlation(ecc_context* ctx, int on)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    ctx->use_corr = on ? 1 : 0;
     return ECC_OK;
 }
 

@@ -77,6 +77,7 @@ struct ecc_context {
     double object_radius = 0.0;
     double dkappa = 0.0;
     int interp = ECC_INTERP_TEXTURE;
+    int use_corr = 0;
 
     // ---- scratch ----
     float* vals_d = nullptr;  // one float per evaluated (set,pair)
@@ -97,6 +98,8 @@ struct ecc_context {
     size_t cost_cap = 0;
 
     eccb200::ImagePool pool;
+    float* ramp_g_d = nullptr;  // ramp-filter kernel g[n_t] (ecc_radon.cu)
+    int ramp_n_t = 0;
     eccb200::HybridStage hybrid;
 
     // ---- profiling ----
@@ -147,6 +150,7 @@ struct PairLaunch {
     int sample_cap;
     int is_derivative;
     int interp;
+    int use_corr;  // correlation variant instead of the SSD
     // outputs
     float* vals_d;   // n_sets*n_pairs
     float* image_d;  // all-pairs: n_views*n_views cost image or null (only with n_sets==1)
@@ -165,6 +169,7 @@ int launch_derive_views(ecc_context* ctx, const double* Ps_d, int n, float* Pinv
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
                 int n_alpha, int n_t, int filter, int post, int interp, float* out_d);
 void free_image_pool(ecc_context* ctx);
+int ramp_filter(ecc_context* ctx, float* dtrs_d, int n, int n_alpha, int n_t);
 // ---- launchers (ecc_radon_hybrid.cu) ----
 int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, const float* images_d, int n, int n_u,
                         int n_v, int n_alpha, int n_t, int post, float* out_d);

@@ -10,7 +10,9 @@
 // image side by side (coherent texture footprints, no divergence), and the 8 warps of a CTA are
 // 8 neighbouring angles over the same strip of the image (L1 reuse).  Sample positions follow the
 // reference exactly (clipped entry point, t += 0.66f accumulation, +-1/2 px derivative lines).
+#include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "ecc_geometry.cuh"
 #include "ecc_internal.h"
@@ -177,6 +179,38 @@ radon_kernel_split(const cudaTextureObject_t* __restrict__ images, int n_u_i, in
     }
 }
 
+// Ramp filter along t (reference RadonIntermediate.cu:173-237: batched cuFFT R2C over the columns, bin k multiplied by
+// k * (-0.5f / (n_t * (n_t/2+1))), unnormalised C2R).  That is a circular convolution of every alpha column with the
+// real kernel g[j] = sum_k H_k e^{2 pi i jk/n} (H extended Hermitian); g is tabulated once per n_t on the host in
+// fp64 and applied directly -- O(n_t^2) per column, 0.45 GFLOP per 768x768 intermediate, not on the hot path.
+constexpr int kRampCols = 16;
+__global__ void __launch_bounds__(256)
+ramp_kernel(float* __restrict__ data, const float* __restrict__ g, int n_alpha, int n_t)
+{
+    extern __shared__ float ramp_smem[];
+    float* gs = ramp_smem;                    // [n_t]
+    float* xs = ramp_smem + n_t;              // [n_t][kRampCols]
+    float* img = data + (size_t)blockIdx.y * n_t * n_alpha;
+    const int c0 = blockIdx.x * kRampCols;
+    for (int k = threadIdx.x; k < n_t; k += blockDim.x) gs[k] = g[k];
+    for (int k = threadIdx.x; k < n_t * kRampCols; k += blockDim.x) {
+        const int m = k / kRampCols, c = k - m * kRampCols;
+        xs[k] = (c0 + c < n_alpha) ? img[(size_t)m * n_alpha + c0 + c] : 0.f;
+    }
+    __syncthreads();
+    const int c = threadIdx.x % kRampCols, lane_t = threadIdx.x / kRampCols, lanes = blockDim.x / kRampCols;
+    if (c0 + c >= n_alpha) return;
+    for (int t = lane_t; t < n_t; t += lanes) {
+        float acc = 0.f;
+        int j = t;  // (t - m) mod n_t
+        for (int m = 0; m < n_t; m++) {
+            acc = fmaf(xs[m * kRampCols + c], gs[j], acc);
+            j = (j == 0) ? n_t - 1 : j - 1;
+        }
+        img[(size_t)t * n_alpha + c0 + c] = acc;
+    }
+}
+
 // Work counter: the number of bilinear samples the Radon kernel takes per projection for this geometry (same
 // clipping and the same t += 0.66f walk, no fetches).
 __global__ void radon_count_kernel(int n_u_i, int n_v_i, int n_alpha, int n_t, int lines_per_bin,
@@ -228,6 +262,44 @@ int ensure_pool(ecc_context* ctx, int n_u, int n_v, int count)
 
 }  // namespace
 
+// In-place ramp filter of n intermediates (device memory).
+int ramp_filter(ecc_context* ctx, float* dtrs_d, int n, int n_alpha, int n_t)
+{
+    if (ctx->ramp_n_t != n_t) {
+        // g[j] = H_0 + 2 sum_{0<k<n/2} H_k cos(2 pi jk/n) (+ H_{n/2} (-1)^j for even n), H_k = k * scale in fp32 as the
+        // reference forms it (RadonIntermediate.cu:181-182,218)
+        const int n_theta = n_t / 2 + 1;
+        const float scale = -0.5f / (n_t * n_theta);
+        std::vector<float> g(n_t);
+        const double w = 2.0 * 3.14159265358979323846 / n_t;
+        for (int j = 0; j < n_t; j++) {
+            double acc = 0.0;
+            for (int k = 1; k < n_theta; k++) {
+                const double Hk = (double)((float)k * scale);
+                const long long jk = ((long long)j * k) % n_t;
+                const bool nyquist = (n_t % 2 == 0) && (k == n_t / 2);
+                acc += (nyquist ? 1.0 : 2.0) * Hk * cos(w * (double)jk);
+            }
+            g[j] = (float)acc;
+        }
+        if (ctx->ramp_g_d) cudaFree(ctx->ramp_g_d);
+        ctx->ramp_g_d = nullptr;
+        ctx->ramp_n_t = 0;
+        ECC_CUDA(ctx, cudaMalloc(&ctx->ramp_g_d, sizeof(float) * n_t));
+        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->ramp_g_d, g.data(), sizeof(float) * n_t, cudaMemcpyHostToDevice, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // g lives on this stack frame
+        ctx->ramp_n_t = n_t;
+    }
+    const size_t smem = sizeof(float) * ((size_t)n_t + (size_t)n_t * kRampCols);
+    if (smem > 220 * 1024) return fail(ctx, ECC_ERR_UNSUPPORTED, "ramp filter: n_t too large for the shared-memory tile");
+    ECC_CUDA(ctx, cudaFuncSetAttribute(ramp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int slot = prof_begin(ctx, FAM_RADON);
+    ramp_kernel<<<dim3((n_alpha + kRampCols - 1) / kRampCols, n), 256, smem, ctx->stream>>>(dtrs_d, ctx->ramp_g_d, n_alpha, n_t);
+    prof_end(ctx, slot);
+    ECC_CUDA(ctx, cudaGetLastError());
+    return ECC_OK;
+}
+
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count)
 {
     unsigned long long* total_d = nullptr;
@@ -261,7 +333,7 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
     const int pool = n_images < kPool ? n_images : kPool;
     int rc = ensure_pool(ctx, n_u, n_v, pool);
     if (rc) return rc;
-    const bool deriv = (filter == ECC_FILTER_DERIVATIVE);
+    const bool deriv = (filter == ECC_FILTER_DERIVATIVE);  // ramp: plain line integrals first (RadonIntermediate.cu:160-168)
     for (int first = 0; first < n_images; first += pool) {
         const int n = (n_images - first < pool) ? n_images - first : pool;
         for (int k = 0; k < n; k++) {
@@ -304,6 +376,10 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
         }
         prof_end(ctx, slot);
         ECC_CUDA(ctx, cudaGetLastError());
+        if (filter == ECC_FILTER_RAMP) {
+            const int rc3 = ramp_filter(ctx, dst, n, n_alpha, n_t);
+            if (rc3) return rc3;
+        }
     }
     return ECC_OK;
 }

@@ -45,10 +45,11 @@ public:
         return *this;
     }
 
-    /// Tell Metric to compute correlation instead of SSD.  Not part of the hot path.
+    /// Tell Metric to compute correlation instead of SSD (EpipolarConsistencyRadonIntermediate.h:43): pairs are scored by
+    /// 1 - cc, as the reference's use_corr path forms it.
     MetricRadonIntermediate& useCorrelation(bool corr = true)
     {
-        if (corr) detail::check(ECC_ERR_UNSUPPORTED, 0x0, "useCorrelation(true): correlation mode");
+        detail::check(ecc_use_correlation(ctx, corr ? 1 : 0), ctx, "ecc_use_correlation");
         use_corr = corr;
         return *this;
     }

@@ -48,10 +48,11 @@ enum {
     ECC_ERR_CUDA = -1,        /* a CUDA runtime call failed                       */
     ECC_ERR_INVALID = -2,     /* bad argument                                     */
     ECC_ERR_STATE = -3,       /* matrices / dtrs not set, size mismatch           */
-    ECC_ERR_UNSUPPORTED = -4  /* e.g. ramp filter (reference RadonIntermediate.cu:173-237, "next" row N4) */
+    ECC_ERR_UNSUPPORTED = -4  /* a size the implementation does not cover (e.g. ramp filter with n_t > 3000)   */
 };
 
-/* RadonIntermediate::Filter / PostProcess, LibEpipolarConsistency/RadonIntermediate.h:21-28 */
+/* RadonIntermediate::Filter / PostProcess, LibEpipolarConsistency/RadonIntermediate.h:21-28.  ECC_FILTER_RAMP: plain
+ * line integrals followed by the ramp filter along t (RadonIntermediate.cu:173-237). */
 enum { ECC_FILTER_DERIVATIVE = 0, ECC_FILTER_RAMP = 1, ECC_FILTER_NONE = 2 };
 enum { ECC_POST_IDENTITY = 0, ECC_POST_SQRT = 1, ECC_POST_LOG = 2 };
 
@@ -137,6 +138,10 @@ int ecc_get_object_radius(ecc_context* ctx, double* radius_mm);
 /* Metric::setEpipolarPlaneStep / setdKappa (EpipolarConsistency.cpp:86-89), 0 = automatic. */
 int ecc_set_epipolar_plane_step(ecc_context* ctx, double dkappa_rad);
 int ecc_set_interpolation(ecc_context* ctx, int interp);
+/* MetricRadonIntermediate::useCorrelation (EpipolarConsistencyRadonIntermediate.h:43): every evaluate* call then scores a
+ * pair by 1 - cc, cc the un-centred correlation of the two redundant signals exactly as the reference forms it (weights
+ * kappa_max/kappa per sample, EpipolarConsistencyRadonIntermediate.cu:115-149,209,274; .cpp:127-131) instead of the SSD. */
+int ecc_use_correlation(ecc_context* ctx, int on);
 
 /* ---- Metric evaluation ------------------------------------------------------------------------
  * evaluate(float* cost_image) (EpipolarConsistencyRadonIntermediate.cpp:166-225): all n(n-1)/2

@@ -402,7 +402,7 @@ double oracle_radon_num_samples(int n_u, int n_v, int n_alpha, int n_t, int filt
 double oracle_ecc(const double* Ps, int n_views, const float* dtrs, int n_dtrs, int n_alpha,
                   int n_t, float step_alpha, float step_t, int n_u, int n_v, int is_derivative,
                   double object_radius_mm, double dkappa_d, int interp, int fast_sincos,
-                  const int* idx4, int n_pairs, float* out, int* ksamples)
+                  const int* idx4, int n_pairs, float* out, int* ksamples, int use_corr)
 {
     (void)step_alpha;
     (void)n_dtrs;
@@ -446,7 +446,7 @@ double oracle_ecc(const double* Ps, int n_views, const float* dtrs, int n_dtrs, 
         const float dk = K1[6], kmax = K1[7];
         const float* d0 = dtrs + dtr_len * r0;
         const float* d1 = dtrs + dtr_len * r1;
-        double acc = 0;
+        double acc = 0, sxx = 0, syy = 0, sxy = 0;
         int m = 0;
         // .cu:192-197 / :258-263 kappa grid; .cu:86-113 +/- kappa
         for (; m < sample_cap; m++) {
@@ -454,15 +454,29 @@ double oracle_ecc(const double* Ps, int n_views, const float* dtrs, int n_dtrs, 
             if (kappa >= kmax) break;
             float s, c;
             sincos_model(kappa, fast_sincos, &s, &c);
-            const float vp = redundancy(K0, d0, n_alpha, n_t, range_t, c, s, is_derivative, interp) -
-                             redundancy(K1, d1, n_alpha, n_t, range_t, c, s, is_derivative, interp);
+            const float xp = redundancy(K0, d0, n_alpha, n_t, range_t, c, s, is_derivative, interp);
+            const float yp = redundancy(K1, d1, n_alpha, n_t, range_t, c, s, is_derivative, interp);
             c = -c;  // .cu:106: minus kappa via the oppositely oriented line
-            const float vm = redundancy(K0, d0, n_alpha, n_t, range_t, c, s, is_derivative, interp) -
-                             redundancy(K1, d1, n_alpha, n_t, range_t, c, s, is_derivative, interp);
-            const float consistency = (vp * vp + vm * vm) * K0[6];  // .cu:112
-            acc += (double)(consistency * dk);                      // .cu:204,269 (atomicAdd there)
+            const float xm = redundancy(K0, d0, n_alpha, n_t, range_t, c, s, is_derivative, interp);
+            const float ym = redundancy(K1, d1, n_alpha, n_t, range_t, c, s, is_derivative, interp);
+            if (use_corr) {
+                // .cu:115-149 with the factor the launcher passes for "1/n": kappa_max/kappa (.cu:209,274)
+                const float w = kmax / kappa;
+                sxx += (double)(w * (xp * xp + xm * xm));
+                syy += (double)(w * (yp * yp + ym * ym));
+                sxy += (double)(w * (xp * yp + xm * ym));
+            } else {
+                const float vp = xp - yp, vm = xm - ym;
+                const float consistency = (vp * vp + vm * vm) * K0[6];  // .cu:112
+                acc += (double)(consistency * dk);                      // .cu:204,269 (atomicAdd there)
+            }
         }
-        const float value = (float)acc;
+        float value = (float)acc;
+        if (use_corr) {
+            // cc() and "1 - corr", EpipolarConsistencyRadonIntermediate.cpp:127-131,207-210,304-308 (un-centred)
+            const float xx = (float)sxx, yy = (float)syy, xy = (float)sxy;
+            value = 1.0f - xy / (sqrtf(xx) * sqrtf(yy));
+        }
         if (ksamples) ksamples[p] = m;
         if (out) {
             if (all_pairs) out[p0 + (size_t)p1 * n_views] = value;  // .cu:269

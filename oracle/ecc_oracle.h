@@ -58,7 +58,7 @@ int oracle_line_to_sample(float* line, float range_t);
  * (kernel body) with the image sampled like the reference's texture
  * (LibUtilsCuda/CudaBindlessTexture.cpp:36-40: unnormalised, linear, clamp).
  * img: n_v rows of n_u floats.  out: n_t rows of n_alpha floats (alpha fastest).
- * filter: 0 derivative, 2 none (1 = ramp is not restated).  post: 0 identity, 1 sqrt, 2 log. */
+ * filter: 0 derivative, 2 none (1 = ramp: restated with numpy's FFT in tests/oracle_lib.py::ramp_filter on top of filter 2).  post: 0 identity, 1 sqrt, 2 log. */
 void oracle_radon(const float* img, int n_u, int n_v, int n_alpha, int n_t, int filter, int post,
                   int interp, float* out);
 
@@ -74,11 +74,13 @@ double oracle_radon_num_samples(int n_u, int n_v, int n_alpha, int n_t, int filt
  * out: all-pairs -> n_views*n_views cost image, entry i+j*n_views for i<j, other entries untouched
  *      (may be NULL); pair list -> n_pairs floats (may be NULL).
  * ksamples (may be NULL): number of kappa samples taken per pair.
+ * use_corr: the correlation variant (EpipolarConsistencyRadonIntermediate.cu:115-149, .cpp:127-131): pair value =
+ *   1 - sum(w x y) / (sqrt(sum(w x x)) sqrt(sum(w y y))) with w = kappa_max/kappa, as the reference computes it.
  * Returns the mean over evaluated pairs. */
 double oracle_ecc(const double* Ps, int n_views, const float* dtrs, int n_dtrs, int n_alpha,
                   int n_t, float step_alpha, float step_t, int n_u, int n_v, int is_derivative,
                   double object_radius_mm, double dkappa, int interp, int fast_sincos,
-                  const int* idx4, int n_pairs, float* out, int* ksamples);
+                  const int* idx4, int n_pairs, float* out, int* ksamples, int use_corr);
 
 /* --- synthetic data ------------------------------------------------- */
 

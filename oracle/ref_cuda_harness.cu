@@ -17,6 +17,7 @@
 #include <vector>
 using std::abs;
 #include <LibUtilsCuda/culaut/xprojectionmatrix.hxx>
+#include <LibEpipolarConsistency/EpipolarConsistencyCommon.hxx>  // get_ij (pair enumeration), header-only
 
 // the reference's launchers (C++ linkage, defined in the reference .cu files)
 void computeDerivLineIntegrals(cudaTextureObject_t in, int n_x, int n_y, int n_alpha, int n_t, int filter,
@@ -239,6 +240,54 @@ double ref_cuda_metric_evaluate(void* h, const int* idx4, int n_pairs, float rad
         }
     }
     return pairs ? sum / pairs : 0.0;
+}
+
+// evaluate() with useCorrelation(true): the launcher accumulates six floats per pair (five weighted sums + the pair
+// weight, EpipolarConsistencyRadonIntermediate.cu:115-149,182-189), the host forms 1 - cc per pair
+// (EpipolarConsistencyRadonIntermediate.cpp:127-131,200-211,304-308) and the weighted mean (all weights are 1).
+double ref_cuda_metric_evaluate_corr(void* h, const int* idx4, int n_pairs, float radius, float dkappa, float* out_h)
+{
+    RefMetric* M = (RefMetric*)h;
+    const int n = M->n_views;
+    const bool all = (idx4 == nullptr);
+    const int pairs = all ? n * (n - 1) / 2 : n_pairs;
+    const size_t out_len = all ? (size_t)n * n : (size_t)pairs;
+    if (grow(&M->K01s_d, &M->k01_cap, (size_t)pairs * 16)) return -1;
+    if (grow(&M->out_d, &M->out_cap, out_len)) return -1;
+    if (grow(&M->corr_d, &M->corr_cap, (size_t)pairs * 6)) return -1;
+    cudaMemset(M->out_d, 0, sizeof(float) * out_len);
+    cudaMemset(M->corr_d, 0, sizeof(float) * pairs * 6);
+    if (!all) {
+        if (M->idx_cap < (size_t)pairs * 4) {
+            cudaFree(M->idx_d);
+            cudaMalloc(&M->idx_d, sizeof(int) * 4 * pairs);
+            M->idx_cap = (size_t)pairs * 4;
+        }
+        cudaMemcpy(M->idx_d, idx4, sizeof(int) * 4 * pairs, cudaMemcpyHostToDevice);
+    }
+    epipolarConsistency(M->n_u, M->n_v, M->n_dtrs, (char*)M->tex_d, M->n_alpha, M->n_t, M->step_alpha, M->step_t, n,
+                        M->Cs_d, M->PinvTs_d, all ? 0 : pairs, all ? nullptr : M->idx_d, M->K01s_d, M->out_d, radius,
+                        dkappa, M->is_derivative, true, M->corr_d);
+    std::vector<float> sums((size_t)pairs * 6);
+    cudaMemcpy(sums.data(), M->corr_d, sizeof(float) * pairs * 6, cudaMemcpyDeviceToHost);
+    double weighted = 0, weights = 0;
+    for (int k = 0; k < pairs; k++) {
+        const float* q = &sums[(size_t)6 * k];
+        const float corr = q[4] / (sqrt(q[2]) * sqrt(q[3]));
+        const float weight = q[5];
+        const float v = (1.0f - corr) * weight;
+        if (out_h) {
+            if (all) {
+                short i, j;
+                get_ij(k, n, i, j);
+                out_h[(size_t)i + (size_t)j * n] = v;
+            } else
+                out_h[k] = v;
+        }
+        weighted += v;
+        weights += weight;
+    }
+    return weights > 0 ? weighted / weights : 0.0;
 }
 
 }  // extern "C"

@@ -52,7 +52,7 @@ def oracle():
     L.oracle_radon_num_samples.restype = C.c_double
     L.oracle_ecc.argtypes = [_f64p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                              C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
-                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.oracle_ecc.restype = C.c_double
     L.oracle_circular_trajectory.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                              C.c_double, C.c_double, _f64p]
@@ -106,8 +106,22 @@ def radon(img, n_alpha, n_t, filter=0, post=0, interp=INTERP_EXACT):
     img = np.ascontiguousarray(img, np.float32)
     n_v, n_u = img.shape
     out = np.zeros((n_t, n_alpha), np.float32)
+    if filter == 1:  # ramp = plain line integrals (with post-processing) + ramp filter along t
+        oracle().oracle_radon(img, n_u, n_v, n_alpha, n_t, 2, post, interp, out)
+        return ramp_filter(out)
     oracle().oracle_radon(img, n_u, n_v, n_alpha, n_t, filter, post, interp, out)
     return out
+
+
+def ramp_filter(dtr):
+    """apply1DRampFilter (reference RadonIntermediate.cu:186-237) restated with numpy's FFT: R2C along t for every
+    alpha column, bin k times k * (-0.5f / (n_t * (n_t/2+1))) in fp32 (:181-182,218), unnormalised C2R."""
+    n_t = dtr.shape[0]
+    n_theta = n_t // 2 + 1
+    scale = np.float32(-0.5) / np.float32(n_t * n_theta)
+    H = (np.arange(n_theta, dtype=np.float32) * scale).astype(np.float64)
+    F = np.fft.rfft(dtr.astype(np.float64), axis=0) * H[:, None]
+    return (np.fft.irfft(F, n=n_t, axis=0) * n_t).astype(np.float32)
 
 
 def radon_num_samples(n_u, n_v, n_alpha, n_t, filter=0):
@@ -115,7 +129,7 @@ def radon_num_samples(n_u, n_v, n_alpha, n_t, filter=0):
 
 
 def ecc(Ps, dtrs, n_u, n_v, is_derivative=True, object_radius_mm=0.0, dkappa=0.0,
-        interp=INTERP_EXACT, fast_sincos=False, idx4=None, want_out=True, want_ksamples=False):
+        interp=INTERP_EXACT, fast_sincos=False, idx4=None, want_out=True, want_ksamples=False, use_corr=False):
     """Returns (mean, out, ksamples).  Ps: (n,12) col-major doubles; dtrs: (m, n_t, n_alpha)."""
     Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
     dtrs = np.ascontiguousarray(dtrs, np.float32)
@@ -138,7 +152,7 @@ def ecc(Ps, dtrs, n_u, n_v, is_derivative=True, object_radius_mm=0.0, dkappa=0.0
                                int(is_derivative), float(object_radius_mm), float(dkappa), interp,
                                int(fast_sincos), idx_ptr, n_pairs,
                                out.ctypes.data_as(C.c_void_p) if out is not None else None,
-                               ks.ctypes.data_as(C.c_void_p) if ks is not None else None)
+                               ks.ctypes.data_as(C.c_void_p) if ks is not None else None, int(use_corr))
     return mean, out, ks
 
 
@@ -204,6 +218,9 @@ def ref_cuda():
     L.ref_cuda_metric_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                            C.POINTER(C.c_float)]
     L.ref_cuda_metric_evaluate.restype = C.c_double
+    if hasattr(L, "ref_cuda_metric_evaluate_corr"):
+        L.ref_cuda_metric_evaluate_corr.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.ref_cuda_metric_evaluate_corr.restype = C.c_double
     _ref_cuda = L
     return L
 
@@ -251,6 +268,18 @@ class RefCudaMetric:
             mean = self.L.ref_cuda_metric_evaluate(self.h, idx4.ctypes.data_as(C.c_void_p), idx4.shape[0], radius,
                                                    dkappa, out.ctypes.data_as(C.c_void_p), C.byref(ms))
         return mean, out, ms.value
+
+    def evaluate_corr(self, radius, dkappa, idx4=None):
+        """The reference's correlation variant (useCorrelation(true)).  Returns (mean, out)."""
+        if idx4 is None:
+            out = np.zeros((self.n, self.n), np.float32)
+            mean = self.L.ref_cuda_metric_evaluate_corr(self.h, None, 0, radius, dkappa, out.ctypes.data_as(C.c_void_p))
+        else:
+            idx4 = np.ascontiguousarray(idx4, np.int32).reshape(-1, 4)
+            out = np.zeros(idx4.shape[0], np.float32)
+            mean = self.L.ref_cuda_metric_evaluate_corr(self.h, idx4.ctypes.data_as(C.c_void_p), idx4.shape[0], radius,
+                                                        dkappa, out.ctypes.data_as(C.c_void_p))
+        return mean, out
 
     def close(self):
         if self.h:

@@ -99,9 +99,26 @@ def test_radon_filter_and_postprocess(ctx, scene, filter, post):
     assert peak_err(got, want) < (RADON_TOL if post == 0 else 2e-3)  # sqrt/log amplify noise near zero
 
 
-def test_radon_ramp_is_refused(ctx, scene):
-    with pytest.raises(api.EccError):
-        ctx.radon_compute(scene["imgs"][:1], 32, 32, filter=api.FILTER_RAMP)
+@pytest.mark.parametrize("shape", [(160, 128, 96, 80), (150, 100, 70, 75), (64, 90, 33, 47)])
+def test_radon_ramp_vs_oracle(ctx, scene, shape):
+    """Ramp filter (row N4; reference RadonIntermediate.cu:173-237), even and odd n_t."""
+    n_u, n_v, n_a, n_t = shape
+    rng = np.random.default_rng(31)
+    img = rng.random((2, n_v, n_u), dtype=np.float32) * 10
+    want = np.stack([ol.radon(x, n_a, n_t, filter=1) for x in img])
+    got = ctx.radon_compute(img, n_a, n_t, filter=api.FILTER_RAMP, interp=api.INTERP_EXACT)
+    assert peak_err(got, want) < RADON_TOL
+
+
+def test_radon_ramp_vs_reference_cuda(ctx, scene):
+    if ol.ref_cuda() is None:
+        pytest.skip("oracle/_ref/libecc_ref_cuda.so not present")
+    ref, _ = ol.ref_cuda_radon(scene["imgs"][:3], 192, 192, filter=1)
+    got = ctx.radon_compute(scene["imgs"][:3], 192, 192, filter=api.FILTER_RAMP, interp=api.INTERP_TEXTURE)
+    assert peak_err(got, ref) < RADON_TOL
+    # the oracle's numpy restatement of the cuFFT calls is pinned by the same comparison
+    want = np.stack([ol.radon(x, 192, 192, filter=1, interp=ol.INTERP_TEX8) for x in scene["imgs"][:3]])
+    assert peak_err(want, ref) < ORACLE_TEX_RADON_TOL
 
 
 def test_radon_host_and_device_buffers_agree(ctx, scene):
@@ -557,3 +574,58 @@ def test_metric_scales_quadratically_full_size(ctx):
     assert np.allclose(vc[~touched], va[~touched], rtol=1e-6)
     assert np.all(vc[touched] > va[touched])
     assert vc[touched].sum() > 1.5 * va[touched].sum()
+
+
+# ---------------------------------------------------------------------------------------------------
+# correlation variant (row N4 / M8): useCorrelation(true)
+# ---------------------------------------------------------------------------------------------------
+def well_posed_pairs(scene):
+    """Pairs whose baseline passes through the origin (here: views 180 degrees apart) have no defined zero of kappa --
+    the plane through baseline and origin is picked by rounding noise.  The SSD does not care (full pencil, weight
+    ~0); the correlation's kappa_max/kappa weights do.  Such pairs are left out of the correlation comparisons."""
+    _, ssd, _ = ol.ecc(scene["Ps"], scene["dtr_exact"], scene["n_u"], scene["n_v"], interp=ol.INTERP_EXACT)
+    v = pair_values(ssd, scene["n"])
+    return v > 1e-6 * v.max()
+
+
+def test_correlation_vs_oracle(ctx, scene):
+    setup_metric(ctx, scene, scene["dtr_exact"], api.INTERP_EXACT)
+    ctx.use_correlation(True)
+    try:
+        n = scene["n"]
+        ok = well_posed_pairs(scene)
+        assert ok.sum() >= ok.size - 2
+        cost = np.zeros((n, n), np.float32)
+        mean = ctx.evaluate(cost)
+        want_mean, want, _ = ol.ecc(scene["Ps"], scene["dtr_exact"], scene["n_u"], scene["n_v"], interp=ol.INTERP_EXACT, use_corr=True)
+        got_v, want_v = pair_values(cost, n), pair_values(want, n)
+        # 1 - cc is a small difference of numbers near 1: compare on the scale of cc itself
+        assert np.abs(got_v - want_v)[ok].max() < 2e-5
+        assert abs(mean - float(got_v.mean())) < 1e-6  # the mean is the plain mean of the pair values
+        assert (want_v > -1e-6).all() and (want_v < 2.0).all()
+        idx = np.array([(0, 3, 0, 3), (2, 7, 2, 7), (5, 1, 5, 1)], np.int32)
+        out = np.zeros(3, np.float32)
+        m2 = ctx.evaluate_indices(idx, out)
+        _, want2, _ = ol.ecc(scene["Ps"], scene["dtr_exact"], scene["n_u"], scene["n_v"], interp=ol.INTERP_EXACT, use_corr=True, idx4=idx)
+        assert np.abs(out - want2).max() < 2e-5 and abs(m2 - float(want2.mean())) < 2e-5
+    finally:
+        ctx.use_correlation(False)
+
+
+def test_correlation_vs_reference_cuda(ctx, scene):
+    if ol.ref_cuda() is None or not hasattr(ol.ref_cuda(), "ref_cuda_metric_evaluate_corr"):
+        pytest.skip("oracle/_ref/libecc_ref_cuda.so (with the correlation entry point) not present")
+    setup_metric(ctx, scene, scene["dtr_tex"], api.INTERP_TEXTURE)
+    ctx.use_correlation(True)
+    try:
+        n = scene["n"]
+        ok = well_posed_pairs(scene)
+        R = ol.RefCudaMetric(scene["Ps"], scene["dtr_tex"], scene["n_u"], scene["n_v"])
+        ref_mean, ref = R.evaluate_corr(ctx.get_object_radius(), 0.0)
+        R.close()
+        cost = np.zeros((n, n), np.float32)
+        ctx.evaluate(cost)
+        assert np.abs(pair_values(cost, n) - pair_values(ref, n))[ok].max() < 2e-5
+        assert abs(ref_mean - float(pair_values(ref, n).mean())) < 1e-6
+    finally:
+        ctx.use_correlation(False)

@@ -197,3 +197,42 @@ def test_trajectory_geometry():
         x = Pm @ np.array([0, 0, 0, 1.0])
         assert np.allclose(x[:2] / x[2], [160, 128], atol=1e-6)  # origin projects to the principal point
         assert abs(np.linalg.norm(Pm[2, :3]) - 1) < 1e-12  # normalised
+
+
+def test_ramp_filter_restatement():
+    """The numpy restatement of the reference's cuFFT ramp filter against the definition written out as a circular
+    convolution (what the CUDA kernel does), even and odd n_t; constants have no response (H_0 = 0)."""
+    rng = np.random.default_rng(2)
+    for n_t in (16, 15, 48):
+        x = rng.standard_normal((n_t, 5)).astype(np.float32)
+        got = ol.ramp_filter(x)
+        n_theta = n_t // 2 + 1
+        scale = np.float32(-0.5) / np.float32(n_t * n_theta)
+        g = np.zeros(n_t)
+        for j in range(n_t):
+            for k in range(1, n_theta):
+                nyq = (n_t % 2 == 0) and (k == n_t // 2)
+                g[j] += (1.0 if nyq else 2.0) * float(np.float32(k) * scale) * np.cos(2 * np.pi * ((j * k) % n_t) / n_t)
+        want = np.stack([sum(x[m].astype(np.float64) * g[(t - m) % n_t] for m in range(n_t)) for t in range(n_t)])
+        assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+        assert np.abs(ol.ramp_filter(np.ones((n_t, 3), np.float32))).max() < 1e-6
+
+
+def test_correlation_variant_of_the_oracle():
+    """use_corr: 1 - cc (un-centred, weights kappa_max/kappa): ~0 for consistent geometry, larger after a detector
+    shift, within [0, 2]; SSD and correlation rank the two situations the same way."""
+    n, n_u, n_v, n_a, n_t = 5, 96, 80, 96, 96
+    ell = np.array([[0, 0, 0, 60, 40, 50, 1.0], [20, -10, 5, 20, 25, 15, 0.5]])
+    Ps = ol.circular_trajectory(n, 750, 1200, n_u, n_v, 200, 3.0)
+    dtr = np.stack([ol.radon(ol.project_ellipsoids(P, n_u, n_v, ell), n_a, n_t) for P in Ps])
+    m_ok, out_ok, _ = ol.ecc(Ps, dtr, n_u, n_v, use_corr=True)
+    bad = Ps.copy()
+    for c in range(4):
+        bad[2, 0 + 3 * c] += 4.0 * bad[2, 2 + 3 * c]   # view 2: detector shift of 4 px in u
+    m_bad, out_bad, _ = ol.ecc(bad, dtr, n_u, n_v, use_corr=True)
+    vals = np.array([out_ok[j, i] for i in range(n) for j in range(i + 1, n)])
+    assert (vals > -1e-6).all() and (vals < 2.0).all()
+    assert 0 <= m_ok < 0.05 and m_bad > 1.2 * m_ok
+    s_ok, _, _ = ol.ecc(Ps, dtr, n_u, n_v)
+    s_bad, _, _ = ol.ecc(bad, dtr, n_u, n_v)
+    assert s_bad > s_ok
