@@ -157,6 +157,8 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
     L.use_corr = ctx->use_corr;
     L.vals_d = nullptr;
     L.image_d = nullptr;
+    L.splits = 1;
+    L.partials_d = nullptr;
     return ECC_OK;
 }
 
@@ -240,7 +242,7 @@ void ecc_destroy(ecc_context* ctx)
         cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d); cudaFree(it->second.radii_d);
         batch_buffers().erase(it);
     }
-    void* bufs[] = {ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, (void*)ctx->dtr_ptrs_d, ctx->vals_d,
+    void* bufs[] = {ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, (void*)ctx->dtr_ptrs_d, ctx->vals_d, ctx->partials_d,
                     ctx->sums_d, ctx->idx_d, ctx->counts_d, ctx->img_stage_d, ctx->out_stage_d, ctx->cost_d};
     for (void* b : bufs)
         if (b) cudaFree(b);

@@ -81,6 +81,8 @@ struct ecc_context {
 
     // ---- scratch ----
     float* vals_d = nullptr;  // one float per evaluated (set,pair)
+    float* partials_d = nullptr;  // partial sums of split CTA-per-pair launches
+    size_t partials_cap = 0;
     size_t vals_cap = 0;
     double* sums_d = nullptr;  // one double per set
     size_t sums_cap = 0;
@@ -151,6 +153,8 @@ struct PairLaunch {
     int is_derivative;
     int interp;
     int use_corr;  // correlation variant instead of the SSD
+    int splits;          // set by launch_pairs: CTAs per pair (CTA-per-pair launches)
+    float* partials_d;   // [items][splits][3] when splits > 1
     // outputs
     float* vals_d;   // n_sets*n_pairs
     float* image_d;  // all-pairs: n_views*n_views cost image or null (only with n_sets==1)

@@ -629,3 +629,18 @@ def test_correlation_vs_reference_cuda(ctx, scene):
         assert abs(ref_mean - float(pair_values(ref, n).mean())) < 1e-6
     finally:
         ctx.use_correlation(False)
+
+
+def test_small_pair_lists_split_their_samples_over_ctas(ctx, scene):
+    """Few listed pairs (tracking): a pair's kappa samples are spread over several CTAs and added up in a second step;
+    the values agree with the all-pairs launch (one warp per pair) up to summation order."""
+    setup_metric(ctx, scene, scene["dtr_tex"], api.INTERP_TEXTURE, dkappa=float(np.deg2rad(0.02)))
+    n = scene["n"]
+    cost = np.zeros((n, n), np.float32)
+    ctx.evaluate(cost)
+    idx = np.array([(n - 1, i, n - 1, i) for i in range(n - 1)], np.int32)
+    out = np.zeros(n - 1, np.float32)
+    mean = ctx.evaluate_indices(idx, out)
+    want = np.array([cost[n - 1, i] for i in range(n - 1)])
+    assert np.abs(out - want).max() <= 2e-6 * want.max()
+    assert abs(mean - float(out.astype(np.float64).mean())) <= 1e-6 * mean
