@@ -220,6 +220,43 @@ def make_circular_trajectory(n_proj, sid, sdd, n_u, n_v, max_angle_deg, pixel_sp
     return Ps
 
 
+def similarity_2d(x):
+    """ModelSimilarity2D::getInstance (LibProjectiveGeometry/Models/ModelSimilarity2D.hxx:52-72): x = translation u, v,
+    rotation, scale -> 3x3."""
+    x = np.asarray(x, np.float64)
+    H = np.eye(3)
+    if x[2] != 0:
+        H[:2, :2] = [[np.cos(x[2]), -np.sin(x[2])], [np.sin(x[2]), np.cos(x[2])]]
+    H[0, 2], H[1, 2] = x[0], x[1]
+    if x[3] != 0:
+        H[:2, :2] *= 1.0 + x[3]
+    return H
+
+
+def similarity_3d(x):
+    """ModelSimilarity3D::getInstance (ModelSimilarity3D.hxx:64-87): x = translation X, Y, Z, rotation about X, Y, Z
+    (R = Rx Ry Rz), scale -> 4x4."""
+    x = np.asarray(x, np.float64)
+    T = np.eye(4)
+    if x[3] != 0 or x[4] != 0 or x[5] != 0:
+        cx, sx, cy, sy, cz, sz = np.cos(x[3]), np.sin(x[3]), np.cos(x[4]), np.sin(x[4]), np.cos(x[5]), np.sin(x[5])
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        T[:3, :3] = Rx @ Ry @ Rz
+    T[:3, 3] = x[:3]
+    if x[6] != 0:
+        T[:3, :3] *= 1.0 + x[6]
+    return T
+
+
+def camera_similarity_2d3d(P, x):
+    """ModelCameraSimilarity2D3D::getInstance (ModelCameraSimilarity2D3D.hxx:89-92): P' = H2D(x[:4]) P T3D(x[4:]);
+    P and the result are 12 doubles, column-major 3x4."""
+    P = np.asarray(P, np.float64).reshape(4, 3).T
+    return (similarity_2d(x[:4]) @ P @ similarity_3d(x[4:])).T.reshape(12)
+
+
 def derive_views_host(Ps):
     """(P^+)^T and source positions as the metric uses them (fp32), computed on the host."""
     Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)

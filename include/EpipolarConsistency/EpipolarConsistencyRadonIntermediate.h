@@ -115,6 +115,15 @@ public:
         return *this;
     }
 
+    /// NEW: replace one matrix of the current set; only that view is re-derived on the device (tracking loops change a
+    /// single view per step, Gui/SingleImageMotion.h:84-90).
+    MetricRadonIntermediate& updateProjectionMatrix(int index, const ProjectionMatrix& P)
+    {
+        Ps[index] = P;
+        chk(ecc_update_projection_matrix(ctx, index, P.data()), "ecc_update_projection_matrix");
+        return *this;
+    }
+
     /// Radius of the object: the user's value, or the automatic estimate from the first matrix.
     virtual double getObjectRadius() const
     {

@@ -4,6 +4,7 @@
 // the Python mirror of the same ABI.
 #define ECC_FACADE_THROW
 #include <EpipolarConsistency/EpipolarConsistencyRadonIntermediate.h>
+#include <EpipolarConsistency/Adaptors.h>
 
 #include <cmath>
 #include <cstdio>
@@ -136,6 +137,49 @@ static int run_gpu(const char* tmpdir)
     std::printf("batch %.9g %.9g\n", means[0], means[1]);
     ecc.setObjectRadius(50.0).setEpipolarPlaneStep(0.002);
     std::printf("fixed %.9g\n", ecc.evaluate());
+    // ---- adaptors: SingleImageMotion, Registration, Registration3D3D, the similarity models
+    {
+        Geometry::ModelCameraSimilarity2D3D model(Ps[2]);
+        const double x[11] = {1.5, -0.75, 0.004, 0.0, 0.8, -0.4, 0.3, 0.002, -0.003, 0.001, 0.0};
+        model.current_values.assign(x, x + 11);
+        const ProjectionMatrix P2 = model.getInstance();
+        std::printf("model");
+        for (int k = 0; k < 12; k++) std::printf(" %.12g", P2.data()[k]);
+        std::printf("\n");
+        SingleImageMotion sim(Ps, dtrs, 2);
+        sim.getMetricPtr().setObjectRadius(0).setEpipolarPlaneStep(0);
+        const double all0 = sim.evaluate(Ps[2]);
+        const double all1 = sim.evaluate(P2);
+        std::vector<float> per_pair(n - 1);
+        const double moving1 = sim.evaluateMovingPairs(P2, per_pair.data());
+        std::vector<ProjectionMatrix> cands;
+        cands.push_back(Ps[2]);
+        cands.push_back(P2);
+        const std::vector<double> cm = sim.evaluateCandidates(cands);
+        std::printf("sim %.9g %.9g %.9g %.9g %.9g\n", all0, all1, moving1, cm[0], cm[1]);
+        double s = 0;
+        for (int k = 0; k < n - 1; k++) s += per_pair[k];
+        if (std::fabs(s / (n - 1) - moving1) > 1e-6 * moving1) return fail("SingleImageMotion per-pair values");
+        if (std::fabs(cm[1] - moving1) > 1e-6 * moving1) return fail("SingleImageMotion candidates vs sequential");
+        Registration reg(Ps, dtrs);
+        const double r0 = reg.evaluate(Ps[0]);
+        std::printf("reg %.9g\n", r0);
+        std::vector<ProjectionMatrix> Psrc(Ps.begin(), Ps.begin() + 2), Ptgt(Ps.begin() + 2, Ps.end());
+        std::vector<RadonIntermediate*> dsrc(dtrs.begin(), dtrs.begin() + 2), dtgt(dtrs.begin() + 2, dtrs.end());
+        Registration3D3D r33(false, Psrc, dsrc, Ptgt, dtgt);
+        Geometry::ModelSimilarity3D m3;
+        const double id = r33.evaluate(m3.getInstance());
+        m3.current_values[0] = 2.0;  // 2 mm along X
+        m3.current_values[4] = 0.01;
+        const double moved = r33.evaluate(m3.getInstance());
+        std::vector<Geometry::Homography3D> Ts;
+        Ts.push_back(Geometry::Homography3D());
+        Ts.push_back(m3.getInstance());
+        const std::vector<double> rm = r33.evaluateCandidates(Ts);
+        std::printf("reg33 %.9g %.9g %.9g %.9g\n", id, moved, rm[0], rm[1]);
+        if (std::fabs(rm[0] - id) > 1e-6 * id || std::fabs(rm[1] - moved) > 1e-6 * moved) return fail("Registration3D3D candidates vs sequential");
+        if (!(moved > id)) return fail("Registration3D3D: a displaced source must score worse");
+    }
     for (auto d : dtrs) delete d;
     std::printf("OK gpu\n");
     return 0;

@@ -64,7 +64,7 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
             pairs[(int(t[1]), int(t[2]))] = float(t[3])
         elif t[0] in ("radius", "mean", "subset", "fixed"):
             vals[t[0]] = float(t[1])
-        elif t[0] in ("list", "batch"):
+        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33"):
             vals[t[0]] = [float(x) for x in t[1:]]
     # the same scene through the Python mirror
     import torch
@@ -95,6 +95,33 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
     assert abs(vals["batch"][0] - want_batch[0]) <= 1e-7 * mean
     assert abs(vals["batch"][1] - want_batch[1]) <= 1e-7 * want_batch[1]
     assert vals["batch"][1] > 1.1 * vals["batch"][0]
+    # ---- adaptors: the same quantities through the mirror
+    x = [1.5, -0.75, 0.004, 0.0, 0.8, -0.4, 0.3, 0.002, -0.003, 0.001, 0.0]
+    P2 = api.camera_similarity_2d3d(Ps[2], x)
+    assert np.allclose(vals["model"], P2, rtol=1e-11, atol=1e-11)
+    ctx.set_object_radius(0.0)
+    ctx.set_epipolar_plane_step(0.0)
+    ctx.set_projection_matrices(Ps)
+    all0 = ctx.evaluate(None)
+    ctx.update_projection_matrix(2, P2)
+    all1 = ctx.evaluate(None)
+    idx2 = np.array([(2, i, 2, i) for i in range(n) if i != 2], np.int32)
+    moving1 = ctx.evaluate_indices(idx2)
+    assert abs(vals["sim"][0] - all0) <= 1e-7 * all0 and abs(vals["sim"][1] - all1) <= 1e-7 * all1
+    assert abs(vals["sim"][2] - moving1) <= 1e-7 * moving1 and abs(vals["sim"][4] - moving1) <= 1e-6 * moving1
+    assert all1 > all0
+    ctx.set_projection_matrices(Ps)
+    idx0 = np.array([(0, i, 0, i) for i in range(1, n)], np.int32)
+    assert abs(vals["reg"][0] - ctx.evaluate_indices(idx0)) <= 1e-7 * vals["reg"][0]
+    cross = np.array([(i, j, i, j) for j in range(2, n) for i in range(2)], np.int32)
+    assert abs(vals["reg33"][0] - ctx.evaluate_indices(cross)) <= 1e-7 * vals["reg33"][0]
+    T = api.similarity_3d([2.0, 0, 0, 0, 0.01, 0, 0])
+    moved = Ps.copy()
+    for i in range(2):
+        moved[i] = (Ps[i].reshape(4, 3).T @ T).T.reshape(12)
+    ctx.set_projection_matrices(moved)
+    assert abs(vals["reg33"][1] - ctx.evaluate_indices(cross)) <= 1e-7 * vals["reg33"][1]
+    ctx.set_projection_matrices(Ps)
     ctx.set_object_radius(50.0)
     ctx.set_epipolar_plane_step(0.002)
     assert abs(vals["fixed"] - ctx.evaluate(None)) <= 1e-7 * vals["fixed"]
