@@ -130,21 +130,34 @@ __device__ __forceinline__ float bin_texture(cudaTextureObject_t tex, const BinL
     float sum = 0.f, sumo = 0.f;
     float t = L.t;
     bool none_yet = true;
-#define ECC_TEX_A(tt) tex2D<float>(tex, o0 + (tt) * d0, o1 + (tt) * d1)
-#define ECC_TEX_B(tt) tex2D<float>(tex, o0 + (tt) * d0 + d1, o1 + (tt) * d1 - d0)
+    // explicit fma: the executed reference contracts o + t*d into one FFMA and adds the line offset afterwards; left to
+    // the compiler, a product t*d0 that happens to be at hand from the entry-point test is reused uncontracted
+#define ECC_TEX_A(tt) tex2D<float>(tex, fmaf((tt), d0, o0), fmaf((tt), d1, o1))
+#define ECC_TEX_B(tt) tex2D<float>(tex, fmaf((tt), d0, o0) + d1, fmaf((tt), d1, o1) - d0)
     if (!(t + 1.98f > t_max)) {
         const float r3 = t_max - 1.98f;
+        // software pipeline: the fetches of the next block of four are in flight while this block's results are added
+        // (the texture warps are few; what keeps the texture pipe busy is the number of fetches they have in flight)
+        float t1 = t + kStep, t2 = t1 + kStep, t3 = t2 + kStep;
+        float a0 = ECC_TEX_A(t), b0 = ECC_TEX_B(t), a1 = ECC_TEX_A(t1), b1 = ECC_TEX_B(t1);
+        float a2 = ECC_TEX_A(t2), b2 = ECC_TEX_B(t2), a3 = ECC_TEX_A(t3), b3 = ECC_TEX_B(t3);
+        t = t3 + kStep;
 #pragma unroll 1
-        do {
-            const float t1 = t + kStep, t2 = t1 + kStep, t3 = t2 + kStep;
-            const float a0 = ECC_TEX_A(t), b0 = ECC_TEX_B(t), a1 = ECC_TEX_A(t1), b1 = ECC_TEX_B(t1);
-            const float a2 = ECC_TEX_A(t2), b2 = ECC_TEX_B(t2), a3 = ECC_TEX_A(t3), b3 = ECC_TEX_B(t3);
+        while (!(t > r3)) {
+            t1 = t + kStep; t2 = t1 + kStep; t3 = t2 + kStep;
+            const float na0 = ECC_TEX_A(t), nb0 = ECC_TEX_B(t), na1 = ECC_TEX_A(t1), nb1 = ECC_TEX_B(t1);
+            const float na2 = ECC_TEX_A(t2), nb2 = ECC_TEX_B(t2), na3 = ECC_TEX_A(t3), nb3 = ECC_TEX_B(t3);
             sum += a0; sumo += b0;
             sum += a1; sumo += b1;
             sum += a2; sumo += b2;
             sum += a3; sumo += b3;
+            a0 = na0; b0 = nb0; a1 = na1; b1 = nb1; a2 = na2; b2 = nb2; a3 = na3; b3 = nb3;
             t = t3 + kStep;
-        } while (!(t > r3));
+        }
+        sum += a0; sumo += b0;
+        sum += a1; sumo += b1;
+        sum += a2; sumo += b2;
+        sum += a3; sumo += b3;
         none_yet = false;
     }
     const float t1 = t + kStep;
@@ -582,9 +595,9 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
     P.groups_a = (n_alpha + kItemAngles - 1) / kItemAngles;
     P.groups_t = (n_t + kItemT - 1) / kItemT;
     // development knobs (environment): texture warps per CTA, window rows, buffers, CTAs per SM
-    static const int nt = env_int("ECC_HYBRID_NT", 4);
+    static const int nt = env_int("ECC_HYBRID_NT", 8);
     static const int nbuf = env_int("ECC_HYBRID_NBUF", 1) == 2 ? 2 : 1;
-    static const int ctas = env_int("ECC_HYBRID_CTAS", 4);
+    static const int ctas = env_int("ECC_HYBRID_CTAS", 3);
     static const int mode = env_int("ECC_HYBRID_MODE", 0);
     P.mode = mode;
     P.nbuf = nbuf;
