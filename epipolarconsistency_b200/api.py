@@ -40,6 +40,21 @@ def _ptr(x):
     raise TypeError(f"unsupported buffer type {type(x)}")
 
 
+class PreprocessParams(C.Structure):
+    """ecc_preprocess_params (include/ecc_b200.h); field names follow the reference's GetSet keys
+    (Gui/PreProccess.cpp:42-55)."""
+    _fields_ = [("scale", C.c_double), ("bias", C.c_double), ("normalize", C.c_int), ("apply_log", C.c_int),
+                ("border_zero", C.c_int * 4), ("border_feather", C.c_int * 4), ("n_blanks", C.c_int),
+                ("blanks", C.POINTER(C.c_int)), ("flip_u", C.c_int), ("flip_v", C.c_int), ("gaussian_sigma", C.c_double),
+                ("half_kernel_width", C.c_int), ("cos_weight", C.c_int)]
+
+    @classmethod
+    def defaults(cls):
+        p = cls()
+        _lib.load().ecc_preprocess_defaults(C.byref(p))
+        return p
+
+
 class Context:
     """One GPU + one stream (ecc_context).  Thin, explicit wrapper of the C ABI."""
 
@@ -85,6 +100,24 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.ecc_synchronize(self.h))
+
+    # -- pre-processing (in place)
+    def preprocess(self, images, params, Ps=None, blanks=None):
+        """images: (n, n_v, n_u) float32 numpy array or torch cuda tensor; params: PreprocessParams; Ps: (n,12) doubles for
+        the cosine weighting; blanks: (k,4) ints (x0,y0,x1,y1)."""
+        n, n_v, n_u = images.shape
+        keep = None
+        if blanks is not None and len(blanks):
+            keep = np.ascontiguousarray(blanks, np.int32).reshape(-1, 4)
+            params.n_blanks = keep.shape[0]
+            params.blanks = keep.ctypes.data_as(C.POINTER(C.c_int))
+        else:
+            params.n_blanks = 0
+        if Ps is not None:
+            Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
+            assert Ps.shape[0] == n
+        self._check(self.lib.ecc_preprocess(self.h, _ptr(images), n, n_u, n_v, C.addressof(params), _ptr(Ps)))
+        return images
 
     # -- Radon
     def radon_compute(self, images, n_alpha, n_t, filter=FILTER_DERIVATIVE, post=POST_IDENTITY,

@@ -233,6 +233,8 @@ void ecc_destroy(ecc_context* ctx)
     free_image_pool(ctx);
     free_hybrid(ctx);
     if (ctx->ramp_g_d) cudaFree(ctx->ramp_g_d);
+    if (ctx->pre_work_d) cudaFree(ctx->pre_work_d);
+    if (ctx->pre_small_d) cudaFree(ctx->pre_small_d);
     if (ctx->copy_stream) {
         cudaStreamDestroy(ctx->copy_stream);
         for (int b = 0; b < 2; b++) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_consumed[b]); }
@@ -334,6 +336,42 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
         first += n;
     }
     ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ECC_OK;
+}
+
+void ecc_preprocess_defaults(ecc_preprocess_params* p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->scale = 1.0;
+    for (int k = 0; k < 4; k++) { p->border_zero[k] = 1; p->border_feather[k] = 16; }
+    p->gaussian_sigma = 1.84;
+    p->half_kernel_width = 5;
+    p->cos_weight = 1;
+}
+
+int ecc_preprocess(ecc_context* ctx, float* images, int n, int n_u, int n_v, const ecc_preprocess_params* params, const double* Ps)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!images || !params || n < 0 || n_u < 1 || n_v < 1 || params->n_blanks < 0 || (params->n_blanks > 0 && !params->blanks))
+        return fail(ctx, ECC_ERR_INVALID, "ecc_preprocess: bad argument");
+    for (int k = 0; k < 4; k++)
+        if (params->border_zero[k] < 0 || params->border_feather[k] < 0) return fail(ctx, ECC_ERR_INVALID, "ecc_preprocess: negative border");
+    if (n == 0) return ECC_OK;
+    if (is_device_pointer(images)) return preprocess_batch(ctx, images, n, n_u, n_v, params, Ps);
+    // host images: through the device staging buffer in chunks
+    const size_t len = (size_t)n_u * n_v;
+    const int chunk = n < 32 ? n : 32;
+    int rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * len * chunk);
+    if (rc) return rc;
+    for (int first = 0; first < n; first += chunk) {
+        const int m = (n - first < chunk) ? n - first : chunk;
+        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->img_stage_d, images + (size_t)first * len, sizeof(float) * len * m, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = preprocess_batch(ctx, ctx->img_stage_d, m, n_u, n_v, params, Ps ? Ps + (size_t)12 * first : nullptr))) return rc;
+        ECC_CUDA(ctx, cudaMemcpyAsync(images + (size_t)first * len, ctx->img_stage_d, sizeof(float) * len * m, cudaMemcpyDeviceToHost, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return ECC_OK;
 }
 

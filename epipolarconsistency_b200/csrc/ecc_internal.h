@@ -100,6 +100,10 @@ struct ecc_context {
     size_t cost_cap = 0;
 
     eccb200::ImagePool pool;
+    float* pre_work_d = nullptr;   // pre-processing scratch (ecc_preprocess.cu)
+    size_t pre_work_bytes = 0;
+    void* pre_small_d = nullptr;
+    size_t pre_small_bytes = 0;
     float* ramp_g_d = nullptr;  // ramp-filter kernel g[n_t] (ecc_radon.cu)
     int ramp_n_t = 0;
     eccb200::HybridStage hybrid;
@@ -179,6 +183,10 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
                         int n_v, int n_alpha, int n_t, int post, float* out_d);
 void free_hybrid(ecc_context* ctx);
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
+
+// ---- launchers (ecc_preprocess.cu) ----
+int preprocess_batch(ecc_context* ctx, float* images_d, int n, int n_u, int n_v, const ecc_preprocess_params* pp, const double* Ps_h);
+void camera_intrinsics_host(const double* P, double* fu, double* u0, double* v0);
 
 // ---- launchers (ecc_synth.cu) ----
 int synth_projections(ecc_context* ctx, const double* Ps_h, int n, int n_u, int n_v,

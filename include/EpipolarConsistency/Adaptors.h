@@ -156,6 +156,71 @@ public:
 
 namespace EpipolarConsistency {
 
+/// Pre-processing of X-ray projection images (Gui/PreProccess.h:14-52, PreProccess.cpp:57-166) on the device; the
+/// GetSet GUI plumbing of the reference (gui_declare_section / gui_retreive_section) stays with the GUI.
+struct PreProccess {
+    struct Intensity {
+        bool normalize;
+        double bias, scale;
+        bool apply_log;
+        Intensity() : normalize(false), bias(0.0), scale(1.0), apply_log(false) {}
+    } intensity;
+    struct Lowpass {
+        double gaussian_sigma;
+        int half_kernel_width;
+        Lowpass() : gaussian_sigma(1.84), half_kernel_width(5) {}
+    } lowpass;
+    struct ImageGeometry {
+        bool flip_u, flip_v;
+        ImageGeometry() : flip_u(false), flip_v(false) {}
+    } image_geometry;
+    struct Border {
+        Eigen::Vector4i zero, feather;  // left, right, bottom, top
+        std::vector<Eigen::Vector4i> blanks;
+        Border() : zero(1, 1, 1, 1), feather(16, 16, 16, 16) {}
+    } border;
+
+    void process(NRRD::ImageView<float>& image) const { run(image, 0x0); }
+    void apply_weight_cos_principal_ray(NRRD::ImageView<float>& image, const ProjectionMatrix& P) const
+    {
+        // only the cosine weighting: identity intensity, no borders, no low-pass
+        ecc_preprocess_params p;
+        ecc_preprocess_defaults(&p);
+        for (int k = 0; k < 4; k++) p.border_zero[k] = p.border_feather[k] = 0;
+        p.gaussian_sigma = 0;
+        p.cos_weight = 1;
+        ecc_context* ctx = detail::shared_context();
+        detail::check(ecc_preprocess(ctx, (float*)image, 1, image.size(0), image.size(1), &p, P.data()), ctx, "ecc_preprocess");
+    }
+    /// process() and the cosine weighting in one pass over the image (what the loaders do back to back,
+    /// Gui/InputDataDirect.cpp:75-87).
+    void processAndWeight(NRRD::ImageView<float>& image, const ProjectionMatrix& P) const { run(image, &P); }
+
+private:
+    void run(NRRD::ImageView<float>& image, const ProjectionMatrix* P) const
+    {
+        ecc_preprocess_params p;
+        ecc_preprocess_defaults(&p);
+        p.scale = intensity.scale;
+        p.bias = intensity.bias;
+        p.normalize = intensity.normalize;
+        p.apply_log = intensity.apply_log;
+        for (int k = 0; k < 4; k++) { p.border_zero[k] = border.zero[k]; p.border_feather[k] = border.feather[k]; }
+        std::vector<int> flat(4 * border.blanks.size());
+        for (size_t i = 0; i < border.blanks.size(); i++)
+            for (int k = 0; k < 4; k++) flat[4 * i + k] = border.blanks[i][k];
+        p.n_blanks = (int)border.blanks.size();
+        p.blanks = flat.empty() ? 0x0 : flat.data();
+        p.flip_u = image_geometry.flip_u;
+        p.flip_v = image_geometry.flip_v;
+        p.gaussian_sigma = lowpass.gaussian_sigma;
+        p.half_kernel_width = lowpass.half_kernel_width;
+        p.cos_weight = P ? 1 : 0;
+        ecc_context* ctx = detail::shared_context();
+        detail::check(ecc_preprocess(ctx, (float*)image, 1, image.size(0), image.size(1), &p, P ? P->data() : 0x0), ctx, "ecc_preprocess");
+    }
+};
+
 /// Epipolar consistency metric for changes on one projection matrix (Gui/SingleImageMotion.h).
 class SingleImageMotion {
 protected:

@@ -95,6 +95,31 @@ void ecc_radon_bin_sizes(int n_u, int n_v, int n_alpha, int n_t, double* step_al
 int ecc_radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter,
                           double* count);
 
+/* ---- Pre-processing (the step in front of the path) -------------------------------------------------------------
+ * PreProccess::process + apply_weight_cos_principal_ray (Gui/PreProccess.cpp:57-166; parameter names as the
+ * reference's GetSet keys, Gui/PreProccess.cpp:42-55): per pixel v = v*scale + bias (normalize: scale / max of the
+ * image, bias 0), optional -log, negatives / NaN / inf -> 0; zeroed + feathered borders (order: left, right, bottom,
+ * top); blanked rectangles (x0,y0,x1,y1); flips; separable Gaussian low-pass when sigma > 0 and half width > 1;
+ * cosine weighting about the principal point when cos_weight != 0 and matrices are given. */
+typedef struct ecc_preprocess_params {
+    double scale, bias;           /* Intensity/Scale, Intensity/Bias                       */
+    int normalize, apply_log;     /* Intensity/Normalize, Intensity/Apply Minus Logarithm  */
+    int border_zero[4];           /* Border/Zero Border: left, right, bottom, top          */
+    int border_feather[4];        /* Border/Feather                                        */
+    int n_blanks;                 /* Border/Blanks                                         */
+    const int* blanks;            /* n_blanks * 4 ints, host                               */
+    int flip_u, flip_v;           /* Geometry/Flip u-Axis, Flip v-Axis                     */
+    double gaussian_sigma;        /* Lowpass Filter/Gaussian Sigma                         */
+    int half_kernel_width;        /* Lowpass Filter/Half Kernel Width                      */
+    int cos_weight;               /* apply_weight_cos_principal_ray                        */
+} ecc_preprocess_params;
+/* The reference's defaults (Gui/PreProccess.h:17-41): scale 1, bias 0, zero border 1 px, feather 16 px, sigma 1.84, k 5;
+ * cos_weight on (the loaders always apply it, Gui/InputDataDirect.cpp:85). */
+void ecc_preprocess_defaults(ecc_preprocess_params* params);
+/* images [h|d]: n * n_v * n_u floats, processed in place.  Ps (host, nullable): n matrices for the cosine weighting. */
+int ecc_preprocess(ecc_context* ctx, float* images, int n, int n_u, int n_v, const ecc_preprocess_params* params,
+                   const double* Ps);
+
 /* ---- Metric state (MetricRadonIntermediate) ------------------------------------------------ */
 
 /* setRadonIntermediates (EpipolarConsistencyRadonIntermediate.cpp:87-106).  dtrs [h|d]:

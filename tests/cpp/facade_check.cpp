@@ -180,6 +180,18 @@ static int run_gpu(const char* tmpdir)
         if (std::fabs(rm[0] - id) > 1e-6 * id || std::fabs(rm[1] - moved) > 1e-6 * moved) return fail("Registration3D3D candidates vs sequential");
         if (!(moved > id)) return fail("Registration3D3D: a displaced source must score worse");
     }
+    {   // PreProccess facade: defaults clear the border and feather 16 px; cosine weight 1 at the principal point
+        NRRD::Image<float> im(n_u, n_v);
+        for (int i = 0; i < im.length(); i++) ((float*)im)[i] = 5.f;
+        PreProccess pre;
+        pre.lowpass.gaussian_sigma = 0;
+        pre.processAndWeight(im, Ps[0]);
+        const float* q = (const float*)im;
+        if (q[0] != 0.f || q[n_u * (n_v / 2)] != 0.f) return fail("PreProccess border");
+        if (std::fabs(q[n_u * (n_v / 2) + n_u / 2] - 5.f) > 1e-5f) return fail("PreProccess centre");
+        if (!(q[n_u * (n_v / 2) + 8] > 0.f && q[n_u * (n_v / 2) + 8] < 5.f)) return fail("PreProccess feather");
+        std::printf("pre %.9g %.9g\n", q[n_u * (n_v / 2) + 8], q[n_u * 30 + 40]);
+    }
     for (auto d : dtrs) delete d;
     std::printf("OK gpu\n");
     return 0;

@@ -296,3 +296,73 @@ def ref_nrrd():
                                 C.c_char_p, C.c_int]
     L.ref_nrrd_save.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
     return L
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pre-processing: numpy restatement of Gui/PreProccess.cpp:57-166
+# ---------------------------------------------------------------------------------------------------------------
+def _feather(x):
+    """weighting(), EpipolarConsistencyCommon.hxx:30-35"""
+    x = np.float32(x)
+    if x < -1 or x > 1:
+        return np.float32(0)
+    xx = np.float32(x * x)
+    return np.float32(np.float32(1) - np.float32(2) * xx + xx * xx)
+
+
+def camera_intrinsics(P):
+    """K(0,0), K(0,2), K(1,2) of Geometry::getCameraIntrinsics (ProjectionMatrix.cpp:27-67): RQ decomposition of the left
+    3x3 block with positive diagonal and K(2,2) = 1, by numpy's QR of the row-reversed transpose."""
+    M = np.asarray(P, np.float64).reshape(4, 3).T[:, :3]
+    Q, R = np.linalg.qr(M[::-1].T)
+    K = R.T[::-1, ::-1]
+    S = np.diag(np.sign(np.diag(K)))
+    K = K @ S
+    K = K / K[2, 2]
+    return K[0, 0], K[0, 2], K[1, 2]
+
+
+def preprocess(img, scale=1.0, bias=0.0, normalize=False, apply_log=False, zero=(1, 1, 1, 1), feather=(0, 0, 0, 0),
+               blanks=(), flip_u=False, flip_v=False, sigma=1.84, k=5, P=None):
+    img = np.array(img, np.float32)
+    h, w = img.shape
+    scale, bias = np.float32(scale), np.float32(bias)
+    if normalize:  # :66-75
+        scale, bias = np.float32(scale / img.max()), np.float32(0)
+    img = (img * scale).astype(np.float32) + bias  # :81
+    if apply_log:
+        with np.errstate(all="ignore"):
+            img = (-np.log(img)).astype(np.float32)
+    img[(img < 0) | ~np.isfinite(img)] = 0  # :85-86
+    for b in range(zero[0] + feather[0]):  # left :91-93
+        img[:, b] *= np.float32(0) if b <= zero[0] else _feather(1 - np.float32(b - zero[0]) / feather[0])
+    for b in range(1, zero[1] + feather[1] + 1):  # right :96-98
+        img[:, w - b] *= np.float32(0) if b <= zero[1] else _feather(1 - np.float32(b - zero[1]) / feather[1])
+    for b in range(1, zero[2] + feather[2] + 1):  # bottom :101-103
+        img[h - b, :] *= np.float32(0) if b <= zero[2] else _feather(1 - np.float32(b - zero[2]) / feather[2])
+    for b in range(zero[3] + feather[3]):  # top :106-108
+        img[b, :] *= np.float32(0) if b <= zero[3] else _feather(1 - np.float32(b - zero[3]) / feather[3])
+    for (x0, y0, x1, y1) in blanks:  # :111-114 (bounds clamped to the image)
+        img[max(0, y0):max(0, y1), max(0, x0):max(0, x1)] = 0
+    if flip_u:
+        img = img[:, ::-1]
+    if flip_v:
+        img = img[::-1, :]
+    img = np.ascontiguousarray(img)
+    if sigma > 0 and k > 1:  # nrrd_lowpass.hxx:18-33 kernel, :46-79 taps -k .. k-1 (sic), clamped, fp64 sums, float stores
+        kern = np.exp(-0.5 * (np.arange(-k, k + 1) / sigma) ** 2)
+        kern /= kern.sum()
+        work = np.zeros((h, w), np.float64)
+        for o in range(-k, k):
+            work += img[:, np.clip(np.arange(w) + o, 0, w - 1)].astype(np.float64) * kern[o + k]
+        work = work.astype(np.float32)
+        out = np.zeros((h, w), np.float64)
+        for o in range(-k, k):
+            out += work[np.clip(np.arange(h) + o, 0, h - 1), :].astype(np.float64) * kern[o + k]
+        img = out.astype(np.float32)
+    if P is not None and np.any(np.asarray(P) != 0):  # apply_weight_cos_principal_ray :146-166
+        fu, u0, v0 = (np.float32(x) for x in camera_intrinsics(P))
+        pou = np.arange(w, dtype=np.float32)[None, :] - u0
+        pov = np.arange(h, dtype=np.float32)[:, None] - v0
+        img = img * (fu / np.sqrt(pou * pou + pov * pov + fu * fu, dtype=np.float32))
+    return img.astype(np.float32)

@@ -64,7 +64,7 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
             pairs[(int(t[1]), int(t[2]))] = float(t[3])
         elif t[0] in ("radius", "mean", "subset", "fixed"):
             vals[t[0]] = float(t[1])
-        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33"):
+        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre"):
             vals[t[0]] = [float(x) for x in t[1:]]
     # the same scene through the Python mirror
     import torch
@@ -121,6 +121,9 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
         moved[i] = (Ps[i].reshape(4, 3).T @ T).T.reshape(12)
     ctx.set_projection_matrices(moved)
     assert abs(vals["reg33"][1] - ctx.evaluate_indices(cross)) <= 1e-7 * vals["reg33"][1]
+    # PreProccess facade vs the oracle restatement (defaults: zero 1, feather 16; no low-pass in this check)
+    want = ol.preprocess(np.full((n_v, n_u), 5.0, np.float32), sigma=0.0, feather=(16, 16, 16, 16), P=Ps[0])
+    assert abs(vals["pre"][0] - want[n_v // 2, 8]) <= 2e-6 * 5 and abs(vals["pre"][1] - want[30, 40]) <= 2e-6 * 5
     ctx.set_projection_matrices(Ps)
     ctx.set_object_radius(50.0)
     ctx.set_epipolar_plane_step(0.002)

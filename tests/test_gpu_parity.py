@@ -644,3 +644,41 @@ def test_small_pair_lists_split_their_samples_over_ctas(ctx, scene):
     want = np.array([cost[n - 1, i] for i in range(n - 1)])
     assert np.abs(out - want).max() <= 2e-6 * want.max()
     assert abs(mean - float(out.astype(np.float64).mean())) <= 1e-6 * mean
+
+
+# ---------------------------------------------------------------------------------------------------
+# pre-processing (row N3)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [
+    dict(),
+    dict(scale=0.002, bias=0.05, apply_log=True, zero=(2, 0, 3, 1), feather=(6, 9, 0, 5), blanks=[(10, 20, 30, 44)], flip_u=True),
+    dict(normalize=True, scale=3.0, flip_v=True, sigma=0.0, zero=(0, 0, 0, 0)),
+    dict(sigma=2.5, k=3, flip_u=True, flip_v=True, feather=(4, 4, 4, 4), cos=False),
+])
+def test_preprocess_vs_oracle(ctx, case):
+    import torch
+    case = dict(case)
+    cos = case.pop("cos", True)
+    n, n_u, n_v = 3, 150, 110
+    rng = np.random.default_rng(41)
+    raw = (rng.random((n, n_v, n_u), dtype=np.float32) * 900 + 50).astype(np.float32)
+    Ps = ol.circular_trajectory(n, 750, 1200, n_u, n_v, 200, 2.0)
+    p = api.PreprocessParams.defaults()
+    p.scale, p.bias = case.get("scale", 1.0), case.get("bias", 0.0)
+    p.normalize, p.apply_log = int(case.get("normalize", False)), int(case.get("apply_log", False))
+    for k in range(4):
+        p.border_zero[k] = case.get("zero", (1, 1, 1, 1))[k]
+        p.border_feather[k] = case.get("feather", (0, 0, 0, 0))[k]
+    p.flip_u, p.flip_v = int(case.get("flip_u", False)), int(case.get("flip_v", False))
+    p.gaussian_sigma, p.half_kernel_width = case.get("sigma", 1.84), case.get("k", 5)
+    p.cos_weight = int(cos)
+    want = np.stack([ol.preprocess(raw[i], scale=p.scale, bias=p.bias, normalize=bool(p.normalize), apply_log=bool(p.apply_log),
+                                   zero=tuple(p.border_zero), feather=tuple(p.border_feather), blanks=case.get("blanks", ()),
+                                   flip_u=bool(p.flip_u), flip_v=bool(p.flip_v), sigma=p.gaussian_sigma, k=p.half_kernel_width,
+                                   P=Ps[i] if cos else None) for i in range(n)])
+    got_h = ctx.preprocess(raw.copy(), p, Ps=Ps if cos else None, blanks=case.get("blanks"))
+    got_d = ctx.preprocess(torch.from_numpy(raw).cuda(), p, Ps=Ps if cos else None, blanks=case.get("blanks")).cpu().numpy()
+    assert np.array_equal(got_h, got_d)
+    scale = np.abs(want).max()
+    assert np.abs(got_h - want).max() <= 2e-6 * scale
+    assert np.array_equal(got_h == 0, want == 0)  # the zeroed border / blanks are exactly zero in both

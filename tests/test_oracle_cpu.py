@@ -236,3 +236,26 @@ def test_correlation_variant_of_the_oracle():
     s_ok, _, _ = ol.ecc(Ps, dtr, n_u, n_v)
     s_bad, _, _ = ol.ecc(bad, dtr, n_u, n_v)
     assert s_bad > s_ok
+
+
+def test_preprocess_restatement_invariants():
+    """Oracle of the pre-processing step: default parameters clear exactly the first two columns / rows and the last
+    column / row (a border of "zero = 1" runs b = 0..zero inclusive at the left / top, Gui/PreProccess.cpp:91-108); the
+    low-pass keeps constants up to the missing last tap; the intrinsics of a synthetic matrix are the ones it was built
+    from; cosine weights are 1 at the principal point and < 1 elsewhere."""
+    img = np.full((40, 50), 7.0, np.float32)
+    out = ol.preprocess(img, sigma=0.0)
+    assert (out[:, :1] == 0).all() and (out[:1, :] == 0).all() and (out[:, -1] == 0).all() and (out[-1, :] == 0).all()
+    assert (out[2:-1, 2:-1] == 7.0).all()
+    k, sigma = 5, 1.84
+    kern = np.exp(-0.5 * (np.arange(-k, k + 1) / sigma) ** 2)
+    kern /= kern.sum()
+    smooth = ol.preprocess(img, sigma=sigma, k=k, zero=(0, 0, 0, 0))
+    assert abs(smooth[20, 25] - 7.0 * kern[:-1].sum() ** 2) < 1e-5
+    n_u, n_v = 320, 240
+    P = ol.circular_trajectory(4, 750, 1200, n_u, n_v, 200, 1.5)[1]
+    fu, u0, v0 = ol.camera_intrinsics(P)
+    f_traj = n_v / (2.0 * np.tan(0.5 * np.arctan(n_v * 1.5 / 1200)))  # cameraPerspective as makeCircularTrajectory calls it
+    assert abs(u0 - 0.5 * n_u) < 1e-6 and abs(v0 - 0.5 * n_v) < 1e-6 and abs(fu - f_traj) < 1e-9 * fu
+    w = ol.preprocess(np.ones((n_v, n_u), np.float32), sigma=0.0, zero=(0, 0, 0, 0), P=P)
+    assert abs(w[n_v // 2, n_u // 2] - 1.0) < 1e-6 and w[0, 0] < w[n_v // 2, n_u // 2]
