@@ -682,3 +682,27 @@ def test_preprocess_vs_oracle(ctx, case):
     scale = np.abs(want).max()
     assert np.abs(got_h - want).max() <= 2e-6 * scale
     assert np.array_equal(got_h == 0, want == 0)  # the zeroed border / blanks are exactly zero in both
+
+
+def test_metric_on_hybrid_dtrs_within_pair_tolerance(ctx):
+    """End to end: intermediates from the hybrid engine instead of the texture engine (= the reference's kernel, bit for
+    bit) move no pair by more than the per-pair tolerance.  Full-size images so that the bins carry the reference's own
+    fp32 accumulation noise."""
+    import torch
+    n, n_u, n_v, n_a, n_t = 12, 1240, 960, 768, 768
+    Ps = api.make_circular_trajectory(n, 750.0, 1200.0, n_u, n_v, 200.0, 0.308)
+    imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
+    ctx.synth_projections(Ps, n_u, n_v, ELL, imgs)
+    vals = {}
+    for name, interp in (("texture", api.INTERP_TEXTURE), ("hybrid", api.INTERP_HYBRID)):
+        dtrs = ctx.radon_compute(imgs, n_a, n_t, interp=interp)
+        ctx.set_interpolation(api.INTERP_TEXTURE)
+        ctx.set_object_radius(0.0)
+        ctx.set_epipolar_plane_step(float(np.deg2rad(0.01)))
+        ctx.set_projection_matrices(Ps)
+        ctx.set_radon_intermediates(dtrs, n_u, n_v, True)
+        cost = np.zeros((n, n), np.float32)
+        mean = ctx.evaluate(cost)
+        vals[name] = (mean, pair_values(cost, n))
+    assert rel_err(vals["hybrid"][1], vals["texture"][1]).max() < PAIR_TOL_REF
+    assert abs(vals["hybrid"][0] - vals["texture"][0]) < SUM_TOL * vals["texture"][0]
