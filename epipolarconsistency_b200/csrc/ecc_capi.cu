@@ -526,6 +526,12 @@ int ecc_set_projection_matrices(ecc_context* ctx, const double* Ps, int n)
     if (!ctx) return ECC_ERR_INVALID;
     Guard g(ctx);
     if (n < 0 || (n > 0 && !Ps)) return fail(ctx, ECC_ERR_INVALID, "ecc_set_projection_matrices: bad argument");
+    // optimiser loops hand over the whole set every step (Gui/SingleImageMotion.h:84-90): an unchanged set keeps its
+    // derived views on the device
+    if (n > 0 && n == ctx->n_views && ctx->Ps_d && !is_device_pointer(Ps) && ctx->Ps_h.size() == (size_t)12 * n &&
+        std::memcmp(ctx->Ps_h.data(), Ps, sizeof(double) * 12 * n) == 0)
+        return ECC_OK;
+    ctx->geometry_version++;
     ctx->n_views = n;
     ctx->Ps_h.resize((size_t)12 * n);
     if (n == 0) return ECC_OK;
@@ -546,6 +552,7 @@ int ecc_update_projection_matrix(ecc_context* ctx, int index, const double* P)
     // the stream may still be reading the previous host copy of this matrix (async H2D from pageable
     // memory completes before the call returns, so overwriting is safe)
     std::memcpy(&ctx->Ps_h[(size_t)12 * index], P, sizeof(double) * 12);
+    ctx->geometry_version++;
     ECC_CUDA(ctx, cudaMemcpyAsync(ctx->Ps_d + (size_t)12 * index, &ctx->Ps_h[(size_t)12 * index], sizeof(double) * 12,
                                   cudaMemcpyHostToDevice, ctx->stream));
     return launch_derive_views(ctx, ctx->Ps_d + (size_t)12 * index, 1, ctx->PinvTs_d + (size_t)12 * index,
@@ -846,6 +853,13 @@ int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds)
 {
     if (!ctx || !bounds || n_parts < 1) return ECC_ERR_INVALID;
     const long long n = ctx->n_views, total = n * (n - 1) / 2;
+    // the cut depends on the geometry and the sampling settings only: keep it while those stand
+    const std::vector<double> key = {(double)ctx->geometry_version, (double)n_parts, ctx->object_radius, ctx->dkappa,
+                                     (double)ctx->n_t, (double)ctx->step_t, (double)ctx->n_u, (double)ctx->n_v, (double)n};
+    if (key == ctx->partition_key && (int)ctx->partition_bounds.size() == n_parts + 1) {
+        std::memcpy(bounds, ctx->partition_bounds.data(), sizeof(long long) * (n_parts + 1));
+        return ECC_OK;
+    }
     std::vector<int> counts((size_t)total);
     if (total) {
         int rc = ecc_pair_sample_counts(ctx, counts.data());
@@ -861,6 +875,8 @@ int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds)
         while (part < n_parts && run >= all * part / n_parts) bounds[part++] = k + 1;
     }
     while (part <= n_parts) bounds[part++] = total;
+    ctx->partition_key = key;
+    ctx->partition_bounds.assign(bounds, bounds + n_parts + 1);
     return ECC_OK;
 }
 

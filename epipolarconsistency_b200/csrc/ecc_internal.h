@@ -57,6 +57,9 @@ struct ecc_context {
     float* Cs_d = nullptr;      // n*4
     float* PinvTs_d = nullptr;  // n*12
     size_t Ps_cap = 0;          // capacity in matrices of Ps_d / Cs_d / PinvTs_d
+    long long geometry_version = 0;         // bumped whenever a matrix changes
+    std::vector<double> partition_key;      // settings the cached pair partition was computed for
+    std::vector<long long> partition_bounds;
 
     // ---- radon intermediates ----
     int n_dtrs = 0, n_alpha = 0, n_t = 0, n_u = 0, n_v = 0, is_derivative = 1;
