@@ -232,6 +232,7 @@ void ecc_destroy(ecc_context* ctx)
     destroy_dtr_textures(ctx);
     free_image_pool(ctx);
     free_hybrid(ctx);
+    free_hybrid4(ctx);
     if (ctx->ramp_g_d) cudaFree(ctx->ramp_g_d);
     if (ctx->pre_work_d) cudaFree(ctx->pre_work_d);
     if (ctx->pre_small_d) cudaFree(ctx->pre_small_d);

@@ -39,6 +39,21 @@ struct HybridStage {
     alignas(64) unsigned char map_t[128] = {};
 };
 
+// Staging of the quad kernel (ecc_radon_hybrid4.cu): four images interleaved per texel.
+struct Hybrid4Stage {
+    int n_u = 0, n_v = 0, quads = 0;
+    std::vector<cudaArray_t> arrays;           // float4 arrays, one per quad
+    std::vector<cudaTextureObject_t> tex_h;
+    cudaTextureObject_t* tex_d = nullptr;
+    void* lin = nullptr;                       // [quads][n_v][n_u] float4
+    void* pad_n = nullptr;                     // [quads][n_v+1][n_u+1] float4
+    void* pad_t = nullptr;                     // [quads][n_u+1][n_v+1] float4
+    unsigned* queue = nullptr;
+    size_t queue_words = 0;
+    alignas(64) unsigned char map_n[128] = {};
+    alignas(64) unsigned char map_t[128] = {};
+};
+
 }  // namespace eccb200
 
 struct ecc_context {
@@ -110,6 +125,7 @@ struct ecc_context {
     float* ramp_g_d = nullptr;  // ramp-filter kernel g[n_t] (ecc_radon.cu)
     int ramp_n_t = 0;
     eccb200::HybridStage hybrid;
+    eccb200::Hybrid4Stage hybrid4;
 
     // ---- profiling ----
     bool profiling = false;
@@ -185,6 +201,9 @@ int ramp_filter(ecc_context* ctx, float* dtrs_d, int n, int n_alpha, int n_t);
 int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, const float* images_d, int n, int n_u,
                         int n_v, int n_alpha, int n_t, int post, float* out_d);
 void free_hybrid(ecc_context* ctx);
+// ---- launchers (ecc_radon_hybrid4.cu) ----
+int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d);
+void free_hybrid4(ecc_context* ctx);
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
 
 // ---- launchers (ecc_preprocess.cu) ----

@@ -331,9 +331,21 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
 {
     constexpr int kPool = 64;  // projections per launch
     const int pool = n_images < kPool ? n_images : kPool;
+    const bool deriv = (filter == ECC_FILTER_DERIVATIVE);  // ramp: plain line integrals first (RadonIntermediate.cu:160-168)
+    // development knob: ECC_HYBRID_QUADS=0 keeps the one-image-per-item hybrid kernel
+    static const int use_quads = getenv("ECC_HYBRID_QUADS") ? atoi(getenv("ECC_HYBRID_QUADS")) : 1;
+    if (interp == ECC_INTERP_HYBRID && deriv && use_quads) {
+        // the quad kernel stages its images itself (four projections interleaved per texel)
+        for (int first = 0; first < n_images; first += pool) {
+            const int n = (n_images - first < pool) ? n_images - first : pool;
+            const int rc4 = radon_hybrid4_launch(ctx, images_d + (size_t)first * n_u * n_v, n, n_u, n_v, n_alpha, n_t, post,
+                                                 out_d + (size_t)first * n_t * n_alpha);
+            if (rc4) return rc4;
+        }
+        return ECC_OK;
+    }
     int rc = ensure_pool(ctx, n_u, n_v, pool);
     if (rc) return rc;
-    const bool deriv = (filter == ECC_FILTER_DERIVATIVE);  // ramp: plain line integrals first (RadonIntermediate.cu:160-168)
     for (int first = 0; first < n_images; first += pool) {
         const int n = (n_images - first < pool) ? n_images - first : pool;
         for (int k = 0; k < n; k++) {

@@ -1,0 +1,479 @@
+// ecc_radon_hybrid4.cu -- the hybrid Radon kernel over QUADS of projections (sm_100a).
+//
+// Every projection of a data set has the same bin geometry: the sample positions, cell indices and bilinear weights of
+// a bin do not depend on the image.  ecc_radon_hybrid.cu spends ~33 instructions per sample in its shared-memory path,
+// ~19 of them on exactly that geometry.  Here four projections are interleaved texel by texel (float4): the window path
+// computes position, cell and weights once and applies them to four images with four 16-byte shared-memory loads
+// (~14 instructions per sample), and the texture path fetches float4 texels (one fetch = four images, same
+// channel-sample rate of the texture unit, a quarter of the instructions).  Queue, chunking, row windows, fall-backs and
+// the sample set are those of ecc_radon_hybrid.cu; per image the arithmetic is identical, so are the results.
+//   window: [kBoxW columns][kRows rows][4 images] floats, fetched by ONE 4-D TMA box per chunk from an edge-replicated
+//           interleaved copy (transposed for near-horizontal lines); the innermost box dimension is the image quad
+//           (16 bytes), so no start coordinate needs an alignment (cf. the 16-byte rule found in tools/tma_probe.cu).
+#include <climits>
+#include <cstdlib>
+
+#include "ecc_radon_common.cuh"
+
+namespace eccb200 {
+
+namespace {
+
+constexpr int kChunk4 = 16;        // pixels of the primary axis per chunk
+constexpr int kLead4 = 2;          // window columns in front of the chunk
+constexpr int kBoxW4 = 20;         // window columns [16j-2, 16j+18)
+constexpr int kRows4 = 200;        // window rows
+constexpr int kMaxChunks4 = 128;   // primary axis up to 2048 px
+
+struct Hybrid4Params {
+    const cudaTextureObject_t* texs;  // one float4 texture per quad
+    int n_quads, n_img;               // n_img = images that exist (the last quad may be partly empty)
+    int n_u, n_v, n_alpha, n_t, post;
+    int groups_a, groups_t;
+    int mode;
+    unsigned* counters;
+    unsigned* claim;
+    unsigned magic;
+    float* out;
+};
+
+struct Sum4 {
+    float x, y, z, w;
+};
+__device__ __forceinline__ void add4(Sum4& s, const float4& v) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+
+// The whole bin of four images through the texture unit (float4 texels), in the executed reference's shape
+// (ecc_radon_common.cuh: ref_last_sample); two samples per line in flight.
+__device__ __forceinline__ void bin_texture4(cudaTextureObject_t tex, const BinLine& L, Sum4& res)
+{
+    float o0 = L.o0 + 0.5f, o1 = L.o1 + 0.5f;
+    const float d0 = L.d0, d1 = L.d1, t_max = L.t_max;
+    o0 -= 0.5f * d1;
+    o1 += 0.5f * d0;
+    Sum4 sum = {0.f, 0.f, 0.f, 0.f}, sumo = {0.f, 0.f, 0.f, 0.f};
+    float t = L.t;
+    bool none_yet = true;
+#define ECC_TEX4_A(tt) tex2D<float4>(tex, fmaf((tt), d0, o0), fmaf((tt), d1, o1))
+#define ECC_TEX4_B(tt) tex2D<float4>(tex, fmaf((tt), d0, o0) + d1, fmaf((tt), d1, o1) - d0)
+    if (!(t + 1.98f > t_max)) {
+        const float r3 = t_max - 1.98f;
+#pragma unroll 1
+        do {
+            const float t1 = t + kStep, t2 = t1 + kStep, t3 = t2 + kStep;
+            const float4 a0 = ECC_TEX4_A(t), b0 = ECC_TEX4_B(t), a1 = ECC_TEX4_A(t1), b1 = ECC_TEX4_B(t1);
+            const float4 a2 = ECC_TEX4_A(t2), b2 = ECC_TEX4_B(t2), a3 = ECC_TEX4_A(t3), b3 = ECC_TEX4_B(t3);
+            add4(sum, a0); add4(sumo, b0);
+            add4(sum, a1); add4(sumo, b1);
+            add4(sum, a2); add4(sumo, b2);
+            add4(sum, a3); add4(sumo, b3);
+            t = t3 + kStep;
+        } while (!(t > r3));
+        none_yet = false;
+    }
+    const float t1 = t + kStep;
+    if (!(t1 > t_max)) {
+        const float4 a0 = ECC_TEX4_A(t), b0 = ECC_TEX4_B(t), a1 = ECC_TEX4_A(t1), b1 = ECC_TEX4_B(t1);
+        add4(sum, a0); add4(sumo, b0);
+        add4(sum, a1); add4(sumo, b1);
+        t = t1 + kStep;
+        none_yet = false;
+    }
+    if (t <= t_max || none_yet) {
+        add4(sum, ECC_TEX4_A(t));
+        add4(sumo, ECC_TEX4_B(t));
+    }
+#undef ECC_TEX4_A
+#undef ECC_TEX4_B
+    res.x = (sum.x - sumo.x) * kStep;
+    res.y = (sum.y - sumo.y) * kStep;
+    res.z = (sum.z - sumo.z) * kStep;
+    res.w = (sum.w - sumo.w) * kStep;
+}
+
+// One sample position applied to the four images of the window: position -> cell and fractions -> weights once
+// (ecc_radon_hybrid.cu: sample_window has the derivation), four 16-byte loads, then per image
+// v00 + (w10 (v10-v00) + w01 (v01-v00) + w11 (v11-v00)) / 256.
+__device__ __forceinline__ void sample_window4(unsigned base, float pri, float sec, Sum4& acc)
+{
+    const float Ps = fmaf(pri, 256.f, -127.5f);
+    const float Ss = fmaf(sec, 256.f, -127.5f);
+    const unsigned Pi = __float_as_uint(__fadd_rd(Ps, 8388608.f));
+    const unsigned Si = __float_as_uint(__fadd_rd(Ss, 8388608.f));
+    const unsigned a = Pi & 255u, b = Si & 255u;
+    const unsigned addr = base + (((Pi >> 8) * kRows4 + (Si >> 8)) << 4);
+    float4 v00, v01, v10, v11;
+    asm volatile(
+        "ld.shared.v4.f32 {%0, %1, %2, %3}, [%16];\n"
+        "ld.shared.v4.f32 {%4, %5, %6, %7}, [%16+16];\n"
+        "ld.shared.v4.f32 {%8, %9, %10, %11}, [%16+3200];\n"
+        "ld.shared.v4.f32 {%12, %13, %14, %15}, [%16+3216];\n"
+        : "=f"(v00.x), "=f"(v00.y), "=f"(v00.z), "=f"(v00.w), "=f"(v01.x), "=f"(v01.y), "=f"(v01.z), "=f"(v01.w), "=f"(v10.x),
+          "=f"(v10.y), "=f"(v10.z), "=f"(v10.w), "=f"(v11.x), "=f"(v11.y), "=f"(v11.z), "=f"(v11.w)
+        : "r"(addr));
+    const unsigned w11 = (a * b + 128u) >> 8;
+    const float f11 = __uint2float_rn(w11), f10 = __uint2float_rn(a - w11), f01 = __uint2float_rn(b - w11);
+#define ECC_ONE(c)                                                              \
+    {                                                                           \
+        float t = f10 * (v10.c - v00.c);                                        \
+        t = fmaf(f01, v01.c - v00.c, t);                                        \
+        t = fmaf(f11, v11.c - v00.c, t);                                        \
+        acc.c += fmaf(t, 0.00390625f, v00.c);                                   \
+    }
+    ECC_ONE(x) ECC_ONE(y) ECC_ONE(z) ECC_ONE(w)
+#undef ECC_ONE
+}
+static_assert(kRows4 * 16 == 3200, "sample_window4 hard-codes the column pitch");
+
+struct Item4 {
+    int quad, ix, iy;
+};
+__device__ __forceinline__ Item4 item_bins4(int item, int wi, int lane, const Hybrid4Params& p)
+{
+    Item4 r;
+    const int per_quad = p.groups_a * p.groups_t;
+    r.quad = item / per_quad;
+    const int rem = item - r.quad * per_quad;
+    const int tg = rem / p.groups_a, ag = rem - tg * p.groups_a;
+    const int q4 = lane >> 2, ql = lane & 3;
+    r.ix = ag * kItemAngles + (wi & 3) * 2 + (ql & 1);
+    r.iy = tg * kItemT + (wi >> 2) * 16 + q4 * 2 + (ql >> 1);
+    return r;
+}
+
+__device__ __forceinline__ void store4(const Hybrid4Params& p, const Item4& B, const Sum4& r, bool valid)
+{
+    const size_t stride = (size_t)p.n_t * p.n_alpha;
+    float* dst = p.out + (size_t)B.quad * 4 * stride + (size_t)B.iy * p.n_alpha + B.ix;
+    const int left = p.n_img - B.quad * 4;
+    const float v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        if (c < left) dst[c * stride] = valid ? post_process(v[c], p.post) : 0.f;
+}
+
+template <int MAXTHREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
+radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_constant__ CUtensorMap map_t, const Hybrid4Params p)
+{
+    extern __shared__ __align__(128) unsigned char window_raw[];
+    __shared__ __align__(8) unsigned long long mbar_store[1];
+    __shared__ int s_item, s_jmin, s_jmax, s_fallback;
+    __shared__ int win_lo[kMaxChunks4], win_hi[kMaxChunks4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned total_items = (unsigned)(p.n_quads * p.groups_a * p.groups_t);
+    const float n_u = (float)p.n_u, n_v = (float)p.n_v;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar_store[0]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= kWindowWarps) {
+        if (p.mode == 2) return;
+        // ---------------- texture warps ----------------
+        for (;;) {
+            int sub = 0;
+            if (lane == 0) sub = take_back(p.counters, p.claim, total_items);
+            sub = __shfl_sync(0xffffffffu, sub, 0);
+            if (sub < 0) break;
+            const int item = (int)total_items - 1 - sub / kSubTiles;
+            const Item4 B = item_bins4(item, sub % kSubTiles, lane, p);
+            if (B.ix >= p.n_alpha || B.iy >= p.n_t) continue;
+            const BinLine L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
+            Sum4 r = {0.f, 0.f, 0.f, 0.f};
+            if (L.valid) bin_texture4(p.texs[B.quad], L, r);
+            store4(p, B, r, L.valid);
+        }
+        return;
+    }
+
+    // ---------------- window warps ----------------
+    if (p.mode == 1) return;
+    const unsigned window_base = smem_u32(window_raw);
+    const unsigned buf_bytes = (unsigned)kRows4 * kBoxW4 * 16u;
+    const unsigned mbar0 = smem_u32(&mbar_store[0]);
+    unsigned phase0 = 0;
+    for (;;) {
+        if (tid == 0) {
+            s_item = take_front(p.counters, p.claim, total_items);
+            s_jmin = INT_MAX;
+            s_jmax = INT_MIN;
+            s_fallback = 0;
+        }
+        if (tid < kMaxChunks4) { win_lo[tid] = INT_MAX; win_hi[tid] = INT_MIN; }
+        group_sync();
+        const int item = s_item;
+        if (item < 0) break;
+        const Item4 B = item_bins4(item, warp, lane, p);
+        const bool in_range = B.ix < p.n_alpha && B.iy < p.n_t;
+        BinLine L;
+        L.valid = false;
+        L.swapped = false;
+        if (in_range) L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
+        bool safe = false;
+        if (in_range && L.valid) {
+            const float ax = L.o0 + L.t * L.d0, ay = L.o1 + L.t * L.d1, bx = L.o0 + L.t_max * L.d0, by = L.o1 + L.t_max * L.d1;
+            const float lo = 1.f - 1e-3f, hx = n_u - 1.f + 1e-3f, hy = n_v - 1.f + 1e-3f;
+            safe = !L.swapped && fminf(ax, bx) >= lo && fmaxf(ax, bx) <= hx && fminf(ay, by) >= lo && fmaxf(ay, by) <= hy;
+        }
+        const bool live = safe;
+
+        const int per_quad = p.groups_a * p.groups_t;
+        const int ag = (item % per_quad) % p.groups_a;
+        const float alpha_mid = ((ag * kItemAngles + 0.5f * (kItemAngles - 1)) / (float)p.n_alpha - 0.5f) * ECC_PI_F;
+        const bool vertical = fabsf(sinf(alpha_mid)) > fabsf(cosf(alpha_mid));
+        const int dir = (vertical && alpha_mid < 0.f) ? -1 : 1;
+
+        float oA0 = L.o0 + 0.5f, oA1 = L.o1 + 0.5f;
+        oA0 -= 0.5f * L.d1;
+        oA1 += 0.5f * L.d0;
+        const float op = vertical ? oA1 : oA0, dp = vertical ? L.d1 : L.d0;
+        const float os = vertical ? oA0 : oA1, ds = vertical ? L.d0 : L.d1;
+        const float offp = vertical ? -L.d0 : L.d1, offs = vertical ? L.d1 : -L.d0;
+        const float inv_dp = live ? 1.f / dp : 0.f;
+
+        int jmin_l = INT_MAX, jmax_l = INT_MIN;
+        if (live) {
+            const float pa = fmaf(L.t, dp, op) - 0.5f, pb = fmaf(L.t_max, dp, op) - 0.5f;
+            const int ja = (int)floorf(fminf(pa, pb) * (1.f / kChunk4)), jb = (int)floorf(fmaxf(pa, pb) * (1.f / kChunk4));
+            jmin_l = ja - 1;
+            jmax_l = jb + 1;
+        }
+        {
+            const int wmin = __reduce_min_sync(0xffffffffu, jmin_l), wmax = __reduce_max_sync(0xffffffffu, jmax_l);
+            if (lane == 0 && wmin <= wmax) { atomicMin(&s_jmin, wmin + 1); atomicMax(&s_jmax, wmax - 1); }
+        }
+        group_sync();
+        const int jlo = s_jmin, jhi = s_jmax;
+        const int n_chunks = jhi - jlo + 1;
+        const bool too_long = n_chunks > kMaxChunks4;
+
+        if (n_chunks > 0 && !too_long) {
+            for (int k = 0; k < n_chunks; k++) {
+                const int j = jlo + k;
+                int lo = INT_MAX, hi = INT_MIN;
+                if (live && j >= jmin_l && j <= jmax_l) {
+                    const float t0 = ((float)(j * kChunk4 - 2) + 0.5f - op) * inv_dp;
+                    const float t1 = ((float)(j * kChunk4 + kChunk4 + 2) + 0.5f - op) * inv_dp;
+                    const float s0 = fmaf(fmaxf(fminf(t0, t1), L.t - 2.f), ds, os);
+                    const float s1 = fmaf(fminf(fmaxf(t0, t1), L.t_max + 2.f), ds, os);
+                    lo = (int)floorf(fminf(s0, s1) - 2.0f);
+                    hi = (int)floorf(fmaxf(s0, s1) + 1.0f) + 1;
+                }
+                const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+                if (lane == 0 && wlo <= whi) { atomicMin(&win_lo[k], wlo); atomicMax(&win_hi[k], whi); }
+            }
+        }
+        group_sync();
+        if (n_chunks > 0 && !too_long && tid < n_chunks) {
+            if (win_lo[tid] <= win_hi[tid] && win_hi[tid] - win_lo[tid] + 1 > kRows4) s_fallback = 1;
+        }
+        if (tid == 0 && too_long) s_fallback = 1;
+        group_sync();
+        const bool fallback = s_fallback != 0;
+
+        Sum4 result = {0.f, 0.f, 0.f, 0.f};
+        if (n_chunks > 0 && !fallback) {
+            const CUtensorMap* map = vertical ? &map_n : &map_t;
+            float t = live ? L.t : 3.0e38f;
+            const float t_max = live ? ref_last_sample(L.t, L.t_max) : -3.0e38f;
+            Sum4 sum = {0.f, 0.f, 0.f, 0.f}, sumo = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < n_chunks; k++) {
+                const int kk = dir > 0 ? k : n_chunks - 1 - k;
+                const int j = jlo + kk;
+                const int lo = win_lo[kk], hi = win_hi[kk];
+                group_sync();  // everybody is done with the window
+                if (lo > hi) continue;
+                if (tid == 0) {
+                    mbar_expect_tx(mbar0, buf_bytes);
+                    tma_load_4d(window_base, map, 0, lo, j * kChunk4 - kLead4, B.quad, mbar0);
+                }
+                mbar_wait(mbar0, phase0);
+                phase0 ^= 1u;
+                float lim = t_max;
+                if (k + 1 < n_chunks) {
+                    const float edge = (float)(dir > 0 ? (j + 1) * kChunk4 : j * kChunk4) + 0.5f;
+                    lim = fminf(t_max, (edge - op) * inv_dp);
+                }
+                const unsigned base = window_base - 16u * ((p.magic + (unsigned)(j * kChunk4 - kLead4)) * kRows4 + p.magic + (unsigned)lo);
+#pragma unroll 1
+                for (; t <= lim; t += kStep) {
+                    const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
+                    sample_window4(base, pri, sec, sum);
+                    sample_window4(base, pri + offp, sec + offs, sumo);
+                }
+            }
+            result.x = (sum.x - sumo.x) * kStep;
+            result.y = (sum.y - sumo.y) * kStep;
+            result.z = (sum.z - sumo.z) * kStep;
+            result.w = (sum.w - sumo.w) * kStep;
+        }
+        if (in_range) {
+            if (L.valid && (fallback || !safe)) bin_texture4(p.texs[B.quad], L, result);
+            store4(p, B, result, L.valid);
+        }
+        group_sync();
+    }
+}
+
+// ---- staging: four images interleaved texel by texel ------------------------------------------------------------------
+// lin  [q][n_v][n_u] float4            -> copied into the quad's CUDA array (texture path)
+// padn [q][n_v+1][n_u+1] float4        edge-replicated (window path, near-vertical lines)
+// padt [q][n_u+1][n_v+1] float4        its transpose (near-horizontal lines)
+__global__ void interleave4_kernel(const float* __restrict__ src, int n_img, int n_u, int n_v, float4* __restrict__ lin,
+                                   float4* __restrict__ padn)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, q = blockIdx.z;
+    if (x > n_u) return;
+    const int xs = min(x, n_u - 1), ys = min(y, n_v - 1);
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int img = q * 4 + c;
+        v[c] = img < n_img ? src[((size_t)img * n_v + ys) * n_u + xs] : 0.f;
+    }
+    const float4 t = make_float4(v[0], v[1], v[2], v[3]);
+    padn[((size_t)q * (n_v + 1) + y) * (n_u + 1) + x] = t;
+    if (x < n_u && y < n_v) lin[((size_t)q * n_v + y) * n_u + x] = t;
+}
+__global__ void transpose4_kernel(const float4* __restrict__ padn, int n_u, int n_v, float4* __restrict__ padt)
+{
+    __shared__ float4 tile[16][17];
+    const int q = blockIdx.z, x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+    const float4* s = padn + (size_t)q * (n_v + 1) * (n_u + 1);
+    {
+        const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+        if (x <= n_u && y <= n_v) tile[threadIdx.y][threadIdx.x] = s[(size_t)y * (n_u + 1) + x];
+    }
+    __syncthreads();
+    {
+        const int x = x0 + threadIdx.y, y = y0 + threadIdx.x;  // output row = x, column = y
+        if (x <= n_u && y <= n_v) padt[((size_t)q * (n_u + 1) + x) * (n_v + 1) + y] = tile[threadIdx.x][threadIdx.y];
+    }
+}
+
+int encode_map4(ecc_context* ctx, CUtensorMap* map, float4* base, int pitch, int rows, int count)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(ctx, ECC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    const cuuint64_t dims[4] = {4, (cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)count};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)pitch * 16u, (cuuint64_t)pitch * rows * 16u};
+    const cuuint32_t box[4] = {4, kRows4, kBoxW4, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, ECC_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed (" + std::to_string((int)r) + ")");
+    return ECC_OK;
+}
+
+}  // namespace
+
+void free_hybrid4(ecc_context* ctx)
+{
+    Hybrid4Stage& H = ctx->hybrid4;
+    for (auto t : H.tex_h) cudaDestroyTextureObject(t);
+    for (auto a : H.arrays) cudaFreeArray(a);
+    if (H.tex_d) cudaFree(H.tex_d);
+    if (H.lin) cudaFree(H.lin);
+    if (H.pad_n) cudaFree(H.pad_n);
+    if (H.pad_t) cudaFree(H.pad_t);
+    if (H.queue) cudaFree(H.queue);
+    H = Hybrid4Stage();
+}
+
+// n images (device, dense) -> their Radon intermediates; works on ceil(n/4) quads.
+int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d)
+{
+    Hybrid4Stage& H = ctx->hybrid4;
+    const int nq = (n + 3) / 4;
+    if (H.n_u != n_u || H.n_v != n_v || H.quads < nq) {
+        const int quads = nq > H.quads ? nq : H.quads;
+        free_hybrid4(ctx);
+        H.n_u = n_u;
+        H.n_v = n_v;
+        const size_t px = (size_t)n_u * n_v, pxp = (size_t)(n_u + 1) * (n_v + 1);
+        ECC_CUDA(ctx, cudaMalloc(&H.lin, sizeof(float4) * px * quads));
+        ECC_CUDA(ctx, cudaMalloc(&H.pad_n, sizeof(float4) * pxp * quads));
+        ECC_CUDA(ctx, cudaMalloc(&H.pad_t, sizeof(float4) * pxp * quads));
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+        for (int k = 0; k < quads; k++) {
+            cudaArray_t arr = nullptr;
+            ECC_CUDA(ctx, cudaMallocArray(&arr, &desc, n_u, n_v));
+            H.arrays.push_back(arr);
+            cudaResourceDesc res = {};
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = arr;
+            cudaTextureDesc td = {};
+            td.normalizedCoords = 0;
+            td.filterMode = cudaFilterModeLinear;
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.readMode = cudaReadModeElementType;
+            cudaTextureObject_t tex = 0;
+            ECC_CUDA(ctx, cudaCreateTextureObject(&tex, &res, &td, nullptr));
+            H.tex_h.push_back(tex);
+            H.quads = k + 1;
+        }
+        ECC_CUDA(ctx, cudaMalloc(&H.tex_d, sizeof(cudaTextureObject_t) * quads));
+        ECC_CUDA(ctx, cudaMemcpyAsync(H.tex_d, H.tex_h.data(), sizeof(cudaTextureObject_t) * quads, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = encode_map4(ctx, (CUtensorMap*)H.map_n, (float4*)H.pad_n, n_u + 1, n_v + 1, quads);
+        if (rc) return rc;
+        rc = encode_map4(ctx, (CUtensorMap*)H.map_t, (float4*)H.pad_t, n_v + 1, n_u + 1, quads);
+        if (rc) return rc;
+    }
+    interleave4_kernel<<<dim3((n_u + 1 + 127) / 128, n_v + 1, nq), 128, 0, ctx->stream>>>(images_d, n, n_u, n_v, (float4*)H.lin, (float4*)H.pad_n);
+    transpose4_kernel<<<dim3((n_u + 1 + 15) / 16, (n_v + 1 + 15) / 16, nq), dim3(16, 16), 0, ctx->stream>>>((const float4*)H.pad_n, n_u, n_v, (float4*)H.pad_t);
+    for (int q = 0; q < nq; q++)
+        ECC_CUDA(ctx, cudaMemcpy2DToArrayAsync(H.arrays[q], 0, 0, (const float4*)H.lin + (size_t)q * n_u * n_v, sizeof(float4) * n_u,
+                                               sizeof(float4) * n_u, n_v, cudaMemcpyDeviceToDevice, ctx->stream));
+    Hybrid4Params P;
+    P.texs = H.tex_d;
+    P.n_quads = nq;
+    P.n_img = n;
+    P.n_u = n_u;
+    P.n_v = n_v;
+    P.n_alpha = n_alpha;
+    P.n_t = n_t;
+    P.post = post;
+    P.groups_a = (n_alpha + kItemAngles - 1) / kItemAngles;
+    P.groups_t = (n_t + kItemT - 1) / kItemT;
+    const size_t queue_words = 2 + (size_t)nq * P.groups_a * P.groups_t;
+    if (H.queue_words < queue_words) {
+        if (H.queue) cudaFree(H.queue);
+        H.queue = nullptr;
+        H.queue_words = 0;
+        ECC_CUDA(ctx, cudaMalloc(&H.queue, sizeof(unsigned) * queue_words));
+        H.queue_words = queue_words;
+    }
+    ECC_CUDA(ctx, cudaMemsetAsync(H.queue, 0, sizeof(unsigned) * queue_words, ctx->stream));
+    P.counters = H.queue;
+    P.claim = H.queue + 2;
+    P.magic = 0x4B0000u;
+    P.out = out_d;
+    static const int nt = env_int("ECC_HYBRID4_NT", 8);
+    static const int ctas = env_int("ECC_HYBRID4_CTAS", 2);
+    static const int mode = env_int("ECC_HYBRID_MODE", 0);
+    P.mode = mode;
+    const int threads = (kWindowWarps + nt) * 32;
+    const size_t smem = (size_t)kRows4 * kBoxW4 * 16;
+    const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;
+    const CUtensorMap& mt = *(const CUtensorMap*)H.map_t;
+    const int slot = prof_begin(ctx, FAM_RADON);
+    if (threads <= 512 && ctas <= 2) {
+        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid4_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        radon_hybrid4_kernel<512, 2><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
+    } else if (threads <= 384 && ctas == 3) {
+        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid4_kernel<384, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        radon_hybrid4_kernel<384, 3><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
+    } else {
+        prof_end(ctx, slot);
+        return fail(ctx, ECC_ERR_INVALID, "ECC_HYBRID4_NT / ECC_HYBRID4_CTAS: unsupported combination");
+    }
+    prof_end(ctx, slot);
+    ECC_CUDA(ctx, cudaGetLastError());
+    return ECC_OK;
+}
+
+}  // namespace eccb200
