@@ -332,17 +332,22 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
     constexpr int kPool = 64;  // projections per launch
     const int pool = n_images < kPool ? n_images : kPool;
     const bool deriv = (filter == ECC_FILTER_DERIVATIVE);  // ramp: plain line integrals first (RadonIntermediate.cu:160-168)
-    // development knob: ECC_HYBRID_QUADS=0 keeps the one-image-per-item hybrid kernel
+    // development knob: ECC_HYBRID_QUADS=0 keeps the one-image-per-item hybrid kernel for everything
     static const int use_quads = getenv("ECC_HYBRID_QUADS") ? atoi(getenv("ECC_HYBRID_QUADS")) : 1;
-    if (interp == ECC_INTERP_HYBRID && deriv && use_quads) {
-        // the quad kernel stages its images itself (four projections interleaved per texel)
-        for (int first = 0; first < n_images; first += pool) {
-            const int n = (n_images - first < pool) ? n_images - first : pool;
+    if (interp == ECC_INTERP_HYBRID && deriv && use_quads && n_images >= 3) {
+        // quads of projections through the quad kernel (it stages its images itself, four interleaved per texel); a
+        // remainder of three is padded to a quad, one or two left-over images take the one-image hybrid kernel below
+        const int rem = n_images % 4;
+        const int n_quad_images = (rem == 3) ? n_images : n_images - rem;
+        for (int first = 0; first < n_quad_images; first += pool) {
+            const int n = (n_quad_images - first < pool) ? n_quad_images - first : pool;
             const int rc4 = radon_hybrid4_launch(ctx, images_d + (size_t)first * n_u * n_v, n, n_u, n_v, n_alpha, n_t, post,
                                                  out_d + (size_t)first * n_t * n_alpha);
             if (rc4) return rc4;
         }
-        return ECC_OK;
+        if (n_quad_images == n_images) return ECC_OK;
+        return radon_batch(ctx, images_d + (size_t)n_quad_images * n_u * n_v, n_images - n_quad_images, n_u, n_v, n_alpha, n_t,
+                           filter, post, interp, out_d + (size_t)n_quad_images * n_t * n_alpha);
     }
     int rc = ensure_pool(ctx, n_u, n_v, pool);
     if (rc) return rc;

@@ -22,7 +22,7 @@ namespace {
 constexpr int kChunk4 = 16;        // pixels of the primary axis per chunk
 constexpr int kLead4 = 2;          // window columns in front of the chunk
 constexpr int kBoxW4 = 20;         // window columns [16j-2, 16j+18)
-constexpr int kRows4 = 200;        // window rows
+constexpr int kRows4 = 201;        // window rows; odd, so that neighbouring columns start one 16-byte bank group apart
 constexpr int kMaxChunks4 = 128;   // primary axis up to 2048 px
 
 struct Hybrid4Params {
@@ -105,8 +105,8 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
     asm volatile(
         "ld.shared.v4.f32 {%0, %1, %2, %3}, [%16];\n"
         "ld.shared.v4.f32 {%4, %5, %6, %7}, [%16+16];\n"
-        "ld.shared.v4.f32 {%8, %9, %10, %11}, [%16+3200];\n"
-        "ld.shared.v4.f32 {%12, %13, %14, %15}, [%16+3216];\n"
+        "ld.shared.v4.f32 {%8, %9, %10, %11}, [%16+3216];\n"
+        "ld.shared.v4.f32 {%12, %13, %14, %15}, [%16+3232];\n"
         : "=f"(v00.x), "=f"(v00.y), "=f"(v00.z), "=f"(v00.w), "=f"(v01.x), "=f"(v01.y), "=f"(v01.z), "=f"(v01.w), "=f"(v10.x),
           "=f"(v10.y), "=f"(v10.z), "=f"(v10.w), "=f"(v11.x), "=f"(v11.y), "=f"(v11.z), "=f"(v11.w)
         : "r"(addr));
@@ -122,7 +122,7 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
     ECC_ONE(x) ECC_ONE(y) ECC_ONE(z) ECC_ONE(w)
 #undef ECC_ONE
 }
-static_assert(kRows4 * 16 == 3200, "sample_window4 hard-codes the column pitch");
+static_assert(kRows4 * 16 == 3216, "sample_window4 hard-codes the column pitch");
 
 struct Item4 {
     int quad, ix, iy;
