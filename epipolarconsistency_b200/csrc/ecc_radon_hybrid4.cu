@@ -19,9 +19,12 @@ namespace eccb200 {
 
 namespace {
 
-constexpr int kChunk4 = 16;        // pixels of the primary axis per chunk
-constexpr int kLead4 = 2;          // window columns in front of the chunk
-constexpr int kBoxW4 = 20;         // window columns [16j-2, 16j+18)
+#ifndef ECC_CHUNK4
+#define ECC_CHUNK4 16
+#endif
+constexpr int kChunk4 = ECC_CHUNK4;     // pixels of the primary axis per chunk
+constexpr int kLead4 = 2;               // window columns in front of the chunk
+constexpr int kBoxW4 = ECC_CHUNK4 + 4;  // window columns [c0-2, c0+chunk+2)
 constexpr int kRows4 = 201;        // window rows; odd, so that neighbouring columns start one 16-byte bank group apart
 constexpr int kMaxChunks4 = 128;   // primary axis up to 2048 px
 
