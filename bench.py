@@ -218,19 +218,19 @@ def run_b200(args):
                     "mean_ecc": mean_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": ("radon_hybrid_kernel (texture data pipe + issue-slot bound; " if args.radon == "hybrid" else "radon_kernel (texture-unit bound; ") + "algorithmic tap bytes vs HBM copy peak)",
+            "roofline": {"bound": "hbm", "kernel": ("radon_hybrid4_kernel (bound by the two on-chip data pipes: texture + shared memory; " if args.radon == "hybrid" else "radon_kernel (texture-unit bound; ") + "algorithmic tap bytes vs HBM copy peak)",
                          "achieved": radon_gbs, "peak": peak, "unit": "GB/s", "frac": radon_gbs / peak, "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 64-projection launch of this command under
-                         # ncu --set full (profiles/ncu_radon_hybrid_bench_r01.txt: 449.8 + 142.0 MB), scaled to the
+                         # ncu --set full (profiles/ncu_radon_hybrid4_bench_r01.txt: 532.6 + 147.7 MB), scaled to the
                          # projections per launch of this run; only known for the C3 image size and the hybrid engine
-                         "traffic": (5.918e8 / 64.0 * (hi - lo) * args.steps / max(radon_launches, 1)
+                         "traffic": (6.803e8 / 64.0 * (hi - lo) * args.steps / max(radon_launches, 1)
                                      if (args.radon == "hybrid" and args.workload == "c3") else None),
                          "samples_per_s": radon_gbs * 1e9 / 16.0,
                          "tex_rate_frac": (radon_gbs * 1e9 / 16.0) / 1.09e12,
                          "note": "16 B per bilinear sample x %.4g samples per projection, on-chip traffic (hence frac > 1 against the "
-                                 "HBM copy peak; DRAM moves 9.2 MB per projection); tex_rate_frac = samples/s over the measured tex2D rate of "
+                                 "HBM copy peak; DRAM moves 10.6 MB per projection); tex_rate_frac = samples/s over the measured tex2D rate of "
                                  "this GPU (1.09e12/s at 1965 MHz, profiles/tex_probe_r01.txt); ncu of a launch of this command: texture "
-                                 "data pipe 99 %% of peak, issue slots 89 %% active (profiles/ncu_radon_hybrid_bench_r01.txt)" % samples_per_proj},
+                                 "data pipe 97 %% of peak, shared-memory pipe 81 %%, issue slots 54 %% (profiles/ncu_radon_hybrid4_bench_r01.txt)" % samples_per_proj},
             "roofline_pairs": {"bound": "hbm", "kernel": "pairs_kernel (L1/texture gather bound)", "achieved": pairs_gbs, "peak": peak,
                                "unit": "GB/s", "frac": pairs_gbs / peak, "kappa_samples": float(counts.sum())},
         }
