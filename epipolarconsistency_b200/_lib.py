@@ -45,6 +45,7 @@ SIGNATURES = {
     "ecc_pair_sample_counts": (C.c_int, [c_ctx, c_vp]),
     "ecc_partition_pairs": (C.c_int, [c_ctx, C.c_int, c_vp]),
     "ecc_make_circular_trajectory": (None, [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, c_vp]),
+    "ecc_camera_intrinsics": (None, [c_vp, c_vp, c_vp, c_vp]),
     "ecc_preprocess_defaults": (None, [c_vp]),
     "ecc_preprocess": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "ecc_synth_projections": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),

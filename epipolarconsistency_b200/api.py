@@ -253,6 +253,15 @@ def make_circular_trajectory(n_proj, sid, sdd, n_u, n_v, max_angle_deg, pixel_sp
     return Ps
 
 
+def camera_intrinsics(P):
+    """(focal length in px, principal point u, v) of a projection matrix: K(0,0), K(0,2), K(1,2) of
+    Geometry::getCameraIntrinsics (ProjectionMatrix.cpp:27-67)."""
+    P = np.ascontiguousarray(P, np.float64).reshape(12)
+    f, u, v = C.c_double(), C.c_double(), C.c_double()
+    _lib.load().ecc_camera_intrinsics(_ptr(P), C.addressof(f), C.addressof(u), C.addressof(v))
+    return f.value, u.value, v.value
+
+
 def similarity_2d(x):
     """ModelSimilarity2D::getInstance (LibProjectiveGeometry/Models/ModelSimilarity2D.hxx:52-72): x = translation u, v,
     rotation, scale -> 3x3."""

@@ -340,6 +340,15 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
     return ECC_OK;
 }
 
+void ecc_camera_intrinsics(const double* P, double* focal_px, double* principal_u, double* principal_v)
+{
+    double fu = 0, u0 = 0, v0 = 0;
+    if (P) camera_intrinsics_host(P, &fu, &u0, &v0);
+    if (focal_px) *focal_px = fu;
+    if (principal_u) *principal_u = u0;
+    if (principal_v) *principal_v = v0;
+}
+
 void ecc_preprocess_defaults(ecc_preprocess_params* p)
 {
     if (!p) return;

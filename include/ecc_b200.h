@@ -120,6 +120,10 @@ void ecc_preprocess_defaults(ecc_preprocess_params* params);
 int ecc_preprocess(ecc_context* ctx, float* images, int n, int n_u, int n_v, const ecc_preprocess_params* params,
                    const double* Ps);
 
+/* K(0,0), K(0,2), K(1,2) of Geometry::getCameraIntrinsics (LibProjectiveGeometry/ProjectionMatrix.cpp:27-67; RQ decomposition
+ * with positive diagonal, K(2,2) = 1): focal length in pixels and principal point, as the cosine weighting uses them. Host only. */
+void ecc_camera_intrinsics(const double* P, double* focal_px, double* principal_u, double* principal_v);
+
 /* ---- Metric state (MetricRadonIntermediate) ------------------------------------------------ */
 
 /* setRadonIntermediates (EpipolarConsistencyRadonIntermediate.cpp:87-106).  dtrs [h|d]:

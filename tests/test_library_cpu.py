@@ -61,3 +61,29 @@ def test_derived_views_bit_identical_to_reference_headers():
     A, Cs = api.derive_views_host(gold["Ps"])
     assert np.array_equal(A, gold["pinvT"])
     assert np.array_equal(Cs, gold["Cs"])
+
+
+def test_camera_intrinsics_and_similarity_models_host():
+    """Host helpers of the library against independent numpy restatements: the closed-form intrinsics equal numpy's RQ
+    decomposition (also for a skewed, scaled matrix); the similarity models compose as the reference's do."""
+    import oracle_lib as ol
+    from epipolarconsistency_b200 import api
+    rng = np.random.default_rng(3)
+    Ps = ol.circular_trajectory(5, 750, 1200, 640, 480, 200, 0.8)
+    K = np.array([[900.0, 3.0, 310.0], [0, 880.0, 255.0], [0, 0, 1.0]])
+    for P in list(Ps) + [(-2.5 * K @ np.hstack([np.linalg.qr(rng.standard_normal((3, 3)))[0], rng.standard_normal((3, 1))])).T.reshape(12)]:
+        got = api.camera_intrinsics(P)
+        want = ol.camera_intrinsics(P)
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-9)
+    P = Ps[2]
+    assert np.array_equal(api.camera_similarity_2d3d(P, [0] * 11), P)
+    x = [1.5, -2.0, 0.01, 0.02, 3.0, -1.0, 2.0, 0.02, -0.01, 0.03, 0.01]
+    H, T = api.similarity_2d(x[:4]), api.similarity_3d(x[4:])
+    assert np.allclose(H[:2, :2] @ H[:2, :2].T, (1.02 ** 2) * np.eye(2)) and H[0, 2] == 1.5 and H[1, 2] == -2.0
+    R = T[:3, :3] / 1.01
+    assert np.allclose(R @ R.T, np.eye(3)) and abs(np.linalg.det(R) - 1) < 1e-12 and np.array_equal(T[:3, 3], [3.0, -1.0, 2.0])
+    # R = Rx Ry Rz: a point on the z axis is moved by Ry then Rx only
+    z = R @ np.array([0, 0, 1.0])
+    assert np.allclose(z, [np.sin(0.01 * -1) * 0 + np.sin(-0.01), -np.sin(0.02) * np.cos(-0.01), np.cos(0.02) * np.cos(-0.01)], atol=1e-12)
+    want = (H @ P.reshape(4, 3).T @ T).T.reshape(12)
+    assert np.allclose(api.camera_similarity_2d3d(P, x), want, rtol=1e-13, atol=1e-13)
