@@ -3,8 +3,9 @@
 1240x960 (config C3: Radon intermediates 768x768, dkappa 0.01 deg, 200 deg short scan, ~122k pairs).
 
 One STEP = one pass of the hot path over the synthetic data set:
-    Radon intermediates of all projections (sharded by projection) -> all-gather -> set matrices ->
-    all-pairs ECC (pairs partitioned by equal work) -> reduce -> mean on the host.
+    Radon intermediates of all projections (sharded by projection; on several GPUs every kernel stores its bins into
+    all ranks' buffers over NVLink) -> set matrices -> all-pairs ECC (pairs partitioned by equal work, values published
+    to all ranks) -> fixed-order sum -> mean on the host.
 `value`   whole-job pairs/s with the projection images already resident in HBM.
 `e2e`     the same through the public C ABI with HOST (pinned) image buffers: H2D of the images and D2H of the
           n x n cost image + mean are inside the timed region.
@@ -120,7 +121,7 @@ def run_b200(args):
     images_host.copy_(images)
     cost_dev = torch.zeros((n, n), dtype=torch.float32, device=dev)
     cost_host = torch.zeros((n, n), dtype=torch.float32, pin_memory=True)
-    pipe = ShardedPipeline(ctx, rank, world, device=dev)
+    pipe = ShardedPipeline(ctx, rank, world, device=dev, transport=args.exchange)
     ctx.set_interpolation(api.INTERP_TEXTURE)
     ctx.set_object_radius(0.0)
     ctx.set_epipolar_plane_step(float(np.deg2rad(W["dkappa_deg"])))
@@ -207,6 +208,11 @@ def run_b200(args):
                                          "texture": "texture unit (reference CUDA numerics, bit-identical Radon bins)",
                                          "exact": "Radon with exact fp32 weights; metric through the texture unit"}[args.radon],
                        "sharding": f"projections block-sharded over {world} GPU(s), pairs partitioned by equal kappa samples",
+                       "exchange": ("none (1 GPU)" if world == 1 else
+                                    "peer stores: the Radon kernels write every bin into all ranks' buffers over NVLink, pair values published "
+                                    "the same way, flag barriers in peer memory; no collective on the data path" if pipe._team_key is not None else
+                                    "NCCL all-gather of the dtr blocks + all-reduce of cost image and sum"
+                                    + (f" (team transport unavailable: {pipe.team_error})" if pipe.team_error else "")),
                        "l2": "inputs larger than L2 (%.2f GB images + %.2f GB dtrs per step)" % (n * n_u * n_v * 4 / 1e9, n * n_a * n_t * 4 / 1e9)},
             "stages": {"radon_intermediates_per_s": world * (hi - lo) / ((radon_ms / args.steps) * 1e-3) if radon_ms > 0 else None,
                        "radon_kernel_ms_per_step_rank0": radon_ms / args.steps,
@@ -341,6 +347,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--exchange", default="team", choices=["team", "nccl"],
+                    help="multi-GPU transport: team (peer stores from inside the kernels + flag barriers, default) or nccl (collectives after the kernels)")
     ap.add_argument("--radon", default="hybrid", choices=["hybrid", "texture", "exact"],
                     help="Radon engine: hybrid (texture unit + shared-memory path, default), texture (bit-identical to the reference kernel), exact")
     args = ap.parse_args()

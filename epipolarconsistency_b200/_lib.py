@@ -44,6 +44,14 @@ SIGNATURES = {
     "ecc_evaluate_batch": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
     "ecc_pair_sample_counts": (C.c_int, [c_ctx, c_vp]),
     "ecc_partition_pairs": (C.c_int, [c_ctx, C.c_int, c_vp]),
+    "ecc_team_create": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
+    "ecc_team_connect": (C.c_int, [c_ctx, c_vp]),
+    "ecc_team_connect_pointers": (C.c_int, [c_ctx, c_vp]),
+    "ecc_team_block": (C.c_int, [c_ctx, C.POINTER(c_vp), C.POINTER(c_vp)]),
+    "ecc_team_destroy": (C.c_int, [c_ctx]),
+    "ecc_team_radon_compute": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ecc_team_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),
+    "ecc_team_barrier": (C.c_int, [c_ctx]),
     "ecc_make_circular_trajectory": (None, [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, c_vp]),
     "ecc_camera_intrinsics": (None, [c_vp, c_vp, c_vp, c_vp]),
     "ecc_preprocess_defaults": (None, [c_vp]),

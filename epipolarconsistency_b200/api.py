@@ -225,6 +225,68 @@ class Context:
         self._check(self.lib.ecc_partition_pairs(self.h, int(n_parts), _ptr(bounds)))
         return bounds
 
+    # -- multi-GPU team (include/ecc_b200.h "Multi-GPU team"): peer-mapped blocks, no collective on the data path
+    TEAM_HANDLE_BYTES = 64
+
+    def team_create(self, rank, world, n_total, n_alpha, n_t):
+        """Allocates this rank's block; returns its handle (bytes) for the other processes."""
+        handle = np.zeros(self.TEAM_HANDLE_BYTES, np.uint8)
+        self._check(self.lib.ecc_team_create(self.h, int(rank), int(world), int(n_total), int(n_alpha), int(n_t), _ptr(handle)))
+        self._team_shape = (int(n_total), int(n_t), int(n_alpha))
+        return handle.tobytes()
+
+    def team_connect(self, handles):
+        """handles: the world handles in rank order (bytes each)."""
+        blob = np.frombuffer(b"".join(handles), np.uint8).copy()
+        self._check(self.lib.ecc_team_connect(self.h, _ptr(blob)))
+
+    def team_connect_pointers(self, blocks):
+        """blocks: the ranks' block addresses (team_block()[0]) when all ranks live in this process."""
+        arr = (C.c_void_p * len(blocks))(*[int(b) for b in blocks])
+        self._check(self.lib.ecc_team_connect_pointers(self.h, C.addressof(arr)))
+
+    def team_block(self):
+        """(address of the own block, address of the dtrs inside it)."""
+        b, d = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.ecc_team_block(self.h, C.byref(b), C.byref(d)))
+        return b.value, d.value
+
+    def team_dtrs(self):
+        """The block's Radon intermediates as a torch tensor view (n_total, n_t, n_alpha); memory owned by the context."""
+        import torch
+        _, d = self.team_block()
+        n, n_t, n_a = self._team_shape
+
+        class _Mem:  # __cuda_array_interface__ carrier
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (n, n_t, n_a), "typestr": "<f4", "data": (d, False), "version": 2}
+        m._owner = self
+        return torch.as_tensor(m, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def team_destroy(self):
+        self._check(self.lib.ecc_team_destroy(self.h))
+
+    def team_radon_compute(self, images, first, n_u, n_v, filter=FILTER_DERIVATIVE, post=POST_IDENTITY, interp=INTERP_TEXTURE):
+        n_local = 0 if images is None else images.shape[0]
+        self._check(self.lib.ecc_team_radon_compute(self.h, _ptr(images) if n_local else None, int(first), n_local, n_u, n_v,
+                                                    filter, post, interp))
+
+    def team_set_radon_intermediates(self, n_u, n_v, is_derivative=True):
+        """setRadonIntermediates with the team block's dtrs (borrowed, zero copy)."""
+        _, d = self.team_block()
+        n, n_t, n_alpha = self._team_shape
+        sa, st = self.radon_bin_sizes(n_u, n_v, n_alpha, n_t)
+        self._check(self.lib.ecc_set_radon_intermediates(self.h, d, n, n_alpha, n_t, sa, st, n_u, n_v, int(is_derivative)))
+
+    def team_evaluate(self, cost_image=None, want_mean=True):
+        m = C.c_double()
+        self._check(self.lib.ecc_team_evaluate(self.h, _ptr(cost_image), C.byref(m) if want_mean else None))
+        return m.value if want_mean else None
+
+    def team_barrier(self):
+        self._check(self.lib.ecc_team_barrier(self.h))
+
     # -- synthetic data
     def synth_projections(self, Ps, n_u, n_v, ellipsoids, images, cos_weight=True, zero_border=True):
         Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)

@@ -233,6 +233,7 @@ void ecc_destroy(ecc_context* ctx)
     free_image_pool(ctx);
     free_hybrid(ctx);
     free_hybrid4(ctx);
+    team_free(ctx);
     if (ctx->ramp_g_d) cudaFree(ctx->ramp_g_d);
     if (ctx->pre_work_d) cudaFree(ctx->pre_work_d);
     if (ctx->pre_small_d) cudaFree(ctx->pre_small_d);
@@ -285,6 +286,16 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
 {
     if (!ctx) return ECC_ERR_INVALID;
     Guard g(ctx);
+    return eccb200::radon_compute_impl(ctx, images, n_images, n_u, n_v, n_alpha, n_t, filter, post, interp, dtrs_out, true);
+}
+
+}  // extern "C"
+
+int eccb200::fill_pair_launch(ecc_context* ctx, PairLaunch& L) { return fill_launch(ctx, L); }
+
+int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_images, int n_u, int n_v, int n_alpha, int n_t,
+                                int filter, int post, int interp, float* dtrs_out, bool final_sync)
+{
     if (!images || !dtrs_out || n_images < 0 || n_u < 2 || n_v < 2 || n_alpha < 1 || n_t < 1)
         return fail(ctx, ECC_ERR_INVALID, "ecc_radon_compute: bad argument");
     if (filter != ECC_FILTER_DERIVATIVE && filter != ECC_FILTER_NONE && filter != ECC_FILTER_RAMP) return fail(ctx, ECC_ERR_INVALID, "bad filter");
@@ -336,9 +347,11 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
             ECC_CUDA(ctx, cudaMemcpyAsync(dtrs_out + (size_t)first * dtr_elems, dst, sizeof(float) * dtr_elems * n, cudaMemcpyDeviceToHost, ctx->stream));
         first += n;
     }
-    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (final_sync) ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ECC_OK;
 }
+
+extern "C" {
 
 void ecc_camera_intrinsics(const double* P, double* focal_px, double* principal_u, double* principal_v)
 {

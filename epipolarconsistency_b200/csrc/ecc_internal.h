@@ -54,6 +54,33 @@ struct Hybrid4Stage {
     alignas(64) unsigned char map_t[128] = {};
 };
 
+// Peer mirrors of an output buffer (multi-GPU team, ecc_team.cu): a kernel that stores out[k] also stores the same
+// element of every other rank's copy, *(float*)((char*)&out[k] + delta[r]) for r < n, over NVLink.
+constexpr int kMaxPeers = 15;
+struct Mirrors {
+    long long delta[kMaxPeers];
+    int n;
+};
+
+// The GPUs of one node that work on one data set (one process and one context per GPU).  Every rank owns ONE device
+// block [flags | pair values | all Radon intermediates] and maps the blocks of all other ranks (CUDA IPC, or plain
+// pointers inside one process); kernels write their results into every block directly.
+struct Team {
+    int rank = 0, world = 0;  // world == 0: no team
+    int n_total = 0, n_alpha = 0, n_t = 0;
+    size_t block_bytes = 0, vals_offset = 0, dtrs_offset = 0;
+    void* block = nullptr;            // own block (cudaMalloc)
+    std::vector<void*> bases;         // [world] block of every rank in this process's address space (own included)
+    std::vector<void*> opened;        // the ones mapped with cudaIpcOpenMemHandle
+    unsigned** flag_tables_d = nullptr;  // [world] device table of the ranks' flag arrays
+    unsigned* status_d = nullptr;     // set by a barrier that timed out
+    unsigned epoch = 0;
+    bool connected = false;
+    bool mirror_radon = false;        // while ecc_team_radon_compute runs: Radon kernels mirror their stores
+    float* dtrs() const { return (float*)((char*)block + dtrs_offset); }
+    float* vals() const { return (float*)((char*)block + vals_offset); }
+};
+
 }  // namespace eccb200
 
 struct ecc_context {
@@ -126,6 +153,7 @@ struct ecc_context {
     int ramp_n_t = 0;
     eccb200::HybridStage hybrid;
     eccb200::Hybrid4Stage hybrid4;
+    eccb200::Team team;
 
     // ---- profiling ----
     bool profiling = false;
@@ -183,6 +211,7 @@ struct PairLaunch {
     float* image_d;  // all-pairs: n_views*n_views cost image or null (only with n_sets==1)
 };
 int launch_pairs(ecc_context* ctx, const PairLaunch& L);
+int fill_pair_launch(ecc_context* ctx, PairLaunch& L);  // everything that depends on the context state only (ecc_capi.cu)
 int launch_pair_counts(ecc_context* ctx, const PairLaunch& L, int* counts_d);
 int launch_sum_sets(ecc_context* ctx, const float* vals_d, long long n_pairs, int n_sets,
                     double* sums_d);
@@ -205,6 +234,16 @@ void free_hybrid(ecc_context* ctx);
 int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d);
 void free_hybrid4(ecc_context* ctx);
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
+
+// ---- multi-GPU team (ecc_team.cu) ----
+// Mirrors for stores into [out, out + bytes) when that range lies in the team's own block and mirroring is on, else n = 0.
+Mirrors team_mirrors(const ecc_context* ctx, const void* out);
+// Copies [ptr, ptr + bytes) of the own block to the same place of every other block (for kernels that do not mirror themselves).
+int team_publish(ecc_context* ctx, const void* ptr, size_t bytes);
+int team_barrier(ecc_context* ctx);
+void team_free(ecc_context* ctx);
+int radon_compute_impl(ecc_context* ctx, const float* images, int n_images, int n_u, int n_v, int n_alpha, int n_t, int filter,
+                       int post, int interp, float* dtrs_out, bool sync_device_path);
 
 // ---- launchers (ecc_preprocess.cu) ----
 int preprocess_batch(ecc_context* ctx, float* images_d, int n, int n_u, int n_v, const ecc_preprocess_params* pp, const double* Ps_h);

@@ -397,6 +397,11 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
             const int rc3 = ramp_filter(ctx, dst, n, n_alpha, n_t);
             if (rc3) return rc3;
         }
+        // multi-GPU team: these engines do not mirror their stores themselves (the hybrid kernels do)
+        if (ctx->team.mirror_radon) {
+            const int rc4 = team_publish(ctx, dst, sizeof(float) * (size_t)n * n_t * n_alpha);
+            if (rc4) return rc4;
+        }
     }
     return ECC_OK;
 }

@@ -138,7 +138,15 @@ struct HybridParams {
     unsigned* claim;         // [items], zeroed before the launch
     unsigned magic;          // 0x4B0000, kept out of the compiler's sight (see sample_window)
     float* out;
+    Mirrors mir;             // multi-GPU team: every bin is also stored into the other ranks' buffers
 };
+
+__device__ __forceinline__ void store_bin(const HybridParams& p, size_t index, float val)
+{
+    float* d = p.out + index;
+    *d = val;
+    for (int r = 0; r < p.mir.n; r++) *(float*)((char*)d + p.mir.delta[r]) = val;
+}
 
 struct ItemBins {
     int img, ix, iy;
@@ -160,7 +168,7 @@ __device__ __forceinline__ ItemBins item_bins(int item, int wi, int lane, const 
 template <int MAXTHREADS, int MINBLOCKS>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
 radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_constant__ CUtensorMap map_t,
-                    const HybridParams p)
+                    const __grid_constant__ HybridParams p)
 {
     extern __shared__ __align__(128) unsigned char window_raw[];
     __shared__ __align__(8) unsigned long long mbar_store[2];
@@ -194,7 +202,7 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
             const BinLine L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
             float r = 0.f;
             if (L.valid) r = post_process(bin_texture(p.texs[B.img], L), p.post);
-            p.out[B.img * img_stride + (size_t)B.iy * p.n_alpha + B.ix] = r;
+            store_bin(p, B.img * img_stride + (size_t)B.iy * p.n_alpha + B.ix, r);
         }
         return;
     }
@@ -350,7 +358,7 @@ radon_hybrid_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_cons
             // the (rare) lines outside the window path: items too long / too tall for the window, and lines that miss
             // the inset box (they may sample outside the image: clamp addressing)
             if (L.valid && (fallback || !safe)) result = bin_texture(p.texs[B.img], L);
-            p.out[B.img * img_stride + (size_t)B.iy * p.n_alpha + B.ix] = L.valid ? post_process(result, p.post) : 0.f;
+            store_bin(p, B.img * img_stride + (size_t)B.iy * p.n_alpha + B.ix, L.valid ? post_process(result, p.post) : 0.f);
         }
         group_sync();  // s_item / tables are rewritten at the top
     }
@@ -458,6 +466,7 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
     P.claim = H.queue + 2;
     P.magic = 0x4B0000u;
     P.out = out_d;
+    P.mir = team_mirrors(ctx, out_d);
     const int threads = (kWindowWarps + nt) * 32;
     const size_t smem = (size_t)kRows * kBoxW * 4 * nbuf;
     const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;

@@ -40,6 +40,7 @@ struct Hybrid4Params {
     unsigned* claim;
     unsigned magic;
     float* out;
+    Mirrors mir;  // multi-GPU team: every bin is also stored into the other ranks' buffers (NVLink peer stores)
 };
 
 struct Sum4 {
@@ -153,12 +154,18 @@ __device__ __forceinline__ void store4(const Hybrid4Params& p, const Item4& B, c
     const float v[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int c = 0; c < 4; c++)
-        if (c < left) dst[c * stride] = valid ? post_process(v[c], p.post) : 0.f;
+        if (c < left) {
+            const float val = valid ? post_process(v[c], p.post) : 0.f;
+            float* d = dst + c * stride;
+            *d = val;
+            for (int r = 0; r < p.mir.n; r++) *(float*)((char*)d + p.mir.delta[r]) = val;
+        }
 }
 
 template <int MAXTHREADS, int MINBLOCKS>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
-radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_constant__ CUtensorMap map_t, const Hybrid4Params p)
+radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_constant__ CUtensorMap map_t,
+                     const __grid_constant__ Hybrid4Params p)
 {
     extern __shared__ __align__(128) unsigned char window_raw[];
     __shared__ __align__(8) unsigned long long mbar_store[1];
@@ -470,6 +477,7 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     P.claim = H.queue + 2;
     P.magic = 0x4B0000u;
     P.out = out_d;
+    P.mir = team_mirrors(ctx, out_d);
     static const int nt = env_int("ECC_HYBRID4_NT", 8);
     static const int ctas = env_int("ECC_HYBRID4_CTAS", 2);
     static const int mode = env_int("ECC_HYBRID_MODE", 0);

@@ -10,6 +10,15 @@ SURVEY.md section 8e: the reference is single-GPU; the path shards naturally wit
            locally, no exchange.
   final    all-reduce(sum) of the n*n cost image (disjoint entries, 984 KB at C3) and of the scalar sum.
 
+Two transports for the exchange and the final reduction:
+  "team"   (default when it can be set up) no collective on the data path: every rank's block of device memory is mapped
+           into all other ranks (CUDA IPC over NVLink/NVSwitch, include/ecc_b200.h "Multi-GPU team"); the Radon kernels
+           store each bin into all blocks, pair values are published the same way, flag barriers in peer memory order
+           the stages.  torch.distributed only carries the 64-byte handles at set-up.  Mean and cost image are the same
+           bits on every rank.
+  "nccl"   all-gather + all-reduce after the kernels (the first version; kept as the comparison and as the transport
+           for ranks without peer access).
+
 The class takes the compute object as a parameter (an `api.Context`); the CPU tests drive the same host logic
 with a stub compute object over the gloo backend.
 """
@@ -26,11 +35,52 @@ def shard_bounds(n, world):
 
 
 class ShardedPipeline:
-    def __init__(self, compute, rank=0, world=1, device=None, group=None):
+    def __init__(self, compute, rank=0, world=1, device=None, group=None, transport="nccl"):
         self.c = compute
         self.rank, self.world, self.group = rank, world, group
         self.device = device
         self._full = None
+        self.transport = transport if world > 1 else "nccl"
+        self._team_key = None
+        self.team_error = None
+
+    # -- team set-up: allocate the own block, exchange the handles, map the peers ---------------------------------
+    def _ensure_team(self, n_total, n_alpha, n_t):
+        """True when the team transport is ready for this data-set shape.  Every rank takes the same decision: a rank
+        that fails reports it in the handle exchange and all ranks fall back to the collectives."""
+        key = (n_total, n_alpha, n_t)
+        if self._team_key == key:
+            return True
+        if self.transport != "team":
+            return False
+        import torch.distributed as dist
+        handle, err = None, None
+        try:
+            handle = self.c.team_create(self.rank, self.world, n_total, n_alpha, n_t)
+        except Exception as e:  # noqa: BLE001 -- reported to every rank below
+            err = f"rank {self.rank}: {e}"
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (handle, err), group=self.group)
+        errors = [g[1] for g in gathered if g[1]]
+        if not errors:
+            try:
+                self.c.team_connect([g[0] for g in gathered])
+            except Exception as e:  # noqa: BLE001
+                err = f"rank {self.rank}: {e}"
+            gathered2 = [None] * self.world
+            dist.all_gather_object(gathered2, err, group=self.group)
+            errors = [g for g in gathered2 if g]
+        if errors:
+            self.team_error = "; ".join(errors)
+            self.transport = "nccl"
+            try:
+                self.c.team_destroy()
+            except Exception:  # noqa: BLE001
+                pass
+            return False
+        self._team_key = key
+        self._full = self.c.team_dtrs()
+        return True
 
     # -- stage 1 + exchange -------------------------------------------------------------------------------
     def radon_allgather(self, local_images, n_total, n_alpha, n_t, **radon_kwargs):
@@ -40,6 +90,10 @@ class ShardedPipeline:
         bounds = shard_bounds(n_total, self.world)
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         assert local_images.shape[0] == hi - lo, (local_images.shape, lo, hi)
+        if self.world > 1 and self._ensure_team(n_total, n_alpha, n_t):
+            n_v, n_u = local_images.shape[1], local_images.shape[2]
+            self.c.team_radon_compute(local_images if hi > lo else None, lo, n_u, n_v, **radon_kwargs)
+            return self._full
         if self._full is None or tuple(self._full.shape) != (n_total, n_t, n_alpha):
             self._full = torch.empty((n_total, n_t, n_alpha), dtype=torch.float32, device=self.device)
         full = self._full
@@ -62,6 +116,8 @@ class ShardedPipeline:
         Returns the mean over all pairs (same value on every rank)."""
         import torch
         total = n_views * (n_views - 1) // 2
+        if self.world > 1 and self._team_key is not None:
+            return self.c.team_evaluate(cost_image)  # complete cost image and the mean, the same bits on every rank
         bounds = self.c.partition_pairs(self.world) if self.world > 1 else np.array([0, total])
         lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
         s = self.c.evaluate_range(lo, hi, cost_image)

@@ -202,6 +202,41 @@ int ecc_pair_sample_counts(ecc_context* ctx, int* counts);
  * bounds: n_parts+1 entries, bounds[0]=0, bounds[n_parts]=n(n-1)/2. */
 int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds);
 
+/* ---- Multi-GPU team: the GPUs of one node on one data set, one process (or thread) and one context per GPU ----------
+ * The reference is single-GPU.  A team shards the path with NO collective on the data path: every
+ * rank owns one device block [flags | pair values | the Radon intermediates of all n_total projections] that is mapped
+ * into all other ranks (CUDA IPC over NVLink/NVSwitch); the Radon kernels store every finished bin into all blocks, the
+ * pair values are published the same way, and flag barriers in peer memory order the stages.  Results (mean, cost
+ * image) are identical on every rank and bit-identical to a single GPU's for the same intermediates.
+ *   rank r:  ecc_team_create(...) -> exchange the handles (any transport: MPI, torch.distributed, a pipe)
+ *            -> ecc_team_connect(all handles) -> per step: ecc_team_radon_compute(own block of projections)
+ *            -> ecc_set_radon_intermediates(dtrs of ecc_team_block) once -> ecc_set_projection_matrices
+ *            -> ecc_team_evaluate.
+ * Every rank must make the same sequence of ecc_team_radon_compute / ecc_team_evaluate / ecc_team_barrier calls. */
+#define ECC_TEAM_HANDLE_BYTES 64
+/* Allocates this rank's block for n_total projections of n_t x n_alpha bins; handle_out (ECC_TEAM_HANDLE_BYTES, nullable
+ * when world == 1) identifies it to the other processes.  world <= 16.  A team of one needs no connect. */
+int ecc_team_create(ecc_context* ctx, int rank, int world, int n_total, int n_alpha, int n_t, unsigned char* handle_out);
+/* handles: world * ECC_TEAM_HANDLE_BYTES bytes in rank order (the own entry is ignored). */
+int ecc_team_connect(ecc_context* ctx, const unsigned char* handles);
+/* The same for ranks that live in ONE process (one context per GPU, or several on one GPU): blocks[r] = rank r's block
+ * (ecc_team_block).  Team calls are then made from one thread per rank, or in any order that keeps every rank's stream
+ * fed: the barriers wait on the device, not on the host. */
+int ecc_team_connect_pointers(ecc_context* ctx, void* const* blocks);
+/* block: start of the own block; dtrs: the n_total * n_t * n_alpha floats inside it (either may be NULL). */
+int ecc_team_block(ecc_context* ctx, void** block, float** dtrs);
+int ecc_team_destroy(ecc_context* ctx);
+/* Radon intermediates of projections [first, first + n_local) of the data set from images [h|d] (n_local * n_v * n_u
+ * floats), stored into every rank's block, followed by a team barrier on the stream: work queued after this call sees
+ * the intermediates of ALL ranks.  Asynchronous for device images. */
+int ecc_team_radon_compute(ecc_context* ctx, const float* images, int first, int n_local, int n_u, int n_v, int filter,
+                           int post_process, int interp);
+/* All pairs, cut into world ranges of equal kappa-sample count (ecc_partition_pairs); this rank scores range [rank].
+ * cost_image [h|d], nullable: as ecc_evaluate, complete on every rank.  mean: over all pairs, the same on every rank. */
+int ecc_team_evaluate(ecc_context* ctx, float* cost_image, double* mean);
+/* A barrier of its own on the stream (e.g. before a rank overwrites data its peers may still read). */
+int ecc_team_barrier(ecc_context* ctx);
+
 /* ---- Host helpers that the reference keeps next to the metric ------------------------------ */
 
 /* ProjTable::makeCircularTrajectory (HeaderOnly/Utils/Projtable.hxx:138-165). Ps: n*12 doubles. */

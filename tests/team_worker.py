@@ -1,0 +1,57 @@
+"""Worker of tests/test_gpu_team.py: one rank of a multi-process team (one process per rank, all on the GPUs the box has;
+with a single GPU the ranks share it and the blocks are still mapped through CUDA IPC).  Writes its results as .npz."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world, port, out_dir, engine = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = port
+    import torch
+    import torch.distributed as dist
+    from epipolarconsistency_b200 import api
+    from epipolarconsistency_b200.distributed import ShardedPipeline, shard_bounds
+    from team_scene import make_scene
+
+    dev_index = rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev_index)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        S = make_scene()
+        n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
+        ctx = api.Context(dev_index)
+        bounds = shard_bounds(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        local = torch.from_numpy(S["imgs"][lo:hi]).cuda()
+        pipe = ShardedPipeline(ctx, rank, world, device=torch.device("cuda", dev_index), transport="team")
+        ctx.set_interpolation(api.INTERP_TEXTURE)
+        ctx.set_epipolar_plane_step(S["dkappa"])
+        interp = {"texture": api.INTERP_TEXTURE, "hybrid": api.INTERP_HYBRID}[engine]
+        means = []
+        for step in range(2):  # twice: the second step overwrites buffers the peers have read
+            src = local if step == 0 else S["imgs"][lo:hi]  # device images, then host images
+            full = pipe.radon_allgather(src, n, n_a, n_t, interp=interp)
+            ctx.set_radon_intermediates(full, n_u, n_v, True)
+            ctx.set_projection_matrices(S["Ps"])
+            cost = torch.zeros((n, n), dtype=torch.float32, device="cuda")
+            means.append(pipe.evaluate_all_pairs(n, cost))
+        assert pipe._team_key is not None, f"team transport not used: {pipe.team_error}"
+        cost_host = np.zeros((n, n), np.float32)
+        mean_host = ctx.team_evaluate(cost_host)
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), dtrs=full.cpu().numpy(), cost=cost.cpu().numpy(), means=np.array(means),
+                 cost_host=cost_host, mean_host=mean_host)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

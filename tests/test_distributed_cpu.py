@@ -37,7 +37,49 @@ class StubCompute:
         return s
 
 
-def _worker(rank, world, port, n_total, results):
+class StubTeam(StubCompute):
+    """The team entry points of api.Context without a GPU: the "peer stores" are emulated with a gloo all-gather inside
+    the stub, so that what is tested is the pipeline's set-up logic (handle exchange in rank order, the common decision,
+    the fall-back) and its routing of the two stages."""
+
+    def __init__(self, n_views, world, rank, fail_create=False):
+        super().__init__(n_views, world)
+        self.rank, self.fail_create = rank, fail_create
+        self.connected_with = None
+        self.destroyed = False
+
+    def team_create(self, rank, world, n_total, n_alpha, n_t):
+        if self.fail_create:
+            raise RuntimeError("no peer access")
+        self._full = torch.zeros((n_total, n_t, n_alpha))
+        return f"handle-of-rank-{rank}".encode()
+
+    def team_connect(self, handles):
+        self.connected_with = list(handles)
+
+    def team_destroy(self):
+        self.destroyed = True
+
+    def team_dtrs(self):
+        return self._full
+
+    def team_radon_compute(self, images, first, n_u, n_v, **kw):
+        n_total, n_t, n_alpha = self._full.shape
+        bounds = shard_bounds(n_total, self.world)
+        mine = torch.zeros((max(b - a for a, b in zip(bounds, bounds[1:])), n_t, n_alpha))
+        if images is not None:
+            mine[:images.shape[0]] = images.mean(dim=(1, 2))[:, None, None]
+        parts = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine)
+        for r in range(self.world):
+            self._full[bounds[r]:bounds[r + 1]] = parts[r][:bounds[r + 1] - bounds[r]]
+
+    def team_evaluate(self, cost_image=None, want_mean=True):
+        total = self.n * (self.n - 1) // 2
+        return self.evaluate_range(0, total, cost_image) / total
+
+
+def _worker(rank, world, port, n_total, results, mode="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,11 +87,18 @@ def _worker(rank, world, port, n_total, results):
         bounds = shard_bounds(n_total, world)
         lo, hi = bounds[rank], bounds[rank + 1]
         local = torch.stack([torch.full((6, 8), float(k)) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 6, 8))
-        pipe = ShardedPipeline(StubCompute(n_total, world), rank, world, device="cpu")
+        if mode == "nccl":
+            compute, transport = StubCompute(n_total, world), "nccl"
+        else:
+            compute, transport = StubTeam(n_total, world, rank, fail_create=(mode == "team-fails" and rank == 1)), "team"
+        pipe = ShardedPipeline(compute, rank, world, device="cpu", transport=transport)
         full = pipe.radon_allgather(local, n_total, 5, 4)
         cost = torch.zeros((n_total, n_total))
         mean = pipe.evaluate_all_pairs(n_total, cost)
-        results[rank] = (full[:, 0, 0].tolist(), mean, cost.numpy().copy())
+        extra = None
+        if mode != "nccl":
+            extra = (pipe.transport, pipe.team_error, compute.connected_with, compute.destroyed)
+        results[rank] = (full[:, 0, 0].tolist(), mean, cost.numpy().copy(), extra)
     finally:
         dist.destroy_process_group()
 
@@ -60,10 +109,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(n_total, world=2):
+def _run(n_total, world=2, mode="nccl"):
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), n_total, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_total, results, mode), nprocs=world, join=True)
     return dict(results)
 
 
@@ -73,12 +122,18 @@ def test_shard_bounds():
     assert shard_bounds(1, 4) == [0, 1, 1, 1, 1]
 
 
-def _check(n_total):
-    res = _run(n_total)
+def _check(n_total, mode="nccl"):
+    res = _run(n_total, mode=mode)
     pairs = [(i, j) for i in range(n_total) for j in range(i + 1, n_total)]
     want_mean = np.mean([1000.0 * i + j for i, j in pairs])
     for rank in (0, 1):
-        dtr_vals, mean, cost = res[rank]
+        dtr_vals, mean, cost, extra = res[rank]
+        if mode == "team":  # both ranks connected with the handles in rank order
+            assert extra[0] == "team" and extra[1] is None
+            assert extra[2] == [b"handle-of-rank-0", b"handle-of-rank-1"]
+        if mode == "team-fails":  # one rank could not create its block: BOTH fall back to the collectives and say why
+            assert extra[0] == "nccl" and "rank 1: no peer access" in extra[1]
+            assert extra[2] is None and extra[3]
         assert dtr_vals == [float(k) for k in range(n_total)]  # every rank ends with all dtrs, in order
         assert abs(mean - want_mean) < 1e-9
         for i, j in pairs:
@@ -91,3 +146,11 @@ def test_world2_even_shards():
 
 def test_world2_ragged_shards():
     _check(5)
+
+
+def test_world2_team_transport():
+    _check(5, mode="team")
+
+
+def test_world2_team_falls_back_together():
+    _check(6, mode="team-fails")

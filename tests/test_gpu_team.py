@@ -1,0 +1,133 @@
+"""Multi-GPU team (include/ecc_b200.h "Multi-GPU team", csrc/ecc_team.cu) on the GPU box: every rank's results must be the
+single-GPU results BIT FOR BIT (texture engine: deterministic), whichever way the blocks are mapped --
+  * ranks as threads of one process, blocks connected by pointer (ecc_team_connect_pointers),
+  * ranks as processes, blocks connected through CUDA IPC handles carried by torch.distributed (gloo) -- the bench's way.
+With one GPU in the box the ranks share it; the code path (peer stores, flag barriers, publish, fixed-order sum) is the same."""
+import os
+import socket
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from epipolarconsistency_b200 import api
+from team_scene import make_scene
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def single_gpu(S, interp):
+    c = api.Context()
+    try:
+        dtrs = c.radon_compute(S["imgs"], S["n_a"], S["n_t"], interp=interp)
+        c.set_interpolation(api.INTERP_TEXTURE)
+        c.set_epipolar_plane_step(S["dkappa"])
+        c.set_radon_intermediates(dtrs, S["n_u"], S["n_v"], True)
+        c.set_projection_matrices(S["Ps"])
+        cost = np.zeros((S["n"], S["n"]), np.float32)
+        mean = c.evaluate(cost)
+        return dtrs, cost, mean
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_team_threads_bit_identical_to_single_gpu(world):
+    import torch
+    from epipolarconsistency_b200.distributed import shard_bounds
+    S = make_scene()
+    n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
+    want_dtrs, want_cost, want_mean = single_gpu(S, api.INTERP_TEXTURE)
+    n_dev = torch.cuda.device_count()
+    ctxs = [api.Context(r % n_dev, stream=None) for r in range(world)]  # own streams: the ranks run concurrently
+    try:
+        for r, c in enumerate(ctxs):
+            c.team_create(r, world, n, n_a, n_t)
+        blocks = [c.team_block()[0] for c in ctxs]
+        for c in ctxs:
+            c.team_connect_pointers(blocks)
+        bounds = shard_bounds(n, world)
+        out = [None] * world
+        errors = []
+
+        def run(r):
+            try:
+                c = ctxs[r]
+                torch.cuda.set_device(r % n_dev)
+                c.set_interpolation(api.INTERP_TEXTURE)
+                c.set_epipolar_plane_step(S["dkappa"])
+                for step in range(2):
+                    lo, hi = bounds[r], bounds[r + 1]
+                    c.team_radon_compute(S["imgs"][lo:hi] if hi > lo else None, lo, n_u, n_v, interp=api.INTERP_TEXTURE)
+                    c.team_set_radon_intermediates(n_u, n_v, True)
+                    c.set_projection_matrices(S["Ps"])
+                    cost = np.zeros((n, n), np.float32)
+                    mean = c.team_evaluate(cost)
+                c.synchronize()
+                dtrs = c.team_dtrs().cpu().numpy()
+                out[r] = (dtrs, cost, mean)
+            except Exception as e:  # noqa: BLE001
+                errors.append((r, repr(e)))
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=180)
+        assert not errors, errors
+        for r in range(world):
+            dtrs, cost, mean = out[r]
+            assert np.array_equal(dtrs, want_dtrs), f"rank {r}: dtrs differ"
+            assert np.array_equal(cost, want_cost), f"rank {r}: cost image differs"
+            assert mean == want_mean, f"rank {r}: mean {mean} vs {want_mean}"
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("engine", ["texture", "hybrid"])
+def test_team_processes_over_cuda_ipc(tmp_path, engine):
+    world = 2
+    S = make_scene()
+    port = str(_free_port())
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "team_worker.py"), str(r), str(world), port, str(tmp_path), engine],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    logs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+            out += "\n[timeout]"
+        logs.append(out)
+    assert all(p.returncode == 0 for p in procs), "\n----\n".join(logs)
+    interp = api.INTERP_TEXTURE if engine == "texture" else api.INTERP_HYBRID
+    want_dtrs, want_cost, want_mean = single_gpu(S, interp)
+    res = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    for r in range(world):
+        if engine == "texture":  # deterministic engine: bit for bit
+            assert np.array_equal(res[r]["dtrs"], want_dtrs)
+            assert np.array_equal(res[r]["cost"], want_cost)
+            assert res[r]["means"][1] == want_mean
+        else:  # which bins take which pipe depends on scheduling: the engine's own tolerance
+            peak = np.abs(want_dtrs).max()
+            assert np.abs(res[r]["dtrs"] - want_dtrs).max() < 1e-4 * peak
+            assert abs(res[r]["means"][1] - want_mean) < 1e-3 * abs(want_mean)
+        assert res[r]["means"][0] == pytest.approx(res[r]["means"][1], rel=1e-3)
+        # host and device cost images of the same step are the same values
+        assert np.array_equal(res[r]["cost_host"], res[r]["cost"])
+        assert res[r]["mean_host"] == res[r]["means"][1]
+    # every rank holds the same bits
+    assert np.array_equal(res[0]["dtrs"], res[1]["dtrs"])
+    assert np.array_equal(res[0]["cost"], res[1]["cost"])
+    assert res[0]["means"][1] == res[1]["means"][1]
