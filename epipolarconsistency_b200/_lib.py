@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libecc_b200.so")
+# ECC_B200_LIB: development override (a build of the same sources with other compile-time knobs)
+LIB_PATH = os.environ.get("ECC_B200_LIB") or os.path.join(PKG_DIR, "lib", "libecc_b200.so")
 
 c_ctx = C.c_void_p
 c_vp = C.c_void_p

@@ -329,7 +329,10 @@ void free_image_pool(ecc_context* ctx)
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
                 int n_alpha, int n_t, int filter, int post, int interp, float* out_d)
 {
-    constexpr int kPool = 64;  // projections per launch
+    constexpr int kPool = 64;  // projections per launch (texture engines: one CUDA array per projection)
+    // the quad kernel is persistent: every launch ends with a tail (CTAs run dry one by one) and starts with its image
+    // staging, so fewer, larger launches (2.4 GB of staging at the C3 image size)
+    constexpr int kPoolQuad = 128;
     const int pool = n_images < kPool ? n_images : kPool;
     const bool deriv = (filter == ECC_FILTER_DERIVATIVE);  // ramp: plain line integrals first (RadonIntermediate.cu:160-168)
     // development knob: ECC_HYBRID_QUADS=0 keeps the one-image-per-item hybrid kernel for everything
@@ -339,8 +342,8 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
         // remainder of three is padded to a quad, one or two left-over images take the one-image hybrid kernel below
         const int rem = n_images % 4;
         const int n_quad_images = (rem == 3) ? n_images : n_images - rem;
-        for (int first = 0; first < n_quad_images; first += pool) {
-            const int n = (n_quad_images - first < pool) ? n_quad_images - first : pool;
+        for (int first = 0; first < n_quad_images; first += kPoolQuad) {
+            const int n = (n_quad_images - first < kPoolQuad) ? n_quad_images - first : kPoolQuad;
             const int rc4 = radon_hybrid4_launch(ctx, images_d + (size_t)first * n_u * n_v, n, n_u, n_v, n_alpha, n_t, post,
                                                  out_d + (size_t)first * n_t * n_alpha);
             if (rc4) return rc4;

@@ -106,7 +106,11 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
     const unsigned Pi = __float_as_uint(__fadd_rd(Ps, 8388608.f));
     const unsigned Si = __float_as_uint(__fadd_rd(Ss, 8388608.f));
     const unsigned a = Pi & 255u, b = Si & 255u;
+#ifdef ECC_CONFLICT_PROBE  // development: rows forced onto distinct bank groups per 8 lanes (WRONG results; speed bound)
+    const unsigned addr = base + (((Pi >> 8) * kRows4 + (((Si >> 8) & ~7u) | ((threadIdx.x - (Pi >> 8)) & 7u))) << 4);
+#else
     const unsigned addr = base + (((Pi >> 8) * kRows4 + (Si >> 8)) << 4);
+#endif
     float4 v00, v01, v10, v11;
     asm volatile(
         "ld.shared.v4.f32 {%0, %1, %2, %3}, [%16];\n"
@@ -485,7 +489,11 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     static const int lane_map = env_int("ECC_HYBRID4_LANEMAP", 2);
     P.lane_map = lane_map;
     const int threads = (kWindowWarps + nt) * 32;
+#ifdef ECC_CONFLICT_PROBE
+    const size_t smem = (size_t)kRows4 * kBoxW4 * 16 + 1024;
+#else
     const size_t smem = (size_t)kRows4 * kBoxW4 * 16;
+#endif
     const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;
     const CUtensorMap& mt = *(const CUtensorMap*)H.map_t;
     const int slot = prof_begin(ctx, FAM_RADON);

@@ -5,6 +5,7 @@
 #define ECC_FACADE_THROW
 #include <EpipolarConsistency/EpipolarConsistencyRadonIntermediate.h>
 #include <EpipolarConsistency/Adaptors.h>
+#include <EpipolarConsistency/Projtable.h>
 
 #include <cmath>
 #include <cstdio>
@@ -68,6 +69,24 @@ static int run_cpu(const char* tmpdir)
     for (int i = 0; i < one.length(); i++) ((float*)one)[i] = 0.25f * i - 3.f;
     one.meta_info["Filter"] = "Derivative";
     if (!one.save(std::string(tmpdir) + "/facade_same.nrrd")) return fail("save same");
+    // .ompl: one matrix per line, meta line, comment (Projtable.hxx:168-220)
+    {
+        std::vector<Geometry::ProjectionMatrix> Ps = ProjTable::makeCircularTrajectory(3, 750.0, 1200.0, 160, 128, 200.0, 2.0);
+        Ps[1](0, 3) = 1.0 / 3.0;
+        Ps[2](2, 0) = -1234567.890123456;
+        const std::string ompl = std::string(tmpdir) + "/facade.ompl";
+        if (!ProjTable::saveProjectionsOneMatrixPerLine(Ps, ompl, " three views", 0.308, 1240, 960)) return fail("ompl save");
+        std::map<std::string, std::string> meta;
+        std::vector<Geometry::ProjectionMatrix> back_ps = ProjTable::loadProjectionsOneMatrixPerLine(ompl, &meta);
+        if (back_ps.size() != 3) return fail("ompl count");
+        if (meta["comment"] != " three views" || meta["spacing"] != "0.308" || meta["detector_size_px"] != "1240 960") return fail("ompl meta");
+        for (int i = 0; i < 3; i++)
+            for (int k = 0; k < 12; k++) {
+                const double a = Ps[i].data()[k], b = back_ps[i].data()[k];
+                if (std::fabs(a - b) > 1e-11 * std::fabs(a)) return fail("ompl values (12 significant digits)");
+            }
+        if (ProjTable::stringToProjectionMatrix("1 2 3")(1, 1) != 1.0) return fail("ompl malformed line -> [I|0]");
+    }
     std::printf("OK cpu\n");
     return 0;
 }

@@ -24,6 +24,23 @@ def test_facade_builds_and_cpu_checks(tmp_path):
     assert r.returncode == 0 and "OK cpu" in r.stdout, r.stdout + r.stderr
 
 
+def test_ompl_layout(tmp_path):
+    """One-matrix-per-line projection files (Projtable.hxx:168-220, EigenToStr.hxx:135-142): the facade's writer against an
+    independent restatement of the format -- '[a b c d; e f g h; i j k l] ' with 12 significant digits -- and its reader."""
+    build()
+    subprocess.run([EXE, "cpu", str(tmp_path)], check=True, stdout=subprocess.DEVNULL)
+    lines = open(tmp_path / "facade.ompl").read().split("\n")
+    assert lines[0] == "# three views"
+    assert lines[1] == '#> spacing="0.308" detector_size_px="1240 960"'
+    Ps = ol.circular_trajectory(3, 750, 1200, 160, 128, 200, 2.0).reshape(3, 4, 3).transpose(0, 2, 1).copy()  # (n, row, col)
+    Ps[1][0, 3] = 1.0 / 3.0
+    Ps[2][2, 0] = -1234567.890123456
+    for k in range(3):
+        want = "[" + "; ".join(" ".join("%.12g" % v for v in row) for row in Ps[k]) + "] "
+        assert lines[2 + k] == want
+    assert lines[5] == ""
+
+
 def test_nrrd_layout_against_reference_reader_and_writer(tmp_path):
     R = ol.ref_nrrd()
     if R is None:
