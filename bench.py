@@ -233,12 +233,22 @@ def run_b200(args):
                                      if (args.radon == "hybrid" and args.workload == "c3") else None),
                          "samples_per_s": radon_gbs * 1e9 / 16.0,
                          "tex_rate_frac": (radon_gbs * 1e9 / 16.0) / 1.09e12,
+                         # the bound that applies: the SM's two on-chip data pipes together, 64 B/clk (texture) + 128 B/clk
+                         # (shared memory) per SM = 192 B x 148 SMs x the SM clock sampled during this run
+                         "onchip_peak_gbs": 192.0 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                         "onchip_frac": radon_gbs / (192.0 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9),
                          "note": "16 B per bilinear sample x %.4g samples per projection, on-chip traffic (hence frac > 1 against the "
                                  "HBM copy peak; DRAM moves 10.6 MB per projection); tex_rate_frac = samples/s over the measured tex2D rate of "
                                  "this GPU (1.09e12/s at 1965 MHz, profiles/tex_probe_r01.txt); ncu of a launch of this command: texture "
                                  "data pipe 97 %% of peak, shared-memory pipe 81 %%, issue slots 54 %% (profiles/ncu_radon_hybrid4_bench_r01.txt)" % samples_per_proj},
             "roofline_pairs": {"bound": "hbm", "kernel": "pairs_kernel (L1/texture gather bound)", "achieved": pairs_gbs, "peak": peak,
-                               "unit": "GB/s", "frac": pairs_gbs / peak, "kappa_samples": float(counts.sum())},
+                               "unit": "GB/s", "frac": pairs_gbs / peak, "kappa_samples": float(counts.sum()),
+                               # random-gather rates of this pool's B200 (tools/gather_probe.cu, profiles/gather_probe_r01.txt):
+                               # 32-byte sectors from an L2-resident set / from a 1.17 GB set, bilinear texture fetches from 1.1 GB
+                               "gather_peaks_gbs": {"l2_random_sectors": 4380.0, "hbm_random_sectors": 1021.0, "texture_random_1GB": 427.0},
+                               "frac_of_l2_gather": pairs_gbs / 4380.0,
+                               "note": "64 B of taps per kappa sample; above the random-gather rates because neighbouring kappa samples "
+                                       "share taps in L1TEX (the kernel is issue bound, profiles/ncu_pairs_r01.txt)"},
         }
         if args.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(W, Ps, full_dtrs=pipe._full)

@@ -3,7 +3,9 @@
 //   (1) random 32-byte sectors through the global-load path, working sets from L2-resident (8..96 MB) to the C3 footprint
 //       of all Radon intermediates (1.17 GB, HBM),
 //   (2) random bilinear fetches through the texture path over pitch-2D textures of 768 x 768 floats (the pair kernel's
-//       own lookup, without its locality): 16 B of taps per fetch.
+//       own lookup, without its locality; one texture per warp and fetch): 16 B of taps per fetch.  A first version drew
+//       the texture per LANE: 3.8e9 fetches/s with 496 textures against 1.3e11 with 8 -- a fetch is issued once per
+//       distinct handle in the warp, which is why the pair kernel keeps a pair (two handles) per warp.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/gather_probe tools/gather_probe.cu
 #include <cuda_runtime.h>
 
@@ -52,12 +54,15 @@ __global__ void __launch_bounds__(256) texture_gather(const cudaTextureObject_t*
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     float acc = 0.f;
     unsigned state = mix(tid * 2654435761u + 777u);
+    unsigned wstate = mix((tid >> 5) * 40503u + 99u);  // per warp: the texture of a fetch is uniform over the warp, as in the
+                                                       // pair kernel (a warp works on one pair = two intermediates)
     for (int i = 0; i < iters; i++) {
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             state = mix(state + 0x9e3779b9u);
-            const unsigned t = (unsigned)(((unsigned long long)(state & 0xffffu) * n_tex) >> 16);
+            wstate = mix(wstate + 0x9e3779b9u);
+            const unsigned t = (unsigned)(((unsigned long long)(wstate & 0xffffu) * n_tex) >> 16);
             const unsigned s2 = mix(state);
             const float x = (s2 & 0xffffu) * (1.f / 65536.f), y = (s2 >> 16) * (1.f / 65536.f);
             v[k] = tex2D<float>(texs[t], x, y);
