@@ -308,7 +308,10 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
     // Host memory on either side: stream the batch through device staging in chunks.  Host images go through two
     // staging buffers on a copy stream of their own, so that the upload of chunk i+1 runs under the kernels of chunk i
     // (the first chunk is small: its upload is the only one that is exposed).
-    const int chunk = n_images < 32 ? n_images : 32;
+    // Chunk schedule for host images: 8, 16, 32, 64, 64, ... -- the first upload is the only exposed one, every later
+    // upload (twice the images of the chunk computing above it) hides as long as the link delivers 16 GB/s, and the
+    // persistent kernel gets few, large launches.
+    const int chunk = n_images < 64 ? n_images : 64;
     const int first_chunk = (!in_dev && n_images > 8) ? 8 : chunk;
     int rc;
     if (!in_dev && (rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * img_elems * chunk * 2))) return rc;
@@ -325,10 +328,11 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
         ECC_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
         ECC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
     }
-    int k = 0;
+    int k = 0, want = first_chunk;
     for (int first = 0; first < n_images; k++) {
-        const int want = (k == 0) ? first_chunk : chunk;
-        const int n = (n_images - first < want) ? n_images - first : want;
+        int n = (n_images - first < want) ? n_images - first : want;
+        if (n_images - first - n > 0 && n_images - first - n < 8 && n_images - first <= chunk) n = n_images - first;  // no tiny last launch
+        want = (2 * want < chunk) ? 2 * want : chunk;
         const float* src = images + (size_t)first * img_elems;
         const int b = k & 1;
         if (!in_dev) {

@@ -129,3 +129,24 @@ class ShardedPipeline:
                 dist.all_reduce(cost_image, group=self.group)
             s = float(acc.item())
         return s / total if total else 0.0
+
+    # -- batched mode (BASELINE config C4): K matrix sets against the same dtrs ----------------------------------------
+    def evaluate_batch(self, Ps_sets, idx4=None):
+        """Scores K complete projection-matrix sets (K, n, 12) against the dtrs every rank already holds: the sets are
+        block-sharded over the ranks (a set is the unit of work of the optimiser loops, SURVEY.md section 8e "Batched
+        mode"), each rank runs one batched launch on its sets, and the K means are exchanged (8 bytes per set -- the
+        only traffic).  Returns all K means on every rank."""
+        K = Ps_sets.shape[0]
+        bounds = shard_bounds(K, self.world)
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        mine = self.c.evaluate_batch(Ps_sets[lo:hi], idx4=idx4) if hi > lo else np.zeros(0, np.float64)
+        if self.world == 1:
+            return np.asarray(mine, np.float64)
+        import torch
+        import torch.distributed as dist
+        width = max(b - a for a, b in zip(bounds, bounds[1:]))
+        buf = torch.zeros(width, dtype=torch.float64, device=self.device)
+        buf[:hi - lo] = torch.as_tensor(np.asarray(mine, np.float64), device=self.device)
+        parts = [torch.zeros_like(buf) for _ in range(self.world)]
+        dist.all_gather(parts, buf, group=self.group)
+        return np.concatenate([parts[r][:bounds[r + 1] - bounds[r]].cpu().numpy() for r in range(self.world)])

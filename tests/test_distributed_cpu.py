@@ -26,6 +26,9 @@ class StubCompute:
         total = self.n * (self.n - 1) // 2
         return np.array(shard_bounds(total, n_parts), np.int64)[::1]
 
+    def evaluate_batch(self, Ps_sets, idx4=None):
+        return np.array([float(P[0, 0]) * 2.0 + 1.0 for P in Ps_sets], np.float64)  # a set's "mean" = a function of the set
+
     def evaluate_range(self, lo, hi, cost_image=None, want_sum=True):
         pairs = [(i, j) for i in range(self.n) for j in range(i + 1, self.n)][lo:hi]
         s = 0.0
@@ -87,7 +90,7 @@ def _worker(rank, world, port, n_total, results, mode="nccl"):
         bounds = shard_bounds(n_total, world)
         lo, hi = bounds[rank], bounds[rank + 1]
         local = torch.stack([torch.full((6, 8), float(k)) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 6, 8))
-        if mode == "nccl":
+        if mode in ("nccl", "batch"):
             compute, transport = StubCompute(n_total, world), "nccl"
         else:
             compute, transport = StubTeam(n_total, world, rank, fail_create=(mode == "team-fails" and rank == 1)), "team"
@@ -96,7 +99,10 @@ def _worker(rank, world, port, n_total, results, mode="nccl"):
         cost = torch.zeros((n_total, n_total))
         mean = pipe.evaluate_all_pairs(n_total, cost)
         extra = None
-        if mode != "nccl":
+        if mode == "batch":
+            sets = np.arange(7 * n_total * 12, dtype=np.float64).reshape(7, n_total, 12)  # K = 7 sets: ragged over 2 ranks
+            extra = pipe.evaluate_batch(sets).tolist()
+        elif mode != "nccl":
             extra = (pipe.transport, pipe.team_error, compute.connected_with, compute.destroyed)
         results[rank] = (full[:, 0, 0].tolist(), mean, cost.numpy().copy(), extra)
     finally:
@@ -154,3 +160,11 @@ def test_world2_team_transport():
 
 def test_world2_team_falls_back_together():
     _check(6, mode="team-fails")
+
+
+def test_world2_batched_sets_are_sharded_and_gathered():
+    n_total = 4
+    res = _run(n_total, mode="batch")
+    want = [float(k * n_total * 12) * 2.0 + 1.0 for k in range(7)]
+    for rank in (0, 1):
+        assert res[rank][3] == want  # every rank ends with all K means, in set order
