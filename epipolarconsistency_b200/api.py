@@ -215,6 +215,22 @@ class Context:
                                                 _ptr(means)))
         return means
 
+    def pair_signals(self, i, j, dtr_i=None, dtr_j=None):
+        """evaluateForImagePair (EpipolarConsistencyRadonIntermediate.cpp:324-393): the redundant signals of one pair in
+        ascending kappa.  Returns dict(kappas, signal0, signal1, lines0, lines1, weight, value)."""
+        dtr_i = i if dtr_i is None else dtr_i
+        dtr_j = j if dtr_j is None else dtr_j
+        n, w, v = C.c_int(), C.c_double(), C.c_double()
+        self._check(self.lib.ecc_pair_signals(self.h, i, j, dtr_i, dtr_j, 0, None, None, None, None, None, C.byref(n), None, None))
+        m = n.value
+        out = dict(kappas=np.zeros(m, np.float32), signal0=np.zeros(m, np.float32), signal1=np.zeros(m, np.float32),
+                   lines0=np.zeros((m, 2), np.float32), lines1=np.zeros((m, 2), np.float32))
+        self._check(self.lib.ecc_pair_signals(self.h, i, j, dtr_i, dtr_j, m, _ptr(out["kappas"]), _ptr(out["signal0"]),
+                                              _ptr(out["signal1"]), _ptr(out["lines0"]), _ptr(out["lines1"]), C.byref(n),
+                                              C.byref(w), C.byref(v)))
+        out["weight"], out["value"] = w.value, v.value
+        return out
+
     def pair_sample_counts(self, n_views):
         counts = np.zeros(n_views * (n_views - 1) // 2, np.int32)
         self._check(self.lib.ecc_pair_sample_counts(self.h, _ptr(counts)))

@@ -857,6 +857,60 @@ int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, cons
     return ECC_OK;
 }
 
+int ecc_pair_signals(ecc_context* ctx, int p0, int p1, int dtr0, int dtr1, int capacity, float* kappas, float* signal0,
+                     float* signal1, float* lines0, float* lines1, int* n_samples, double* weight, double* value)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    PairLaunch L;
+    int rc = fill_launch(ctx, L);
+    if (rc) return rc;
+    const int idx_h[4] = {p0, p1, dtr0, dtr1};
+    if ((rc = check_indices(ctx, idx_h, 1))) return rc;
+    if (capacity < 0) return fail(ctx, ECC_ERR_INVALID, "ecc_pair_signals: negative capacity");
+    // scratch: [4 ints idx | 2 ints head | sample_cap * 13 floats], reusing the partial-sum buffer
+    const size_t words = 8 + (size_t)L.sample_cap * 13;
+    size_t cap = ctx->partials_cap * sizeof(float);
+    if ((rc = ensure_bytes(ctx, (void**)&ctx->partials_d, &cap, sizeof(float) * words))) return rc;
+    ctx->partials_cap = cap / sizeof(float);
+    int* idx_d = (int*)ctx->partials_d;
+    int* head_d = idx_d + 4;
+    float* rec_d = ctx->partials_d + 8;
+    if ((rc = ensure_pinned(ctx, sizeof(float) * words))) return rc;
+    std::memcpy(ctx->pinned_h, idx_h, sizeof(idx_h));
+    std::memset((char*)ctx->pinned_h + 16, 0, 16);
+    ECC_CUDA(ctx, cudaMemcpyAsync(idx_d, ctx->pinned_h, 32, cudaMemcpyHostToDevice, ctx->stream));
+    L.idx4_d = idx_d;
+    L.n_pairs = 1;
+    if ((rc = launch_pair_signals(ctx, L, rec_d, head_d))) return rc;
+    ECC_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_h, ctx->partials_d, sizeof(float) * words, cudaMemcpyDeviceToHost, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int* head = (const int*)ctx->pinned_h + 4;
+    const float* rec = (const float*)ctx->pinned_h + 8;
+    const int count = head[0];
+    float w;
+    std::memcpy(&w, &head[1], sizeof(w));
+    if (weight) *weight = (double)w;
+    if (n_samples) *n_samples = 2 * count;
+    // ascending kappa: -kappa_max ... -dkappa/2, +dkappa/2 ... +kappa_max
+    for (int q = 0; q < 2 * count && q < capacity; q++) {
+        const bool minus = q < count;
+        const int m = minus ? count - 1 - q : q - count;
+        const float* r = rec + (size_t)m * 13;
+        if (kappas) kappas[q] = minus ? -r[0] : r[0];
+        if (signal0) signal0[q] = minus ? r[3] : r[1];
+        if (signal1) signal1[q] = minus ? r[4] : r[2];
+        if (lines0) { lines0[2 * q] = minus ? r[9] : r[5]; lines0[2 * q + 1] = minus ? r[10] : r[6]; }
+        if (lines1) { lines1[2 * q] = minus ? r[11] : r[7]; lines1[2 * q + 1] = minus ? r[12] : r[8]; }
+    }
+    if (value) {
+        float v = 0.f;
+        if ((rc = ecc_evaluate_indices(ctx, idx_h, 1, &v, nullptr))) return rc;
+        *value = (double)v;
+    }
+    return ECC_OK;
+}
+
 int ecc_pair_sample_counts(ecc_context* ctx, int* counts)
 {
     if (!ctx || !counts) return ECC_ERR_INVALID;

@@ -213,6 +213,8 @@ struct PairLaunch {
 int launch_pairs(ecc_context* ctx, const PairLaunch& L);
 int fill_pair_launch(ecc_context* ctx, PairLaunch& L);  // everything that depends on the context state only (ecc_capi.cu)
 int launch_pair_counts(ecc_context* ctx, const PairLaunch& L, int* counts_d);
+// one pair (L.idx4_d[0..3]): rec_d [sample_cap][13] floats, head_d [2] ints zeroed before the launch (ecc_pairs.cu: pair_signals_kernel)
+int launch_pair_signals(ecc_context* ctx, const PairLaunch& L, float* rec_d, int* head_d);
 int launch_sum_sets(ecc_context* ctx, const float* vals_d, long long n_pairs, int n_sets,
                     double* sums_d);
 // radii_d (nullable): entry s receives the automatic object radius of set s (views_per_set matrices per set),

@@ -5,6 +5,7 @@
 #define ECC_FACADE_METRIC_RADON_INTERMEDIATE_H
 
 #include <set>
+#include <utility>
 #include <vector>
 
 #include "EpipolarConsistency.h"
@@ -200,14 +201,36 @@ public:
 
     /// Visualisation helper of the reference (EpipolarConsistencyRadonIntermediate.cpp:324-393): that code samples on
     /// the CPU with its own texel mapping.  Here: the pair's metric value from the GPU path; sample vectors are not filled.
+    /// The two redundant signals of pair (i, j) for plotting, in ascending kappa (EpipolarConsistencyRadonIntermediate.cpp
+    /// :324-393).  Sampled on the device with the metric's own lookup; returns the pair's metric value (the reference
+    /// returns the last term of its sum only, SURVEY.md Appendix B -- not reproduced).
     virtual double evaluateForImagePair(int i, int j, std::vector<float>* redundant_samples0 = 0x0,
                                         std::vector<float>* redundant_samples1 = 0x0, std::vector<float>* kappas = 0x0)
     {
-        (void)redundant_samples0; (void)redundant_samples1; (void)kappas;
-        std::vector<Eigen::Vector4i> one(1, Eigen::Vector4i(i, j, i, j));
-        float v = 0;
-        evaluate(one, &v);
-        return v;
+        return evaluateForImagePair(i, j, redundant_samples0, redundant_samples1, kappas, 0x0, 0x0);
+    }
+
+    /// ... and the sample locations in the two Radon transforms: (l0, l1) of every epipolar line.
+    double evaluateForImagePair(int i, int j, std::vector<float>* redundant_samples0, std::vector<float>* redundant_samples1,
+                                std::vector<float>* kappas, std::vector<std::pair<float, float> >* radon_samples0,
+                                std::vector<std::pair<float, float> >* radon_samples1)
+    {
+        pushSettings();
+        int n = 0;
+        double value = 0;
+        chk(ecc_pair_signals(ctx, i, j, i, j, 0, 0x0, 0x0, 0x0, 0x0, 0x0, &n, 0x0, &value), "ecc_pair_signals");
+        const bool any = redundant_samples0 || redundant_samples1 || kappas || radon_samples0 || radon_samples1;
+        if (!any || n == 0) return value;
+        std::vector<float> k(n), s0(n), s1(n), l0(2 * (size_t)n), l1(2 * (size_t)n);
+        chk(ecc_pair_signals(ctx, i, j, i, j, n, k.data(), s0.data(), s1.data(), l0.data(), l1.data(), &n, 0x0, 0x0), "ecc_pair_signals");
+        if (redundant_samples0) redundant_samples0->insert(redundant_samples0->end(), s0.begin(), s0.end());
+        if (redundant_samples1) redundant_samples1->insert(redundant_samples1->end(), s1.begin(), s1.end());
+        if (kappas) kappas->insert(kappas->end(), k.begin(), k.end());
+        for (int q = 0; q < n; q++) {
+            if (radon_samples0) radon_samples0->push_back(std::make_pair(l0[2 * q], l0[2 * q + 1]));
+            if (radon_samples1) radon_samples1->push_back(std::make_pair(l1[2 * q], l1[2 * q + 1]));
+        }
+        return value;
     }
 
 protected:

@@ -195,6 +195,18 @@ int ecc_evaluate_indices(ecc_context* ctx, const int* idx4, int n_pairs, float* 
 int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, const int* idx4,
                        int n_pairs, float* out, double* means);
 
+/* evaluateForImagePair (EpipolarConsistencyRadonIntermediate.cpp:324-393, "visualization only"): the two redundant
+ * signals of ONE pair, sampled on the device with the metric's own lookup (the reference walks them on the CPU with
+ * RadonIntermediate::sample, whose texel mapping differs slightly from the metric's).  Entries are in
+ * ascending kappa, -kappa_max ... +kappa_max, at kappa = +-(m + 1/2) dkappa; entry q belongs to the epipolar lines
+ * K0 (cos k, sin k) and K1 (cos k, sin k), whose (l0, l1) go to lines0 / lines1 (2 floats per entry).  All arrays are
+ * host memory of `capacity` entries, each nullable; n_samples receives the number of entries the pair has (also when
+ * capacity is smaller).  weight = K0[6] * dkappa and value = the pair's metric, so that
+ * value = weight * sum_q (signal0[q] - signal1[q])^2 (SSD variant; the reference's own return value is the LAST term
+ * only -- `ecc=` for `ecc+=`, SURVEY.md Appendix B -- which is not reproduced). */
+int ecc_pair_signals(ecc_context* ctx, int p0, int p1, int dtr0, int dtr1, int capacity, float* kappas, float* signal0,
+                     float* signal1, float* lines0, float* lines1, int* n_samples, double* weight, double* value);
+
 /* Number of kappa samples each pair takes (the work measure for equal-work partitioning), in
  * get_ij order; counts: n(n-1)/2 ints, host. */
 int ecc_pair_sample_counts(ecc_context* ctx, int* counts);

@@ -156,6 +156,15 @@ static int run_gpu(const char* tmpdir)
     std::printf("batch %.9g %.9g\n", means[0], means[1]);
     ecc.setObjectRadius(50.0).setEpipolarPlaneStep(0.002);
     std::printf("fixed %.9g\n", ecc.evaluate());
+    {   // evaluateForImagePair: the redundant signals of one pair (visualisation interface of the reference)
+        std::vector<float> s0, s1, ks;
+        std::vector<std::pair<float, float> > r0, r1;
+        const double v = ecc.evaluateForImagePair(1, 4, &s0, &s1, &ks, &r0, &r1);
+        double ssd = 0;
+        for (size_t q = 0; q < s0.size(); q++) ssd += (double)(s0[q] - s1[q]) * (s0[q] - s1[q]);
+        std::printf("signals %.9g %d %.9g %.9g %.9g\n", v, (int)s0.size(), ssd, (double)ks.front(), (double)ks.back());
+        if (s1.size() != s0.size() || ks.size() != s0.size() || r0.size() != s0.size() || r1.size() != s0.size()) return fail("signal sizes");
+    }
     // ---- adaptors: SingleImageMotion, Registration, Registration3D3D, the similarity models
     {
         Geometry::ModelCameraSimilarity2D3D model(Ps[2]);

@@ -81,7 +81,7 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
             pairs[(int(t[1]), int(t[2]))] = float(t[3])
         elif t[0] in ("radius", "mean", "subset", "fixed"):
             vals[t[0]] = float(t[1])
-        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre"):
+        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre", "signals"):
             vals[t[0]] = [float(x) for x in t[1:]]
     # the same scene through the Python mirror
     import torch
@@ -112,6 +112,15 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
     assert abs(vals["batch"][0] - want_batch[0]) <= 1e-7 * mean
     assert abs(vals["batch"][1] - want_batch[1]) <= 1e-7 * want_batch[1]
     assert vals["batch"][1] > 1.1 * vals["batch"][0]
+    # ---- evaluateForImagePair: value, number of samples, sum of squared differences, first and last kappa
+    ctx.set_object_radius(50.0)
+    ctx.set_epipolar_plane_step(0.002)
+    sig = ctx.pair_signals(1, 4)
+    v, cnt, ssd, k_first, k_last = vals["signals"]
+    assert int(cnt) == len(sig["kappas"]) and cnt > 100
+    assert abs(v - sig["value"]) <= 1e-7 * v
+    assert abs(ssd - float(((sig["signal0"].astype(np.float64) - sig["signal1"]) ** 2).sum())) <= 1e-6 * ssd
+    assert k_first == sig["kappas"][0] and k_last == sig["kappas"][-1] and k_first == -k_last
     # ---- adaptors: the same quantities through the mirror
     x = [1.5, -0.75, 0.004, 0.0, 0.8, -0.4, 0.3, 0.002, -0.003, 0.001, 0.0]
     P2 = api.camera_similarity_2d3d(Ps[2], x)

@@ -706,3 +706,58 @@ def test_metric_on_hybrid_dtrs_within_pair_tolerance(ctx):
         vals[name] = (mean, pair_values(cost, n))
     assert rel_err(vals["hybrid"][1], vals["texture"][1]).max() < PAIR_TOL_REF
     assert abs(vals["hybrid"][0] - vals["texture"][0]) < SUM_TOL * vals["texture"][0]
+
+
+# ---- evaluateForImagePair: the redundant signals of one pair (reference EpipolarConsistencyRadonIntermediate.cpp:324-393) ----
+def _bilinear_texture_convention(dtr, a, d):
+    """Bilinear lookup at normalised (a, d): texel centre i at (i + .5) / N, clamp to edge, exact fp32 weights."""
+    n_t, n_a = dtr.shape
+    x, y = np.float32(a) * np.float32(n_a) - np.float32(0.5), np.float32(d) * np.float32(n_t) - np.float32(0.5)
+    fx, fy = np.floor(x), np.floor(y)
+    wx, wy = np.float32(x - fx), np.float32(y - fy)
+    x0, x1 = int(np.clip(fx, 0, n_a - 1)), int(np.clip(fx + 1, 0, n_a - 1))
+    y0, y1 = int(np.clip(fy, 0, n_t - 1)), int(np.clip(fy + 1, 0, n_t - 1))
+    return float((1 - wx) * (1 - wy) * dtr[y0, x0] + wx * (1 - wy) * dtr[y0, x1] + (1 - wx) * wy * dtr[y1, x0] + wx * wy * dtr[y1, x1])
+
+
+@pytest.mark.parametrize("pair", [(0, 5), (2, 3), (7, 1)])
+def test_pair_signals_vs_numpy_restatement(ctx, scene, pair):
+    """Signals = the lookups the metric sums: K0/K1 from the reference's own computeK01 (oracle), line -> (angle, distance)
+    from its lineToSampleDtr, exact-fp32 bilinear lookup restated in numpy; value = weight * sum (s0 - s1)^2."""
+    i, j = pair
+    n_u, n_v, n_t = scene["n_u"], scene["n_v"], scene["n_t"]
+    dk = float(np.deg2rad(0.25))
+    setup_metric(ctx, scene, scene["dtr_exact"], api.INTERP_EXACT)
+    ctx.set_epipolar_plane_step(dk)
+    sig = ctx.pair_signals(i, j)
+    radius = ctx.get_object_radius()
+    A = [ol.pinv_transpose(scene["Ps"][k]) for k in (i, j)]
+    Cs = [ol.source_position(scene["Ps"][k]) for k in (i, j)]
+    diag = float(np.sqrt(np.float32(n_u * n_u + n_v * n_v)))
+    step_t = np.float32(np.sqrt(float(n_u) ** 2 + float(n_v) ** 2) / n_t)
+    K0, K1 = ol.compute_k01(n_u * 0.5, n_v * 0.5, Cs[0], Cs[1], A[0], A[1], radius, float(np.float32(n_t) * step_t * 2), dk)
+    dkappa, kappa_max = float(K1[6]), float(K1[7])
+    count = len(sig["kappas"]) // 2
+    want_k = [np.float32(dkappa) * np.float32(0.5) + np.float32(dkappa) * np.float32(m) for m in range(count)]
+    assert all(k < kappa_max for k in want_k) and not (np.float32(dkappa) * np.float32(0.5 + count) < kappa_max)
+    assert np.allclose(sig["kappas"][count:], want_k, rtol=1e-6) and np.allclose(sig["kappas"][:count], -np.array(want_k[::-1]), rtol=1e-6)
+    range_t = float(np.float32(n_t) * step_t)
+    want = np.zeros((2 * count, 2))
+    for q, kappa in enumerate(sig["kappas"]):
+        c, s_ = np.float32(np.cos(np.float64(kappa))), np.float32(np.sin(np.float64(kappa)))
+        for v, (K, dtr) in enumerate(((K0, scene["dtr_exact"][i]), (K1, scene["dtr_exact"][j]))):
+            line = np.array([K[0] * c + K[3] * s_, K[1] * c + K[4] * s_, K[2] * c + K[5] * s_], np.float32)
+            if v == 0:
+                assert np.allclose(sig["lines0"][q], line[:2], rtol=1e-4, atol=1e-6)
+            smp, flipped = ol.line_to_sample(line, range_t)
+            val = _bilinear_texture_convention(dtr, smp[0], smp[1])
+            want[q, v] = -val if flipped else val
+    peak = np.abs(want).max()
+    assert np.abs(sig["signal0"] - want[:, 0]).max() < 2e-3 * peak  # a lookup next to a bin edge moves with the last ulp of (a, d)
+    assert np.abs(sig["signal1"] - want[:, 1]).max() < 2e-3 * peak
+    ssd = float(((sig["signal0"].astype(np.float64) - sig["signal1"]) ** 2).sum())
+    assert abs(sig["weight"] * ssd - sig["value"]) < 1e-4 * sig["value"]  # the metric adds its terms in fp32
+    assert abs(sig["weight"] - float(K0[6]) * dkappa) < 1e-5 * sig["weight"]
+    out = np.zeros(1, np.float32)
+    ctx.evaluate_indices(np.array([(i, j, i, j)], np.int32), out)
+    assert sig["value"] == float(out[0])
