@@ -226,10 +226,10 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": ("radon_hybrid4_kernel (bound by the two on-chip data pipes: texture + shared memory; " if args.radon == "hybrid" else "radon_kernel (texture-unit bound; ") + "algorithmic tap bytes vs HBM copy peak)",
                          "achieved": radon_gbs, "peak": peak, "unit": "GB/s", "frac": radon_gbs / peak, "peak_source": peak_src,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one 64-projection launch of this command under
-                         # ncu --set full (profiles/ncu_radon_hybrid4_bench_r01.txt: 532.6 + 147.7 MB), scaled to the
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one 128-projection launch of this command under
+                         # ncu --set full (profiles/ncu_radon_hybrid4_bench_r01b.txt: 1133.5 + 318.9 MB), scaled to the
                          # projections per launch of this run; only known for the C3 image size and the hybrid engine
-                         "traffic": (6.803e8 / 64.0 * (hi - lo) * args.steps / max(radon_launches, 1)
+                         "traffic": (1.4524e9 / 128.0 * (hi - lo) * args.steps / max(radon_launches, 1)
                                      if (args.radon == "hybrid" and args.workload == "c3") else None),
                          "samples_per_s": radon_gbs * 1e9 / 16.0,
                          "tex_rate_frac": (radon_gbs * 1e9 / 16.0) / 1.09e12,
@@ -238,9 +238,9 @@ def run_b200(args):
                          "onchip_peak_gbs": 192.0 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
                          "onchip_frac": radon_gbs / (192.0 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9),
                          "note": "16 B per bilinear sample x %.4g samples per projection, on-chip traffic (hence frac > 1 against the "
-                                 "HBM copy peak; DRAM moves 10.6 MB per projection); tex_rate_frac = samples/s over the measured tex2D rate of "
+                                 "HBM copy peak; DRAM moves 11.3 MB per projection); tex_rate_frac = samples/s over the measured tex2D rate of "
                                  "this GPU (1.09e12/s at 1965 MHz, profiles/tex_probe_r01.txt); ncu of a launch of this command: texture "
-                                 "data pipe 97 %% of peak, shared-memory pipe 81 %%, issue slots 54 %% (profiles/ncu_radon_hybrid4_bench_r01.txt)" % samples_per_proj},
+                                 "data pipe 98 %% of peak, shared-memory pipe 82 %%, issue slots 62 %% (profiles/ncu_radon_hybrid4_bench_r01b.txt)" % samples_per_proj},
             "roofline_pairs": {"bound": "hbm", "kernel": "pairs_kernel (L1/texture gather bound)", "achieved": pairs_gbs, "peak": peak,
                                "unit": "GB/s", "frac": pairs_gbs / peak, "kappa_samples": float(counts.sum()),
                                # random-gather rates of this pool's B200 (tools/gather_probe.cu, profiles/gather_probe_r01.txt):
@@ -248,7 +248,7 @@ def run_b200(args):
                                "gather_peaks_gbs": {"l2_random_sectors": 4380.0, "hbm_random_sectors": 1021.0, "texture_random_1GB": 427.0},
                                "frac_of_l2_gather": pairs_gbs / 4380.0,
                                "note": "64 B of taps per kappa sample; above the random-gather rates because neighbouring kappa samples "
-                                       "share taps in L1TEX (the kernel is issue bound, profiles/ncu_pairs_r01.txt)"},
+                                       "share taps in L1TEX (the kernel is issue bound: issue slots 66 %, texture pipe 31 %, profiles/ncu_pairs_r01b.txt)"},
         }
         if args.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(W, Ps, full_dtrs=pipe._full)
