@@ -42,6 +42,7 @@ SIGNATURES = {
     "ecc_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),
     "ecc_evaluate_range": (C.c_int, [c_ctx, C.c_longlong, C.c_longlong, c_vp, C.POINTER(C.c_double)]),
     "ecc_evaluate_indices": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.POINTER(C.c_double)]),
+    "ecc_update_and_evaluate": (C.c_int, [c_ctx, C.c_int, c_vp, c_vp, C.c_int, c_vp, C.POINTER(C.c_double)]),
     "ecc_evaluate_batch": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
     "ecc_pair_signals": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -205,6 +205,14 @@ class Context:
                                                   C.byref(m) if want_mean else None))
         return m.value if want_mean else None
 
+    def update_and_evaluate(self, index, P, idx4, out=None):
+        """One tracking step: replace matrix `index`, evaluate the listed pairs; replayed as one CUDA graph from the third
+        call with the same index / list / settings on.  Returns the mean."""
+        P = np.ascontiguousarray(P, np.float64).reshape(12)
+        m = C.c_double()
+        self._check(self.lib.ecc_update_and_evaluate(self.h, int(index), _ptr(P), _ptr(idx4), idx4.shape[0], _ptr(out), C.byref(m)))
+        return m.value
+
     def evaluate_batch(self, Ps_sets, idx4=None, out=None, want_means=True):
         if isinstance(Ps_sets, np.ndarray):
             Ps_sets = np.ascontiguousarray(Ps_sets, np.float64)

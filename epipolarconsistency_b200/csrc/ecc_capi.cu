@@ -158,6 +158,7 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
     L.vals_d = nullptr;
     L.image_d = nullptr;
     L.splits = 1;
+    L.defer_finalize = 0;
     L.partials_d = nullptr;
     return ECC_OK;
 }
@@ -200,6 +201,8 @@ std::map<ecc_context*, BatchBuffers>& batch_buffers()
 
 extern "C" {
 
+static void track_free(ecc_context* ctx);
+
 int ecc_version(void) { return ECC_B200_VERSION; }
 
 int ecc_create(int device, ecc_context** out)
@@ -234,6 +237,7 @@ void ecc_destroy(ecc_context* ctx)
     free_hybrid(ctx);
     free_hybrid4(ctx);
     team_free(ctx);
+    track_free(ctx);
     if (ctx->ramp_g_d) cudaFree(ctx->ramp_g_d);
     if (ctx->pre_work_d) cudaFree(ctx->pre_work_d);
     if (ctx->pre_small_d) cudaFree(ctx->pre_small_d);
@@ -580,10 +584,15 @@ int ecc_update_projection_matrix(ecc_context* ctx, int index, const double* P)
     // memory completes before the call returns, so overwriting is safe)
     std::memcpy(&ctx->Ps_h[(size_t)12 * index], P, sizeof(double) * 12);
     ctx->geometry_version++;
-    ECC_CUDA(ctx, cudaMemcpyAsync(ctx->Ps_d + (size_t)12 * index, &ctx->Ps_h[(size_t)12 * index], sizeof(double) * 12,
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    return launch_derive_views(ctx, ctx->Ps_d + (size_t)12 * index, 1, ctx->PinvTs_d + (size_t)12 * index,
-                               ctx->Cs_d + (size_t)4 * index);
+    // One view: derived on the host (the same fp64 operation sequence as the device kernel, bit-identical:
+    // tests/test_gpu_parity.py::test_derived_views_device_equals_host_equals_reference) and uploaded as 64 bytes -- a
+    // one-thread fp64 kernel would sit on the critical path of every tracking step for ~8 us.  (Ps_d is only the staging
+    // of the whole-set derivation and is not kept current here.)
+    float A[12], C[4];
+    derive_view(P, A, C);
+    ECC_CUDA(ctx, cudaMemcpyAsync(ctx->PinvTs_d + (size_t)12 * index, A, sizeof(A), cudaMemcpyHostToDevice, ctx->stream));
+    ECC_CUDA(ctx, cudaMemcpyAsync(ctx->Cs_d + (size_t)4 * index, C, sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    return ECC_OK;
 }
 
 int ecc_get_derived_views(ecc_context* ctx, float* PinvTs, float* Cs)
@@ -789,6 +798,140 @@ int ecc_evaluate_indices(ecc_context* ctx, const int* idx4, int n_pairs, float* 
         if (mean) *mean = *sum_h / (double)n_pairs;
         if (host_out) std::memcpy(out, vals_h, sizeof(float) * n_pairs);
     }
+    return ECC_OK;
+}
+
+// ---- tracking step as one CUDA graph -------------------------------------------------------------------------------
+static void track_free(ecc_context* ctx)
+{
+    TrackGraph& T = ctx->track;
+    if (T.exec) cudaGraphExecDestroy(T.exec);
+    if (T.idx_d) cudaFree(T.idx_d);
+    if (T.pinned) cudaFreeHost(T.pinned);
+    T = TrackGraph();
+}
+
+// Records {H2D of the derived view (64 bytes), pair kernel, finalize + sum writing into pinned host memory} on the context's
+// own stream: four nodes.
+static int track_capture(ecc_context* ctx, int index, int n_pairs, bool want_out, const PairLaunch& L_in)
+{
+    TrackGraph& T = ctx->track;
+    if (T.exec) { cudaGraphExecDestroy(T.exec); T.exec = nullptr; }
+    float* view_pin = (float*)T.pinned;            // [12 floats (P+)^T | 4 floats C]
+    double* sum_pin = (double*)(view_pin + 16);
+    float* vals_pin = (float*)(sum_pin + 1);
+    cudaStream_t saved = ctx->stream, cap = ctx->own_stream;
+    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return ECC_ERR_CUDA; }
+    ctx->stream = cap;
+    int rc = ECC_OK;
+    do {
+        if (cudaMemcpyAsync(ctx->PinvTs_d + (size_t)12 * index, view_pin, sizeof(float) * 12, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
+        if (cudaMemcpyAsync(ctx->Cs_d + (size_t)4 * index, view_pin + 12, sizeof(float) * 4, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
+        PairLaunch L = L_in;
+        L.idx4_d = T.idx_d;
+        L.vals_d = ctx->vals_d;
+        L.n_pairs = n_pairs;
+        L.defer_finalize = 1;
+        PairLaunch R;
+        if ((rc = launch_pairs(ctx, L, &R))) break;
+        // finalize + sum in one launch that writes the results straight into the pinned block (no copy nodes)
+        if ((rc = launch_finalize_sum(ctx, R, sum_pin, want_out ? vals_pin : nullptr))) break;
+    } while (0);
+    ctx->stream = saved;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    if (rc == ECC_OK && (e != cudaSuccess || !graph)) rc = ECC_ERR_CUDA;
+    if (rc == ECC_OK && cudaGraphInstantiate(&T.exec, graph, 0) != cudaSuccess) { T.exec = nullptr; rc = ECC_ERR_CUDA; }
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc;
+}
+
+int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const int* idx4, int n_pairs, float* out, double* mean)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!P || index < 0 || index >= ctx->n_views) return fail(ctx, ECC_ERR_INVALID, "ecc_update_and_evaluate: bad index");
+    if (n_pairs < 0 || (n_pairs > 0 && !idx4)) return fail(ctx, ECC_ERR_INVALID, "ecc_update_and_evaluate: bad argument");
+    TrackGraph& T = ctx->track;
+    const bool out_dev = out && is_device_pointer(out);
+    const bool idx_dev = idx4 && is_device_pointer(idx4);
+    static const bool graphs_off = getenv("ECC_NO_GRAPHS") != nullptr;
+    if (graphs_off || T.failed || ctx->profiling || out_dev || n_pairs == 0 || (idx_dev && (uintptr_t)idx4 % 16 != 0)) {
+        int rc = ecc_update_projection_matrix(ctx, index, P);
+        if (rc) return rc;
+        return ecc_evaluate_indices(ctx, idx4, n_pairs, out, mean);
+    }
+    int rc;
+    if (!idx_dev && (rc = check_indices(ctx, idx4, n_pairs))) return rc;
+    // host copy of the matrix first: the automatic object radius reads it (first view only)
+    std::memcpy(&ctx->Ps_h[(size_t)12 * index], P, sizeof(double) * 12);
+    ctx->geometry_version++;
+    PairLaunch L;
+    if ((rc = fill_launch(ctx, L))) return rc;
+    const bool same_list = idx_dev ? false : ((int)T.idx_h.size() == 4 * n_pairs && std::memcmp(T.idx_h.data(), idx4, sizeof(int) * 4 * n_pairs) == 0);
+    const std::vector<double> key = {(double)index, (double)n_pairs, idx_dev ? (double)(uintptr_t)idx4 : -1.0, (double)(out != nullptr),
+                                     (double)L.radius, (double)L.dkappa, (double)L.interp, (double)L.use_corr, (double)L.is_derivative,
+                                     (double)L.n_views, (double)L.n_dtrs, (double)L.n_alpha, (double)L.n_t, (double)L.range_t,
+                                     (double)L.sample_cap, (double)L.dtr_pitch, (double)L.half_nu, (double)L.half_nv,
+                                     (double)(uintptr_t)L.tex_d, (double)(uintptr_t)L.dtr_ptrs_d, (double)(uintptr_t)ctx->Ps_d,
+                                     (double)(uintptr_t)ctx->Cs_d, (double)(uintptr_t)ctx->PinvTs_d, (double)(uintptr_t)ctx->vals_d,
+                                     (double)(uintptr_t)ctx->sums_d, (double)(uintptr_t)ctx->partials_d, (double)(uintptr_t)ctx->dtr_tex_h.size()};
+    const bool replay = T.exec && key == T.key && (idx_dev || same_list);
+    if (!replay) {
+        const bool seen = key == T.pending_key && (idx_dev || same_list);
+        if (!seen) {
+            // first call with these parameters: the plain path (it also sizes every buffer the graph will use)
+            T.pending_key.clear();
+            rc = ecc_update_projection_matrix(ctx, index, P);
+            if (!rc) rc = ecc_evaluate_indices(ctx, idx4, n_pairs, out, mean);
+            if (rc) return rc;
+            if (!idx_dev) T.idx_h.assign(idx4, idx4 + (size_t)4 * n_pairs);
+            // the key as the NEXT call will see it (buffers may have been allocated just now)
+            std::vector<double> k2 = key;
+            PairLaunch L2;
+            if (fill_launch(ctx, L2) == ECC_OK) {
+                k2[18] = (double)(uintptr_t)L2.tex_d; k2[19] = (double)(uintptr_t)L2.dtr_ptrs_d;
+            }
+            k2[20] = (double)(uintptr_t)ctx->Ps_d; k2[21] = (double)(uintptr_t)ctx->Cs_d; k2[22] = (double)(uintptr_t)ctx->PinvTs_d;
+            k2[23] = (double)(uintptr_t)ctx->vals_d; k2[24] = (double)(uintptr_t)ctx->sums_d; k2[25] = (double)(uintptr_t)ctx->partials_d;
+            T.pending_key = k2;
+            return ECC_OK;
+        }
+        // second call: record.  Own copies of the pair list and the pinned block first (outside the capture).
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (T.idx_cap < sizeof(int) * 4 * (size_t)n_pairs) {
+            if (T.idx_d) cudaFree(T.idx_d);
+            T.idx_d = nullptr; T.idx_cap = 0;
+            ECC_CUDA(ctx, cudaMalloc(&T.idx_d, sizeof(int) * 4 * (size_t)n_pairs));
+            T.idx_cap = sizeof(int) * 4 * (size_t)n_pairs;
+        }
+        ECC_CUDA(ctx, cudaMemcpy(T.idx_d, idx4, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyDefault));
+        const size_t need = sizeof(float) * 16 + sizeof(double) + sizeof(float) * (size_t)n_pairs;
+        if (T.pinned_bytes < need) {
+            if (T.pinned) cudaFreeHost(T.pinned);
+            T.pinned = nullptr; T.pinned_bytes = 0;
+            ECC_CUDA(ctx, cudaMallocHost(&T.pinned, need));
+            T.pinned_bytes = need;
+        }
+        if (track_capture(ctx, index, n_pairs, out != nullptr, L) != ECC_OK) {
+            T.failed = true;  // e.g. a driver without stream capture for one of the nodes: plain path from now on
+            rc = ecc_update_projection_matrix(ctx, index, P);
+            if (rc) return rc;
+            return ecc_evaluate_indices(ctx, idx4, n_pairs, out, mean);
+        }
+        T.key = key;
+        T.pending_key.clear();
+    }
+    // replay: the matrix goes through the pinned block, everything else is in the recorded nodes
+    float* view_pin = (float*)T.pinned;
+    derive_view(P, view_pin, view_pin + 12);  // on the host, bit-identical to the device derivation
+    ECC_CUDA(ctx, cudaGraphLaunch(T.exec, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    T.replays++;
+    const double* sum_pin = (const double*)(view_pin + 16);
+    if (mean) *mean = *sum_pin / (double)n_pairs;
+    if (out) std::memcpy(out, (const float*)(sum_pin + 1), sizeof(float) * (size_t)n_pairs);
     return ECC_OK;
 }
 

@@ -81,6 +81,20 @@ struct Team {
     float* vals() const { return (float*)((char*)block + vals_offset); }
 };
 
+// ecc_update_and_evaluate: the {replace one matrix, evaluate a pair list} step of tracking loops, recorded once as a CUDA
+// graph and replayed.  `key` holds everything the recorded nodes depend on (sizes, settings, buffer addresses).
+struct TrackGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<double> key, pending_key;
+    std::vector<int> idx_h;      // the host pair list the device copy below was made from
+    int* idx_d = nullptr;        // own copy of the pair list (the context's idx_d is scratch of other calls)
+    size_t idx_cap = 0;
+    void* pinned = nullptr;      // [12 doubles P | double sum | floats vals]
+    size_t pinned_bytes = 0;
+    bool failed = false;         // capture did not work here: stay on the plain path
+    long long replays = 0;
+};
+
 }  // namespace eccb200
 
 struct ecc_context {
@@ -154,6 +168,7 @@ struct ecc_context {
     eccb200::HybridStage hybrid;
     eccb200::Hybrid4Stage hybrid4;
     eccb200::Team team;
+    eccb200::TrackGraph track;
 
     // ---- profiling ----
     bool profiling = false;
@@ -204,13 +219,18 @@ struct PairLaunch {
     int is_derivative;
     int interp;
     int use_corr;  // correlation variant instead of the SSD
+    int defer_finalize;  // split launches: leave the partial sums for launch_finalize_sum
     int splits;          // set by launch_pairs: CTAs per pair (CTA-per-pair launches)
     float* partials_d;   // [items][splits][3] when splits > 1
     // outputs
     float* vals_d;   // n_sets*n_pairs
     float* image_d;  // all-pairs: n_views*n_views cost image or null (only with n_sets==1)
 };
-int launch_pairs(ecc_context* ctx, const PairLaunch& L);
+// resolved (nullable): the launch record as launched (splits, partials_d filled in)
+int launch_pairs(ecc_context* ctx, const PairLaunch& L, PairLaunch* resolved = nullptr);
+// single matrix set, after launch_pairs(..., &resolved) with defer_finalize: finalize + fixed-order fp64 sum in one launch;
+// sum_out / vals_out (nullable) may be pinned host memory
+int launch_finalize_sum(ecc_context* ctx, const PairLaunch& resolved, double* sum_out, float* vals_out);
 int fill_pair_launch(ecc_context* ctx, PairLaunch& L);  // everything that depends on the context state only (ecc_capi.cu)
 int launch_pair_counts(ecc_context* ctx, const PairLaunch& L, int* counts_d);
 // one pair (L.idx4_d[0..3]): rec_d [sample_cap][13] floats, head_d [2] ints zeroed before the launch (ecc_pairs.cu: pair_signals_kernel)

@@ -264,12 +264,7 @@ public:
     double evaluateMovingPairs(const ProjectionMatrix& P_input, float* out = 0x0)
     {
         Ps[input_index] = P_input;
-        ecc->updateProjectionMatrix(input_index, P_input);
-        if (!out) {
-            tmp_results.resize(indices.size());
-            out = tmp_results.data();
-        }
-        return ecc->evaluate(indices, out);
+        return ecc->updateAndEvaluate(input_index, P_input, indices, out);  // one recorded CUDA graph per step
     }
 
     /// K candidate matrices for the input image scored in one launch (n-1 pairs each); returns the K means.

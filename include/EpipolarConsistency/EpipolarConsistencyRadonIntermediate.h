@@ -125,6 +125,20 @@ public:
         return *this;
     }
 
+    /// NEW: updateProjectionMatrix(index, P) followed by evaluate(indices, out) as ONE call (same results); repeated calls
+    /// with the same index and list replay a recorded CUDA graph (ecc_update_and_evaluate): the step of a tracking loop.
+    double updateAndEvaluate(int index, const ProjectionMatrix& P, const std::vector<Eigen::Vector4i>& indices, float* out = 0x0)
+    {
+        Ps[index] = P;
+        pushSettings();
+        std::vector<int> flat(indices.size() * 4);
+        for (size_t i = 0; i < indices.size(); i++)
+            for (int k = 0; k < 4; k++) flat[4 * i + k] = indices[i][k];
+        double mean = 0;
+        chk(ecc_update_and_evaluate(ctx, index, P.data(), flat.data(), (int)indices.size(), out, &mean), "ecc_update_and_evaluate");
+        return mean;
+    }
+
     /// Radius of the object: the user's value, or the automatic estimate from the first matrix.
     virtual double getObjectRadius() const
     {

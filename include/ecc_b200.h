@@ -188,6 +188,14 @@ int ecc_evaluate_range(ecc_context* ctx, long long pair_begin, long long pair_en
  * (P0,P1,dtr0,dtr1) per pair.  idx4 [h|d]; out [h|d], nullable: n_pairs floats. */
 int ecc_evaluate_indices(ecc_context* ctx, const int* idx4, int n_pairs, float* out, double* mean);
 
+/* One step of a tracking / single-view loop (Gui/SingleImageMotion.h:84-90: one matrix changes, the pair list stays):
+ * ecc_update_projection_matrix(index, P) followed by ecc_evaluate_indices(idx4, n_pairs, out, mean), with the same
+ * results.  From the third call with the same index, list and settings on, the step is replayed as ONE recorded CUDA graph
+ * {upload of the matrix, derivation of its view, pair kernels, sum, download} instead of seven API calls (BASELINE config
+ * C5: the step is launch-latency bound).  idx4 [h|d]; out: host memory or NULL (device memory takes the plain path). */
+int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const int* idx4, int n_pairs, float* out,
+                            double* mean);
+
 /* Batched mode (new capability): n_sets complete projection-matrix sets
  * (n_sets * n * 12 doubles, n = number of matrices per set = current n of the context) scored
  * against the same dtrs in one launch.  idx4 nullable (all pairs).  out [h|d], nullable:

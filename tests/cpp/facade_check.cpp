@@ -180,6 +180,13 @@ static int run_gpu(const char* tmpdir)
         const double all1 = sim.evaluate(P2);
         std::vector<float> per_pair(n - 1);
         const double moving1 = sim.evaluateMovingPairs(P2, per_pair.data());
+        // the same step again and again: plain path, recorded, replayed -- always the same bits
+        for (int rep = 0; rep < 4; rep++) {
+            std::vector<float> again(n - 1);
+            if (sim.evaluateMovingPairs(P2, again.data()) != moving1) return fail("SingleImageMotion graph replay mean");
+            for (int k = 0; k < n - 1; k++)
+                if (again[k] != per_pair[k]) return fail("SingleImageMotion graph replay values");
+        }
         std::vector<ProjectionMatrix> cands;
         cands.push_back(Ps[2]);
         cands.push_back(P2);

@@ -761,3 +761,55 @@ def test_pair_signals_vs_numpy_restatement(ctx, scene, pair):
     out = np.zeros(1, np.float32)
     ctx.evaluate_indices(np.array([(i, j, i, j)], np.int32), out)
     assert sig["value"] == float(out[0])
+
+
+def test_update_and_evaluate_graph_replay_equals_plain_calls(ctx, scene):
+    """ecc_update_and_evaluate: plain path on the first call, recorded on the second, replayed afterwards -- always the
+    bits of update_projection_matrix + evaluate_indices; a changed list, index or setting re-records."""
+    n = scene["n"]
+    setup_metric(ctx, scene, scene["dtr_tex"], api.INTERP_TEXTURE, dkappa=float(np.deg2rad(0.1)))
+    rng = np.random.default_rng(11)
+    live = 4
+    idx = np.array([(live, i, live, i) for i in range(n) if i != live], np.int32)
+
+    def perturbed():
+        P = scene["Ps"][live].reshape(4, 3).T.copy()
+        H = np.eye(3)
+        H[0, 2], H[1, 2] = rng.normal(0, 1.0, 2)
+        return (H @ P).T.reshape(12)
+
+    def plain(k, P, ix):
+        ctx.update_projection_matrix(k, P)
+        out = np.zeros(len(ix), np.float32)
+        return ctx.evaluate_indices(ix, out), out
+
+    for step in range(6):
+        P = perturbed()
+        out = np.zeros(len(idx), np.float32)
+        mean = ctx.update_and_evaluate(live, P, idx, out)
+        want_mean, want = plain(live, P, idx)
+        assert mean == want_mean and np.array_equal(out, want), step
+    # another list (shorter), device-resident, no per-pair output
+    import torch
+    idx2 = torch.from_numpy(idx[:5].copy()).cuda()
+    for step in range(4):
+        P = perturbed()
+        mean = ctx.update_and_evaluate(live, P, idx2)
+        want_mean, _ = plain(live, P, idx[:5])
+        assert mean == want_mean, step
+    # a setting changes between replays
+    ctx.set_epipolar_plane_step(float(np.deg2rad(0.2)))
+    for step in range(4):
+        P = perturbed()
+        mean = ctx.update_and_evaluate(live, P, idx2)
+        want_mean, _ = plain(live, P, idx[:5])
+        assert mean == want_mean, step
+    # the first view carries the automatic object radius: replacing it must not replay a stale radius
+    idx0 = np.array([(0, i, 0, i) for i in range(1, n)], np.int32)
+    for step in range(4):
+        P = scene["Ps"][0].copy()
+        P[9:12] *= 1.0 + 0.01 * (step + 1)   # scale the last column: moves the source, changes the radius estimate
+        mean = ctx.update_and_evaluate(0, P, idx0)
+        want_mean, _ = plain(0, P, idx0)
+        assert mean == want_mean, step
+    ctx.set_projection_matrices(scene["Ps"])

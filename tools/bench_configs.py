@@ -157,6 +157,21 @@ def c5(ctx):
         lat = np.array(lat[200:]) * 1e6
         out[name] = {"calls_per_s": 1e6 / lat.mean(), "p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)),
                      "pairs_per_s": n_ref * 1e6 / lat.mean(), "pair_kernel_us": 1e3 * pk_ms / max(pk_n, 1)}
+        # the same step through ecc_update_and_evaluate: one recorded CUDA graph per call
+        want = []
+        for k in range(4):
+            ctx.update_projection_matrix(n_ref, live[k])
+            want.append(ctx.evaluate_indices(ix))
+        got = [ctx.update_and_evaluate(n_ref, live[k % 64], ix) for k in range(8)][4:]
+        got = [ctx.update_and_evaluate(n_ref, live[k], ix) for k in range(4)]
+        lat = []
+        for k in range(2200):
+            t0 = time.perf_counter()
+            ctx.update_and_evaluate(n_ref, live[k % 64], ix)
+            lat.append(time.perf_counter() - t0)
+        lat = np.array(lat[200:]) * 1e6
+        out[name + "_graph"] = {"calls_per_s": 1e6 / lat.mean(), "p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)),
+                                "pairs_per_s": n_ref * 1e6 / lat.mean(), "identical_to_plain_calls": bool(got == want)}
     return out
 
 
