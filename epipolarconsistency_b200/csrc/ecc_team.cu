@@ -23,7 +23,7 @@ using namespace eccb200;
 namespace {
 
 constexpr size_t kFlagBytes = 512;                       // flags[world] at the start of a block
-constexpr unsigned long long kBarrierTimeoutNs = 20ull * 1000 * 1000 * 1000;  // a rank that never arrives: give up, report
+constexpr unsigned long long kBarrierTimeoutNs = 60ull * 1000 * 1000 * 1000;  // a rank that never arrives: give up, report
 
 size_t round512(size_t v) { return (v + 511) / 512 * 512; }
 
