@@ -813,7 +813,7 @@ static void track_free(ecc_context* ctx)
 
 // Records {H2D of the derived view (64 bytes), pair kernel, finalize + sum writing into pinned host memory} on the context's
 // own stream: four nodes.
-static int track_capture(ecc_context* ctx, int index, int n_pairs, bool want_out, const PairLaunch& L_in)
+static int track_capture(ecc_context* ctx, int index, int n_pairs, bool want_out, const PairLaunch& L_in, const int* idx_user_d)
 {
     TrackGraph& T = ctx->track;
     if (T.exec) { cudaGraphExecDestroy(T.exec); T.exec = nullptr; }
@@ -828,7 +828,7 @@ static int track_capture(ecc_context* ctx, int index, int n_pairs, bool want_out
         if (cudaMemcpyAsync(ctx->PinvTs_d + (size_t)12 * index, view_pin, sizeof(float) * 12, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
         if (cudaMemcpyAsync(ctx->Cs_d + (size_t)4 * index, view_pin + 12, sizeof(float) * 4, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
         PairLaunch L = L_in;
-        L.idx4_d = T.idx_d;
+        L.idx4_d = idx_user_d ? idx_user_d : T.idx_d;  // a device-resident list is read in place at every replay
         L.vals_d = ctx->vals_d;
         L.n_pairs = n_pairs;
         L.defer_finalize = 1;
@@ -900,13 +900,15 @@ int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const 
         }
         // second call: record.  Own copies of the pair list and the pinned block first (outside the capture).
         ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (T.idx_cap < sizeof(int) * 4 * (size_t)n_pairs) {
-            if (T.idx_d) cudaFree(T.idx_d);
-            T.idx_d = nullptr; T.idx_cap = 0;
-            ECC_CUDA(ctx, cudaMalloc(&T.idx_d, sizeof(int) * 4 * (size_t)n_pairs));
-            T.idx_cap = sizeof(int) * 4 * (size_t)n_pairs;
+        if (!idx_dev) {
+            if (T.idx_cap < sizeof(int) * 4 * (size_t)n_pairs) {
+                if (T.idx_d) cudaFree(T.idx_d);
+                T.idx_d = nullptr; T.idx_cap = 0;
+                ECC_CUDA(ctx, cudaMalloc(&T.idx_d, sizeof(int) * 4 * (size_t)n_pairs));
+                T.idx_cap = sizeof(int) * 4 * (size_t)n_pairs;
+            }
+            ECC_CUDA(ctx, cudaMemcpy(T.idx_d, idx4, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyHostToDevice));
         }
-        ECC_CUDA(ctx, cudaMemcpy(T.idx_d, idx4, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyDefault));
         const size_t need = sizeof(float) * 16 + sizeof(double) + sizeof(float) * (size_t)n_pairs;
         if (T.pinned_bytes < need) {
             if (T.pinned) cudaFreeHost(T.pinned);
@@ -914,7 +916,7 @@ int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const 
             ECC_CUDA(ctx, cudaMallocHost(&T.pinned, need));
             T.pinned_bytes = need;
         }
-        if (track_capture(ctx, index, n_pairs, out != nullptr, L) != ECC_OK) {
+        if (track_capture(ctx, index, n_pairs, out != nullptr, L, idx_dev ? idx4 : nullptr) != ECC_OK) {
             T.failed = true;  // e.g. a driver without stream capture for one of the nodes: plain path from now on
             rc = ecc_update_projection_matrix(ctx, index, P);
             if (rc) return rc;

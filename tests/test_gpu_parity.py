@@ -797,12 +797,19 @@ def test_update_and_evaluate_graph_replay_equals_plain_calls(ctx, scene):
         mean = ctx.update_and_evaluate(live, P, idx2)
         want_mean, _ = plain(live, P, idx[:5])
         assert mean == want_mean, step
+    # a device-resident list is read in place: changing its CONTENTS (same address) must show in the next replay
+    idx2[:, 1] = torch.tensor([int(i) for i in idx[4:9, 1]], dtype=torch.int32, device="cuda")
+    idx2[:, 3] = idx2[:, 1]
+    P = perturbed()
+    mean = ctx.update_and_evaluate(live, P, idx2)
+    want_mean, _ = plain(live, P, idx[4:9])
+    assert mean == want_mean
     # a setting changes between replays
     ctx.set_epipolar_plane_step(float(np.deg2rad(0.2)))
     for step in range(4):
         P = perturbed()
         mean = ctx.update_and_evaluate(live, P, idx2)
-        want_mean, _ = plain(live, P, idx[:5])
+        want_mean, _ = plain(live, P, idx[4:9])
         assert mean == want_mean, step
     # the first view carries the automatic object radius: replacing it must not replay a stale radius
     idx0 = np.array([(0, i, 0, i) for i in range(1, n)], np.int32)
