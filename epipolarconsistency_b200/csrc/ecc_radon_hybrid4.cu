@@ -26,7 +26,16 @@ constexpr int kChunk4 = ECC_CHUNK4;     // pixels of the primary axis per chunk
 constexpr int kLead4 = 2;               // window columns in front of the chunk
 constexpr int kBoxW4 = ECC_CHUNK4 + 4;  // window columns [c0-2, c0+chunk+2)
 constexpr int kRows4 = 201;        // window rows; odd, so that neighbouring columns start one 16-byte bank group apart
-constexpr int kMaxChunks4 = 128;   // primary axis up to 2048 px
+constexpr int kMaxChunks4 = 2048 / ECC_CHUNK4;   // primary axis up to 2048 px
+#ifndef ECC_NBUF4
+#define ECC_NBUF4 1
+#endif
+// Window buffers: 2 = the TMA load of the next chunk runs under the current chunk's samples.  Measured (C2 size): the
+// window warps wait for their TMA box a quarter of their time (ncu source view: 12 % of all samples on the mbarrier
+// try_wait), and two buffers make the window path ALONE 10 % faster (chunk 12: 0.906 against 1.011 ms/projection) -- but
+// the kernel as a whole much slower (0.86; chunk 8: 0.79 against 0.62): the second buffer comes out of the SM's L1
+// (carve-out 132 -> 164/228 KB), and the texture path lives on those 124 KB of L1TEX.  Hence one buffer.
+constexpr int kNBuf4 = ECC_NBUF4;
 
 struct Hybrid4Params {
     const cudaTextureObject_t* texs;  // one float4 texture per quad
@@ -172,7 +181,7 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
                      const __grid_constant__ Hybrid4Params p)
 {
     extern __shared__ __align__(128) unsigned char window_raw[];
-    __shared__ __align__(8) unsigned long long mbar_store[1];
+    __shared__ __align__(8) unsigned long long mbar_store[2];
     __shared__ int s_item, s_jmin, s_jmax, s_fallback;
     __shared__ int win_lo[kMaxChunks4], win_hi[kMaxChunks4];
 
@@ -182,6 +191,7 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
 
     if (tid == 0) {
         mbar_init(smem_u32(&mbar_store[0]), 1);
+        mbar_init(smem_u32(&mbar_store[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -210,8 +220,9 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
     if (p.mode == 1) return;
     const unsigned window_base = smem_u32(window_raw);
     const unsigned buf_bytes = (unsigned)kRows4 * kBoxW4 * 16u;
+    const unsigned buf_stride = (buf_bytes + 127u) & ~127u;  // TMA destinations are 128-byte aligned
     const unsigned mbar0 = smem_u32(&mbar_store[0]);
-    unsigned phase0 = 0;
+    unsigned phase0 = 0, phase1 = 0;
     for (;;) {
         if (tid == 0) {
             s_item = take_front(p.counters, p.claim, total_items);
@@ -310,24 +321,37 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
             float t = live ? L.t : 3.0e38f;
             const float t_max = live ? ref_last_sample(L.t, L.t_max) : -3.0e38f;
             Sum4 sum = {0.f, 0.f, 0.f, 0.f}, sumo = {0.f, 0.f, 0.f, 0.f};
+            // issue the load of chunk k (traversal order) into buffer k % kNBuf4
+            auto issue = [&](int k) {
+                const int kk = dir > 0 ? k : n_chunks - 1 - k;
+                const int lo = win_lo[kk], hi = win_hi[kk];
+                if (lo > hi) return;
+                const unsigned b = (kNBuf4 == 2) ? (unsigned)(k & 1) : 0u;
+                const unsigned mb = mbar0 + 8u * b;
+                mbar_expect_tx(mb, buf_bytes);
+                tma_load_4d(window_base + b * buf_stride, map, 0, lo, (jlo + kk) * kChunk4 - kLead4, B.quad, mb);
+            };
+            if (kNBuf4 == 2 && tid == 0) issue(0);
             for (int k = 0; k < n_chunks; k++) {
                 const int kk = dir > 0 ? k : n_chunks - 1 - k;
                 const int j = jlo + kk;
                 const int lo = win_lo[kk], hi = win_hi[kk];
-                group_sync();  // everybody is done with the window
-                if (lo > hi) continue;
-                if (tid == 0) {
-                    mbar_expect_tx(mbar0, buf_bytes);
-                    tma_load_4d(window_base, map, 0, lo, j * kChunk4 - kLead4, B.quad, mbar0);
+                group_sync();  // everybody is done with the buffer that is loaded next
+                if (kNBuf4 == 2) {
+                    if (tid == 0 && k + 1 < n_chunks) issue(k + 1);
+                } else {
+                    if (tid == 0) issue(k);
                 }
-                mbar_wait(mbar0, phase0);
-                phase0 ^= 1u;
+                if (lo > hi) continue;
+                const unsigned b = (kNBuf4 == 2) ? (unsigned)(k & 1) : 0u;
+                if (b == 0) { mbar_wait(mbar0, phase0); phase0 ^= 1u; }
+                else { mbar_wait(mbar0 + 8u, phase1); phase1 ^= 1u; }
                 float lim = t_max;
                 if (k + 1 < n_chunks) {
                     const float edge = (float)(dir > 0 ? (j + 1) * kChunk4 : j * kChunk4) + 0.5f;
                     lim = fminf(t_max, (edge - op) * inv_dp);
                 }
-                const unsigned base = window_base - 16u * ((p.magic + (unsigned)(j * kChunk4 - kLead4)) * kRows4 + p.magic + (unsigned)lo);
+                const unsigned base = window_base + b * buf_stride - 16u * ((p.magic + (unsigned)(j * kChunk4 - kLead4)) * kRows4 + p.magic + (unsigned)lo);
 #pragma unroll 1
                 for (; t <= lim; t += kStep) {
                     const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
@@ -490,9 +514,9 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     P.lane_map = lane_map;
     const int threads = (kWindowWarps + nt) * 32;
 #ifdef ECC_CONFLICT_PROBE
-    const size_t smem = (size_t)kRows4 * kBoxW4 * 16 + 1024;
+    const size_t smem = (((size_t)kRows4 * kBoxW4 * 16 + 127) / 128 * 128) * kNBuf4 + 1024;
 #else
-    const size_t smem = (size_t)kRows4 * kBoxW4 * 16;
+    const size_t smem = (((size_t)kRows4 * kBoxW4 * 16 + 127) / 128 * 128) * kNBuf4;
 #endif
     const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;
     const CUtensorMap& mt = *(const CUtensorMap*)H.map_t;
