@@ -45,9 +45,16 @@ def main():
         assert pipe._team_key is not None, f"team transport not used: {pipe.team_error}"
         cost_host = np.zeros((n, n), np.float32)
         mean_host = ctx.team_evaluate(cost_host)
+        # batched mode: K matrix sets sharded over the ranks, the K means gathered (dtrs already on every rank)
+        K = 5
+        sets = np.stack([S["Ps"]] * K).reshape(K, n, 12).copy()
+        for k in range(1, K):
+            for c in range(4):  # set k: view k shifted by k pixels in u (row0 += k * row2, column-major 3x4)
+                sets[k, k, 0 + 3 * c] += float(k) * sets[k, k, 2 + 3 * c]
+        batch_means = pipe.evaluate_batch(sets)
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), dtrs=full.cpu().numpy(), cost=cost.cpu().numpy(), means=np.array(means),
-                 cost_host=cost_host, mean_host=mean_host)
+                 cost_host=cost_host, mean_host=mean_host, batch_means=batch_means, batch_sets=sets)
         dist.barrier()
     finally:
         dist.destroy_process_group()

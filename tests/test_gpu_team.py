@@ -127,6 +127,19 @@ def test_team_processes_over_cuda_ipc(tmp_path, engine):
         # host and device cost images of the same step are the same values
         assert np.array_equal(res[r]["cost_host"], res[r]["cost"])
         assert res[r]["mean_host"] == res[r]["means"][1]
+    # batched mode over the ranks = one batched launch on one GPU over the same dtrs
+    c = api.Context()
+    try:
+        c.set_interpolation(api.INTERP_TEXTURE)
+        c.set_epipolar_plane_step(S["dkappa"])
+        c.set_radon_intermediates(res[0]["dtrs"], S["n_u"], S["n_v"], True)
+        c.set_projection_matrices(S["Ps"])
+        want_batch = c.evaluate_batch(res[0]["batch_sets"])
+    finally:
+        c.close()
+    for r in range(world):
+        assert np.array_equal(res[r]["batch_means"], want_batch)
+    assert want_batch[1] > want_batch[0]
     # every rank holds the same bits
     assert np.array_equal(res[0]["dtrs"], res[1]["dtrs"])
     assert np.array_equal(res[0]["cost"], res[1]["cost"])
