@@ -158,6 +158,7 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
     L.vals_d = nullptr;
     L.image_d = nullptr;
     L.splits = 1;
+    L.mode_items = 0;
     L.defer_finalize = 0;
     L.partials_d = nullptr;
     return ECC_OK;
@@ -679,6 +680,7 @@ int ecc_evaluate_range(ecc_context* ctx, long long pair_begin, long long pair_en
     ctx->vals_cap = cap / sizeof(float);
     L.pair_begin = pair_begin;
     L.n_pairs = count;
+    L.mode_items = total;  // a range of the all-pairs job: every pair is computed as the whole job would compute it
     L.vals_d = ctx->vals_d;
     const bool img_dev = cost_image && is_device_pointer(cost_image);
     if (cost_image) {

@@ -219,6 +219,8 @@ struct PairLaunch {
     int is_derivative;
     int interp;
     int use_corr;  // correlation variant instead of the SSD
+    long long mode_items;  // > 0: choose warp-per-pair / CTA-per-pair and the split count as for a launch of this many pairs
+                           // (ranges of a larger job: a pair's fp32 sum must not depend on how the job was cut)
     int defer_finalize;  // split launches: leave the partial sums for launch_finalize_sum
     int splits;          // set by launch_pairs: CTAs per pair (CTA-per-pair launches)
     float* partials_d;   // [items][splits][3] when splits > 1

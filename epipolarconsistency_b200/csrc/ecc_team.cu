@@ -319,6 +319,7 @@ int ecc_team_evaluate(ecc_context* ctx, float* cost_image, double* mean)
     if (hi > lo) {
         L.pair_begin = lo;
         L.n_pairs = hi - lo;
+        L.mode_items = total;  // as the single-GPU job computes it (ecc_evaluate_range)
         L.vals_d = T.vals() + lo;
         L.image_d = nullptr;
         if ((rc = launch_pairs(ctx, L))) return rc;

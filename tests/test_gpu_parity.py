@@ -820,3 +820,28 @@ def test_update_and_evaluate_graph_replay_equals_plain_calls(ctx, scene):
         want_mean, _ = plain(0, P, idx0)
         assert mean == want_mean, step
     ctx.set_projection_matrices(scene["Ps"])
+
+
+def test_ranges_are_bit_identical_to_the_whole_job_in_warp_per_pair_mode(ctx):
+    """A job large enough for the warp-per-pair kernel (>= 148 * 64 pairs) cut into 8 equal-work ranges, some of them small
+    enough that a launch of their own would pick the CTA-per-pair kernel: every pair must still come out with the bits of
+    the whole job (the multi-GPU paths evaluate ranges; found at C3 scale: 9126 pairs differed in the last bit)."""
+    n, n_u, n_v, n_a, n_t = 140, 96, 80, 64, 64
+    rng = np.random.default_rng(17)
+    Ps = ol.circular_trajectory(n, 750, 1200, n_u, n_v, 360, 3.0)
+    dtrs = rng.standard_normal((n, n_t, n_a)).astype(np.float32)
+    ctx.set_interpolation(api.INTERP_TEXTURE)
+    ctx.set_object_radius(0.0)
+    ctx.set_epipolar_plane_step(float(np.deg2rad(0.5)))
+    ctx.set_projection_matrices(Ps)
+    ctx.set_radon_intermediates(dtrs, n_u, n_v, True)
+    total = n * (n - 1) // 2
+    assert total >= 148 * 64
+    whole = np.zeros((n, n), np.float32)
+    mean = ctx.evaluate(whole)
+    bounds = ctx.partition_pairs(8)
+    assert min(np.diff(bounds)) < 148 * 64
+    parts = np.zeros((n, n), np.float32)
+    s = sum(ctx.evaluate_range(int(a), int(b), parts) for a, b in zip(bounds[:-1], bounds[1:]))
+    assert np.array_equal(parts, whole)
+    assert s / total == mean
