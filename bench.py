@@ -57,35 +57,70 @@ def hbm_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled every 20 ms through
+    NVML (the nvidia-smi binary takes longer per call than an 8-GPU step lasts); nvidia-smi is the fall-back."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]  # nvmlClocksThrottleReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            if uuid is not None:
+                for name in ("GPU-" + str(uuid), str(uuid)):
+                    try:
+                        handle = pynvml.nvmlDeviceGetHandleByUUID(name.encode())
+                        break
+                    except Exception:
+                        handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = (pynvml, handle)
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            nv, h = self.nvml
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            power = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            return [sm, mx, power] + [bool(mask & b) for b in self.BITS]
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return None
+        r = [x.strip() for x in out.split(",")]
+        return [float(r[0]), float(r[1]), float(r[2])] + [x.lower().startswith("active") for x in r[3:7]]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                row = self.sample()
+                if row:
+                    self.rows.append(row)
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                if self.nvml is not None:
+                    self.nvml = None  # NVML call failed: try the binary from now on
+            self.stop_flag.wait(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(self.NAMES) if any(r[3 + k] for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ===========================================================================================================
@@ -162,7 +197,11 @@ def run_b200(args):
     for _ in range(max(args.warmup, 1)):
         mean = step(images, False)
     # ---- device-resident timing, with per-kernel event profile and clock sampling
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(local_rank).uuid
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     sampler.start()
     ctx.profile_reset()
     ctx.profile_enable(True)
