@@ -233,7 +233,7 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": "all-pairs ECC image-pairs/s, end of Radon intermediates included (C3)",
+            "metric": "all-pairs ECC image-pairs/s, end of Radon intermediates included (%s)" % args.workload.upper(),
             "value": n_pairs / (ms_step * 1e-3),
             "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
@@ -366,7 +366,7 @@ def run_reference(args):
     value = n_pairs / est
     line = {
         "impl": "reference",
-        "metric": "all-pairs ECC image-pairs/s, end of Radon intermediates included (C3)",
+        "metric": "all-pairs ECC image-pairs/s, end of Radon intermediates included (%s)" % args.workload.upper(),
         "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic: analytic 5-ellipsoid phantom, circular cone-beam trajectory, cosine weighted",
