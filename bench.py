@@ -161,7 +161,8 @@ def run_b200(args):
     ctx.set_object_radius(0.0)
     ctx.set_epipolar_plane_step(float(np.deg2rad(W["dkappa_deg"])))
 
-    radon_interp = {"hybrid": api.INTERP_HYBRID, "texture": api.INTERP_TEXTURE, "exact": api.INTERP_EXACT}[args.radon]
+    radon_interp = {"hybrid": api.INTERP_HYBRID, "hybrid-static": api.INTERP_HYBRID_STATIC, "texture": api.INTERP_TEXTURE,
+                    "exact": api.INTERP_EXACT}[args.radon]
 
     def step(src_images, want_cost_on_host):
         full = pipe.radon_allgather(src_images, n, n_a, n_t, interp=radon_interp)
@@ -244,6 +245,7 @@ def run_b200(args):
             "dtype": "f32",
             "data": "synthetic: analytic 5-ellipsoid phantom, circular cone-beam trajectory, cosine weighted; generated on device",
             "config": {"workload": W["name"], "projections": n, "pairs": n_pairs, "interpolation": {"hybrid": "texture-filter arithmetic (reference CUDA numerics); Radon samples split between the texture unit and a shared-memory path with the same 1.8 fixed-point weights",
+                                         "hybrid-static": "as hybrid, with a fixed (geometry-only) assignment of bins to the two paths: bit-reproducible, independent of batching and sharding",
                                          "texture": "texture unit (reference CUDA numerics, bit-identical Radon bins)",
                                          "exact": "Radon with exact fp32 weights; metric through the texture unit"}[args.radon],
                        "sharding": f"projections block-sharded over {world} GPU(s), pairs partitioned by equal kappa samples",
@@ -263,13 +265,13 @@ def run_b200(args):
                     "mean_ecc": mean_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": ("radon_hybrid4_kernel (bound by the two on-chip data pipes: texture + shared memory; " if args.radon == "hybrid" else "radon_kernel (texture-unit bound; ") + "algorithmic tap bytes vs HBM copy peak)",
+            "roofline": {"bound": "hbm", "kernel": ("radon_hybrid4_kernel (bound by the two on-chip data pipes: texture + shared memory; " if args.radon.startswith("hybrid") else "radon_kernel (texture-unit bound; ") + "algorithmic tap bytes vs HBM copy peak)",
                          "achieved": radon_gbs, "peak": peak, "unit": "GB/s", "frac": radon_gbs / peak, "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 128-projection launch of this command under
                          # ncu --set full (profiles/ncu_radon_hybrid4_bench_r01b.txt: 1133.5 + 318.9 MB), scaled to the
                          # projections per launch of this run; only known for the C3 image size and the hybrid engine
                          "traffic": (1.4524e9 / 128.0 * (hi - lo) * args.steps / max(radon_launches, 1)
-                                     if (args.radon == "hybrid" and args.workload == "c3") else None),
+                                     if (args.radon.startswith("hybrid") and args.workload == "c3") else None),
                          "samples_per_s": radon_gbs * 1e9 / 16.0,
                          "tex_rate_frac": (radon_gbs * 1e9 / 16.0) / 1.09e12,
                          # the bound that applies: the SM's two on-chip data pipes together, 64 B/clk (texture) + 128 B/clk
@@ -398,8 +400,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--exchange", default="team", choices=["team", "nccl"],
                     help="multi-GPU transport: team (peer stores from inside the kernels + flag barriers, default) or nccl (collectives after the kernels)")
-    ap.add_argument("--radon", default="hybrid", choices=["hybrid", "texture", "exact"],
-                    help="Radon engine: hybrid (texture unit + shared-memory path, default), texture (bit-identical to the reference kernel), exact")
+    ap.add_argument("--radon", default="hybrid-static", choices=["hybrid", "hybrid-static", "texture", "exact"],
+                    help="Radon engine: hybrid-static (texture unit + shared-memory path, fixed split: bit-reproducible and independent of the "
+                         "number of GPUs; default), hybrid (run-time work queue between the two paths), texture (bit-identical to the reference "
+                         "kernel), exact")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

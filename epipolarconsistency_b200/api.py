@@ -18,7 +18,7 @@ from . import _lib
 
 FILTER_DERIVATIVE, FILTER_RAMP, FILTER_NONE = 0, 1, 2
 POST_IDENTITY, POST_SQRT, POST_LOG = 0, 1, 2
-INTERP_TEXTURE, INTERP_EXACT, INTERP_HYBRID = 0, 1, 2
+INTERP_TEXTURE, INTERP_EXACT, INTERP_HYBRID, INTERP_HYBRID_STATIC = 0, 1, 2, 3
 
 
 class EccError(RuntimeError):

@@ -305,7 +305,8 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
         return fail(ctx, ECC_ERR_INVALID, "ecc_radon_compute: bad argument");
     if (filter != ECC_FILTER_DERIVATIVE && filter != ECC_FILTER_NONE && filter != ECC_FILTER_RAMP) return fail(ctx, ECC_ERR_INVALID, "bad filter");
     if (post < 0 || post > 2) return fail(ctx, ECC_ERR_INVALID, "bad post_process");
-    if (interp != ECC_INTERP_TEXTURE && interp != ECC_INTERP_EXACT && interp != ECC_INTERP_HYBRID) return fail(ctx, ECC_ERR_INVALID, "bad interp");
+    if (interp != ECC_INTERP_TEXTURE && interp != ECC_INTERP_EXACT && interp != ECC_INTERP_HYBRID && interp != ECC_INTERP_HYBRID_STATIC)
+        return fail(ctx, ECC_ERR_INVALID, "bad interp");
     if (n_images == 0) return ECC_OK;
     const bool in_dev = is_device_pointer(images), out_dev = is_device_pointer(dtrs_out);
     const size_t img_elems = (size_t)n_u * n_v, dtr_elems = (size_t)n_alpha * n_t;

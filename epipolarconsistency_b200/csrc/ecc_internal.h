@@ -52,6 +52,9 @@ struct Hybrid4Stage {
     size_t queue_words = 0;
     alignas(64) unsigned char map_n[128] = {};
     alignas(64) unsigned char map_t[128] = {};
+    // static split (ECC_INTERP_HYBRID_STATIC): items [0, split_items) of every quad take the window path; cached per geometry
+    int split_key[4] = {0, 0, 0, 0};  // n_u, n_v, n_alpha, n_t
+    int split_items = -1;
 };
 
 // Peer mirrors of an output buffer (multi-GPU team, ecc_team.cu): a kernel that stores out[k] also stores the same
@@ -255,7 +258,8 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
                         int n_v, int n_alpha, int n_t, int post, float* out_d);
 void free_hybrid(ecc_context* ctx);
 // ---- launchers (ecc_radon_hybrid4.cu) ----
-int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d);
+int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d,
+                         bool static_split = false);
 void free_hybrid4(ecc_context* ctx);
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
 

@@ -337,6 +337,18 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
     const bool deriv = (filter == ECC_FILTER_DERIVATIVE);  // ramp: plain line integrals first (RadonIntermediate.cu:160-168)
     // development knob: ECC_HYBRID_QUADS=0 keeps the one-image-per-item hybrid kernel for everything
     static const int use_quads = getenv("ECC_HYBRID_QUADS") ? atoi(getenv("ECC_HYBRID_QUADS")) : 1;
+    if (interp == ECC_INTERP_HYBRID_STATIC && deriv) {
+        // reproducible mode: every projection through the quad kernel with its static split (a remainder is padded to a
+        // quad), so that a projection's bins do not depend on the batch it arrives in
+        for (int first = 0; first < n_images; first += kPoolQuad) {
+            const int n = (n_images - first < kPoolQuad) ? n_images - first : kPoolQuad;
+            const int rc4 = radon_hybrid4_launch(ctx, images_d + (size_t)first * n_u * n_v, n, n_u, n_v, n_alpha, n_t, post,
+                                                 out_d + (size_t)first * n_t * n_alpha, true);
+            if (rc4) return rc4;
+        }
+        return ECC_OK;
+    }
+    if (interp == ECC_INTERP_HYBRID_STATIC) interp = ECC_INTERP_TEXTURE;  // other filters: the texture engine is reproducible
     if (interp == ECC_INTERP_HYBRID && deriv && use_quads && n_images >= 3) {
         // quads of projections through the quad kernel (it stages its images itself, four interleaved per texel); a
         // remainder of three is padded to a quad, one or two left-over images take the one-image hybrid kernel below

@@ -48,6 +48,8 @@ struct Hybrid4Params {
     unsigned* counters;
     unsigned* claim;
     unsigned magic;
+    int split_items;  // < 0: two-ended run-time queue; >= 0: items [0, split_items) of every quad -> window warps, the rest
+                      // -> texture warps (reproducible results: the path of a bin is a function of the geometry alone)
     float* out;
     Mirrors mir;  // multi-GPU team: every bin is also stored into the other ranks' buffers (NVLink peer stores)
 };
@@ -201,11 +203,20 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
         if (p.mode == 2) return;
         // ---------------- texture warps ----------------
         for (;;) {
-            int sub = 0;
-            if (lane == 0) sub = take_back(p.counters, p.claim, total_items);
-            sub = __shfl_sync(0xffffffffu, sub, 0);
-            if (sub < 0) break;
-            const int item = (int)total_items - 1 - sub / kSubTiles;
+            int sub = 0, item;
+            if (p.split_items >= 0) {  // static split: sub-tiles of the items [split_items, per_quad) of every quad, in order
+                const int tex_items = p.groups_a * p.groups_t - p.split_items;
+                if (lane == 0) sub = (int)atomicAdd(&p.counters[1], 1u);
+                sub = __shfl_sync(0xffffffffu, sub, 0);
+                if (sub >= p.n_quads * tex_items * kSubTiles) break;
+                const int x = sub / kSubTiles;
+                item = (x / tex_items) * (p.groups_a * p.groups_t) + p.split_items + x % tex_items;
+            } else {
+                if (lane == 0) sub = take_back(p.counters, p.claim, total_items);
+                sub = __shfl_sync(0xffffffffu, sub, 0);
+                if (sub < 0) break;
+                item = (int)total_items - 1 - sub / kSubTiles;
+            }
             const Item4 B = item_bins4(item, sub % kSubTiles, lane, p);
             if (B.ix >= p.n_alpha || B.iy >= p.n_t) continue;
             const BinLine L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
@@ -225,7 +236,13 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
     unsigned phase0 = 0, phase1 = 0;
     for (;;) {
         if (tid == 0) {
-            s_item = take_front(p.counters, p.claim, total_items);
+            if (p.split_items >= 0) {  // static split: items [0, split_items) of every quad, in order
+                const unsigned w = atomicAdd(&p.counters[0], 1u);
+                s_item = (p.split_items > 0 && w < (unsigned)(p.n_quads * p.split_items))
+                             ? (int)(w / p.split_items) * (p.groups_a * p.groups_t) + (int)(w % p.split_items) : -1;
+            } else {
+                s_item = take_front(p.counters, p.claim, total_items);
+            }
             s_jmin = INT_MAX;
             s_jmax = INT_MIN;
             s_fallback = 0;
@@ -408,6 +425,46 @@ __global__ void transpose4_kernel(const float4* __restrict__ padn, int n_u, int 
     }
 }
 
+// Bilinear samples per item of one projection (both lines of every bin): the weights for the static split.
+__global__ void item_samples_kernel(int n_u_i, int n_v_i, int n_alpha, int n_t, int groups_a, float* __restrict__ per_item)
+{
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y;
+    if (ix >= n_alpha || iy >= n_t) return;
+    const BinLine L = bin_line(ix, iy, n_alpha, n_t, (float)n_u_i, (float)n_v_i);
+    if (!L.valid) return;
+    const float count = 2.f * (floorf((L.t_max - L.t) / kStep) + 1.f);
+    atomicAdd(&per_item[(iy / kItemT) * groups_a + ix / kItemAngles], count);
+}
+
+// The window path's share of the samples when both pipes run side by side (B200, measured: window path 0.936, texture path
+// 0.677 projections per ms inside the combined kernel); development knob ECC_HYBRID4_SPLIT (per mille).
+int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int n_alpha, int n_t, int groups_a, int groups_t, int* split)
+{
+    if (H.split_items >= 0 && H.split_key[0] == n_u && H.split_key[1] == n_v && H.split_key[2] == n_alpha && H.split_key[3] == n_t) {
+        *split = H.split_items;
+        return ECC_OK;
+    }
+    const int per_quad = groups_a * groups_t;
+    float* counts_d = nullptr;
+    ECC_CUDA(ctx, cudaMalloc(&counts_d, sizeof(float) * per_quad));
+    ECC_CUDA(ctx, cudaMemsetAsync(counts_d, 0, sizeof(float) * per_quad, ctx->stream));
+    item_samples_kernel<<<dim3((n_alpha + 127) / 128, n_t), 128, 0, ctx->stream>>>(n_u, n_v, n_alpha, n_t, groups_a, counts_d);
+    std::vector<float> counts(per_quad);
+    ECC_CUDA(ctx, cudaMemcpyAsync(counts.data(), counts_d, sizeof(float) * per_quad, cudaMemcpyDeviceToHost, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(counts_d);
+    double total = 0;
+    for (float c : counts) total += c;
+    static const double share = env_int("ECC_HYBRID4_SPLIT", 580) / 1000.0;
+    double run = 0;
+    int m = 0;
+    while (m < per_quad && run + counts[m] * 0.5 < share * total) run += counts[m++];
+    H.split_items = m;
+    H.split_key[0] = n_u; H.split_key[1] = n_v; H.split_key[2] = n_alpha; H.split_key[3] = n_t;
+    *split = m;
+    return ECC_OK;
+}
+
 int encode_map4(ecc_context* ctx, CUtensorMap* map, float4* base, int pitch, int rows, int count)
 {
     EncodeTiledFn fn = encode_tiled_fn();
@@ -438,7 +495,8 @@ void free_hybrid4(ecc_context* ctx)
 }
 
 // n images (device, dense) -> their Radon intermediates; works on ceil(n/4) quads.
-int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d)
+int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d,
+                         bool static_split)
 {
     Hybrid4Stage& H = ctx->hybrid4;
     const int nq = (n + 3) / 4;
@@ -505,6 +563,11 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     P.claim = H.queue + 2;
     P.magic = 0x4B0000u;
     P.out = out_d;
+    P.split_items = -1;
+    if (static_split) {
+        const int rcs = static_split_items(ctx, H, n_u, n_v, n_alpha, n_t, P.groups_a, P.groups_t, &P.split_items);
+        if (rcs) return rcs;
+    }
     P.mir = team_mirrors(ctx, out_d);
     static const int nt = env_int("ECC_HYBRID4_NT", 8);
     static const int ctas = env_int("ECC_HYBRID4_CTAS", 2);

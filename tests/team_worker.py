@@ -33,7 +33,7 @@ def main():
         pipe = ShardedPipeline(ctx, rank, world, device=torch.device("cuda", dev_index), transport="team")
         ctx.set_interpolation(api.INTERP_TEXTURE)
         ctx.set_epipolar_plane_step(S["dkappa"])
-        interp = {"texture": api.INTERP_TEXTURE, "hybrid": api.INTERP_HYBRID}[engine]
+        interp = {"texture": api.INTERP_TEXTURE, "hybrid": api.INTERP_HYBRID, "hybrid-static": api.INTERP_HYBRID_STATIC}[engine]
         means = []
         for step in range(2):  # twice: the second step overwrites buffers the peers have read
             src = local if step == 0 else S["imgs"][lo:hi]  # device images, then host images

@@ -845,3 +845,29 @@ def test_ranges_are_bit_identical_to_the_whole_job_in_warp_per_pair_mode(ctx):
     s = sum(ctx.evaluate_range(int(a), int(b), parts) for a, b in zip(bounds[:-1], bounds[1:]))
     assert np.array_equal(parts, whole)
     assert s / total == mean
+
+
+# ---- hybrid engine with the static split: reproducible and independent of batching ------------------------------------
+@pytest.mark.parametrize("shape", [(160, 128, 192, 192), (203, 301, 100, 90), (97, 31, 8, 130), (640, 480, 256, 300)])
+def test_radon_hybrid_static_is_reproducible_and_batch_invariant(ctx, shape):
+    import torch
+    n_u, n_v, n_a, n_t = shape
+    rng = np.random.default_rng(23)
+    img = torch.from_numpy(rng.random((11, n_v, n_u), dtype=np.float32) * 10).cuda()
+    tex = ctx.radon_compute(img, n_a, n_t, interp=api.INTERP_TEXTURE)
+    a = ctx.radon_compute(img, n_a, n_t, interp=api.INTERP_HYBRID_STATIC)
+    b = ctx.radon_compute(img, n_a, n_t, interp=api.INTERP_HYBRID_STATIC)
+    assert torch.equal(a, b)  # run to run
+    parts = torch.cat([ctx.radon_compute(img[lo:hi], n_a, n_t, interp=api.INTERP_HYBRID_STATIC) for lo, hi in ((0, 1), (1, 3), (3, 6), (6, 11))])
+    assert torch.equal(a, parts)  # alone, in twos, threes, fives: the same bits as in one batch
+    host = ctx.radon_compute(img.cpu().numpy(), n_a, n_t, interp=api.INTERP_HYBRID_STATIC)
+    assert np.array_equal(host, a.cpu().numpy())  # host images (chunked uploads) as well
+    assert peak_err(a.cpu().numpy(), tex.cpu().numpy()) < RADON_TOL
+
+
+def test_radon_hybrid_static_other_filters_are_the_texture_engine(ctx, scene):
+    im = scene["imgs"][:3]
+    for filt in (api.FILTER_NONE, api.FILTER_RAMP):
+        a = ctx.radon_compute(im, 96, 80, filter=filt, interp=api.INTERP_HYBRID_STATIC)
+        b = ctx.radon_compute(im, 96, 80, filter=filt, interp=api.INTERP_TEXTURE)
+        assert np.array_equal(a, b)

@@ -94,7 +94,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("engine", ["texture", "hybrid"])
+@pytest.mark.parametrize("engine", ["texture", "hybrid", "hybrid-static"])
 def test_team_processes_over_cuda_ipc(tmp_path, engine):
     world = 2
     S = make_scene()
@@ -111,11 +111,11 @@ def test_team_processes_over_cuda_ipc(tmp_path, engine):
             out += "\n[timeout]"
         logs.append(out)
     assert all(p.returncode == 0 for p in procs), "\n----\n".join(logs)
-    interp = api.INTERP_TEXTURE if engine == "texture" else api.INTERP_HYBRID
+    interp = {"texture": api.INTERP_TEXTURE, "hybrid": api.INTERP_HYBRID, "hybrid-static": api.INTERP_HYBRID_STATIC}[engine]
     want_dtrs, want_cost, want_mean = single_gpu(S, interp)
     res = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
     for r in range(world):
-        if engine == "texture":  # deterministic engine: bit for bit
+        if engine != "hybrid":  # deterministic engines (texture unit only, or hybrid with the static split): bit for bit
             assert np.array_equal(res[r]["dtrs"], want_dtrs)
             assert np.array_equal(res[r]["cost"], want_cost)
             assert res[r]["means"][1] == want_mean
