@@ -314,10 +314,10 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
     // Host memory on either side: stream the batch through device staging in chunks.  Host images go through two
     // staging buffers on a copy stream of their own, so that the upload of chunk i+1 runs under the kernels of chunk i
     // (the first chunk is small: its upload is the only one that is exposed).
-    // Chunk schedule for host images: 8, 16, 32, 64, 64, ... -- the first upload is the only exposed one, every later
-    // upload (twice the images of the chunk computing above it) hides as long as the link delivers 16 GB/s, and the
-    // persistent kernel gets few, large launches.
-    const int chunk = n_images < 64 ? n_images : 64;
+    // Chunk schedule for host images: 8, 16, 32, 64, 128, 128, ... -- the first upload is the only exposed one, every later
+    // upload (at most twice the images of the chunk computing above it) hides as long as the link delivers 16 GB/s, and the
+    // persistent kernel gets few, large launches (1.2 GB of staging at the C3 image size).
+    const int chunk = n_images < 128 ? n_images : 128;
     const int first_chunk = (!in_dev && n_images > 8) ? 8 : chunk;
     int rc;
     if (!in_dev && (rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * img_elems * chunk * 2))) return rc;
