@@ -63,11 +63,12 @@ enum { ECC_POST_IDENTITY = 0, ECC_POST_SQRT = 1, ECC_POST_LOG = 2 };
  * ECC_INTERP_HYBRID (ecc_radon_compute only): the texture filter's arithmetic -- same sample positions, same 1.8
  *   fixed-point weights -- with part of the bins sampled from shared memory instead of through the texture unit, so
  *   that both sampling pipes of an SM work at once.  Bins differ from ECC_INTERP_TEXTURE by the rounding of the
- *   filter's internal sum only (measured <= 1e-5 of the peak, tolerance 1e-4).
+ *   filter's internal sum only (measured <= 3.2e-5 of the peak, tolerance 1e-4).
  * ECC_INTERP_HYBRID_STATIC (ecc_radon_compute only): the hybrid engine with a FIXED assignment of bins to the two
  *   sampling paths (a function of the bin geometry alone, chosen from the bins' sample counts) instead of the run-time
  *   work queue: results are bit-reproducible from run to run and independent of how a data set is batched or sharded
- *   over GPUs, for a few per cent of the speed (every projection goes through the quad kernel). */
+ *   over GPUs; the same speed at the C3 size, at most 3 % slower at the other sizes measured (every projection goes
+ *   through the quad kernel, remainders are padded to four). */
 enum { ECC_INTERP_TEXTURE = 0, ECC_INTERP_EXACT = 1, ECC_INTERP_HYBRID = 2, ECC_INTERP_HYBRID_STATIC = 3 };
 
 typedef struct ecc_context ecc_context;
