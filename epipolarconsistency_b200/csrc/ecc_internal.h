@@ -55,6 +55,8 @@ struct Hybrid4Stage {
     // static split (ECC_INTERP_HYBRID_STATIC): items [0, split_items) of every quad take the window path; cached per geometry
     int split_key[4] = {0, 0, 0, 0};  // n_u, n_v, n_alpha, n_t
     int split_items = -1;
+    int split_cfg = -1;               // window configuration the split was computed for
+    int map_cfg = -1;                 // window configuration the tensor maps are encoded for
 };
 
 // Peer mirrors of an output buffer (multi-GPU team, ecc_team.cu): a kernel that stores out[k] also stores the same

@@ -11,6 +11,7 @@
 //           interleaved copy (transposed for near-horizontal lines); the innermost box dimension is the image quad
 //           (16 bytes), so no start coordinate needs an alignment (cf. the 16-byte rule found in tools/tma_probe.cu).
 #include <climits>
+#include <cmath>
 #include <cstdlib>
 
 #include "ecc_radon_common.cuh"
@@ -19,23 +20,26 @@ namespace eccb200 {
 
 namespace {
 
-#ifndef ECC_CHUNK4
-#define ECC_CHUNK4 16
-#endif
-constexpr int kChunk4 = ECC_CHUNK4;     // pixels of the primary axis per chunk
-constexpr int kLead4 = 2;               // window columns in front of the chunk
-constexpr int kBoxW4 = ECC_CHUNK4 + 4;  // window columns [c0-2, c0+chunk+2)
-constexpr int kRows4 = 201;        // window rows; odd, so that neighbouring columns start one 16-byte bank group apart
-constexpr int kMaxChunks4 = 2048 / ECC_CHUNK4;   // primary axis up to 2048 px
-#ifndef ECC_NBUF4
-#define ECC_NBUF4 1
-#endif
-// Window buffers: 2 = the TMA load of the next chunk runs under the current chunk's samples.  Measured (C2 size): the
-// window warps wait for their TMA box a quarter of their time (ncu source view: 12 % of all samples on the mbarrier
-// try_wait), and two buffers make the window path ALONE 10 % faster (chunk 12: 0.906 against 1.011 ms/projection) -- but
-// the kernel as a whole much slower (0.86; chunk 8: 0.79 against 0.62): the second buffer comes out of the SM's L1
-// (carve-out 132 -> 164/228 KB), and the texture path lives on those 124 KB of L1TEX.  Hence one buffer.
-constexpr int kNBuf4 = ECC_NBUF4;
+constexpr int kLead4 = 2;  // window columns in front of the chunk
+
+// Window configuration (compile time): CHUNK pixels of the primary axis per chunk, window = [CHUNK + 4 columns][ROWS rows]
+// [4 images]; ROWS = 1 mod 8, so that neighbouring columns start one 16-byte bank group apart; NBUF window buffers
+// (2 = the TMA load of the next chunk runs under the current chunk's samples).
+//   Win4<16, 201, 1>  one 64 KB window: the general configuration (bands of up to 201 rows: t-bin spacing up to ~4.5 px).
+//   Win4<10, 137, 2>  two 30 KB windows in the SAME shared memory (the carve-out stays at 132 KB, the texture path keeps its
+//                     124 KB of L1TEX): for t-bin spacings up to ~2.35 px, where a band of 32 bins fits in 137 rows.
+// Measured (C2 size, ms/projection, both pipes): 16/201/1 0.616; with two buffers 12/201 0.859, 8/201 0.785 (the second
+// buffer comes out of L1TEX: carve-out 164-228 KB), 8/169 0.605, 8/161..145 0.588, 6/193 0.604, 10/137 0.578.
+template <int CHUNK, int ROWS, int NBUF>
+struct Win4 {
+    static constexpr int chunk = CHUNK, rows = ROWS, nbuf = NBUF, boxw = CHUNK + 4, max_chunks = 2048 / CHUNK;
+    static_assert(ROWS % 8 == 1, "window height: 1 mod 8 keeps neighbouring columns one bank group apart");
+    static_assert(max_chunks <= kWindowWarps * 32, "one window thread per chunk initialises the row tables");
+    static constexpr size_t buf_bytes = (size_t)ROWS * boxw * 16;
+    static constexpr size_t smem = (buf_bytes + 127) / 128 * 128 * NBUF;
+};
+typedef Win4<16, 201, 1> Win4General;
+typedef Win4<10, 137, 2> Win4Fine;
 
 struct Hybrid4Params {
     const cudaTextureObject_t* texs;  // one float4 texture per quad
@@ -110,6 +114,7 @@ __device__ __forceinline__ void bin_texture4(cudaTextureObject_t tex, const BinL
 // One sample position applied to the four images of the window: position -> cell and fractions -> weights once
 // (ecc_radon_hybrid.cu: sample_window has the derivation), four 16-byte loads, then per image
 // v00 + (w10 (v10-v00) + w01 (v01-v00) + w11 (v11-v00)) / 256.
+template <int kRows4>
 __device__ __forceinline__ void sample_window4(unsigned base, float pri, float sec, Sum4& acc)
 {
     const float Ps = fmaf(pri, 256.f, -127.5f);
@@ -126,11 +131,11 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
     asm volatile(
         "ld.shared.v4.f32 {%0, %1, %2, %3}, [%16];\n"
         "ld.shared.v4.f32 {%4, %5, %6, %7}, [%16+16];\n"
-        "ld.shared.v4.f32 {%8, %9, %10, %11}, [%16+3216];\n"
-        "ld.shared.v4.f32 {%12, %13, %14, %15}, [%16+3232];\n"
+        "ld.shared.v4.f32 {%8, %9, %10, %11}, [%16+%17];\n"
+        "ld.shared.v4.f32 {%12, %13, %14, %15}, [%16+%18];\n"
         : "=f"(v00.x), "=f"(v00.y), "=f"(v00.z), "=f"(v00.w), "=f"(v01.x), "=f"(v01.y), "=f"(v01.z), "=f"(v01.w), "=f"(v10.x),
           "=f"(v10.y), "=f"(v10.z), "=f"(v10.w), "=f"(v11.x), "=f"(v11.y), "=f"(v11.z), "=f"(v11.w)
-        : "r"(addr));
+        : "r"(addr), "n"(kRows4 * 16), "n"(kRows4 * 16 + 16));  // the next column: one window height further
     const unsigned w11 = (a * b + 128u) >> 8;
     const float f11 = __uint2float_rn(w11), f10 = __uint2float_rn(a - w11), f01 = __uint2float_rn(b - w11);
 #define ECC_ONE(c)                                                              \
@@ -143,7 +148,6 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
     ECC_ONE(x) ECC_ONE(y) ECC_ONE(z) ECC_ONE(w)
 #undef ECC_ONE
 }
-static_assert(kRows4 * 16 == 3216, "sample_window4 hard-codes the column pitch");
 
 struct Item4 {
     int quad, ix, iy;
@@ -177,11 +181,12 @@ __device__ __forceinline__ void store4(const Hybrid4Params& p, const Item4& B, c
         }
 }
 
-template <int MAXTHREADS, int MINBLOCKS>
+template <int MAXTHREADS, int MINBLOCKS, typename W>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
 radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_constant__ CUtensorMap map_t,
                      const __grid_constant__ Hybrid4Params p)
 {
+    constexpr int kChunk4 = W::chunk, kBoxW4 = W::boxw, kRows4 = W::rows, kMaxChunks4 = W::max_chunks, kNBuf4 = W::nbuf;
     extern __shared__ __align__(128) unsigned char window_raw[];
     __shared__ __align__(8) unsigned long long mbar_store[2];
     __shared__ int s_item, s_jmin, s_jmax, s_fallback;
@@ -372,8 +377,8 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
 #pragma unroll 1
                 for (; t <= lim; t += kStep) {
                     const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
-                    sample_window4(base, pri, sec, sum);
-                    sample_window4(base, pri + offp, sec + offs, sumo);
+                    sample_window4<kRows4>(base, pri, sec, sum);
+                    sample_window4<kRows4>(base, pri + offp, sec + offs, sumo);
                 }
             }
             result.x = (sum.x - sumo.x) * kStep;
@@ -438,9 +443,11 @@ __global__ void item_samples_kernel(int n_u_i, int n_v_i, int n_alpha, int n_t, 
 
 // The window path's share of the samples when both pipes run side by side (B200, measured: window path 0.936, texture path
 // 0.677 projections per ms inside the combined kernel); development knob ECC_HYBRID4_SPLIT (per mille).
-int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int n_alpha, int n_t, int groups_a, int groups_t, int* split)
+int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int n_alpha, int n_t, int groups_a, int groups_t, int cfg,
+                       int* split)
 {
-    if (H.split_items >= 0 && H.split_key[0] == n_u && H.split_key[1] == n_v && H.split_key[2] == n_alpha && H.split_key[3] == n_t) {
+    if (H.split_items >= 0 && H.split_key[0] == n_u && H.split_key[1] == n_v && H.split_key[2] == n_alpha && H.split_key[3] == n_t &&
+        H.split_cfg == cfg) {
         *split = H.split_items;
         return ECC_OK;
     }
@@ -455,23 +462,26 @@ int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int 
     cudaFree(counts_d);
     double total = 0;
     for (float c : counts) total += c;
-    static const double share = env_int("ECC_HYBRID4_SPLIT", 580) / 1000.0;
+    // general window configuration 580, fine configuration (faster window path) 605 per mille
+    static const int share_env = env_int("ECC_HYBRID4_SPLIT", 0);
+    const double share = (share_env > 0 ? share_env : (cfg == 1 ? 605 : 580)) / 1000.0;
     double run = 0;
     int m = 0;
     while (m < per_quad && run + counts[m] * 0.5 < share * total) run += counts[m++];
     H.split_items = m;
     H.split_key[0] = n_u; H.split_key[1] = n_v; H.split_key[2] = n_alpha; H.split_key[3] = n_t;
+    H.split_cfg = cfg;
     *split = m;
     return ECC_OK;
 }
 
-int encode_map4(ecc_context* ctx, CUtensorMap* map, float4* base, int pitch, int rows, int count)
+int encode_map4(ecc_context* ctx, CUtensorMap* map, float4* base, int pitch, int rows, int count, int box_rows, int box_w)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(ctx, ECC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     const cuuint64_t dims[4] = {4, (cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)count};
     const cuuint64_t strides[3] = {16, (cuuint64_t)pitch * 16u, (cuuint64_t)pitch * rows * 16u};
-    const cuuint32_t box[4] = {4, kRows4, kBoxW4, 1};
+    const cuuint32_t box[4] = {4, (cuuint32_t)box_rows, (cuuint32_t)box_w, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -492,6 +502,36 @@ void free_hybrid4(ecc_context* ctx)
     if (H.pad_t) cudaFree(H.pad_t);
     if (H.queue) cudaFree(H.queue);
     H = Hybrid4Stage();
+}
+
+template <typename W>
+int launch_window_config(ecc_context* ctx, Hybrid4Stage& H, const Hybrid4Params& P, int cfg, int threads, int ctas, int n_u, int n_v)
+{
+    if (H.map_cfg != cfg) {  // the TMA boxes have the window's shape
+        int rc = encode_map4(ctx, (CUtensorMap*)H.map_n, (float4*)H.pad_n, n_u + 1, n_v + 1, H.quads, W::rows, W::boxw);
+        if (rc) return rc;
+        rc = encode_map4(ctx, (CUtensorMap*)H.map_t, (float4*)H.pad_t, n_v + 1, n_u + 1, H.quads, W::rows, W::boxw);
+        if (rc) return rc;
+        H.map_cfg = cfg;
+    }
+#ifdef ECC_CONFLICT_PROBE
+    const size_t smem = W::smem + 1024;
+#else
+    const size_t smem = W::smem;
+#endif
+    const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;
+    const CUtensorMap& mt = *(const CUtensorMap*)H.map_t;
+    if (threads <= 512 && ctas <= 2) {
+        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid4_kernel<512, 2, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        radon_hybrid4_kernel<512, 2, W><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
+    } else if (threads <= 384 && ctas == 3) {
+        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid4_kernel<384, 3, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        radon_hybrid4_kernel<384, 3, W><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
+    } else {
+        return fail(ctx, ECC_ERR_INVALID, "ECC_HYBRID4_NT / ECC_HYBRID4_CTAS: unsupported combination");
+    }
+    ECC_CUDA(ctx, cudaGetLastError());
+    return ECC_OK;
 }
 
 // n images (device, dense) -> their Radon intermediates; works on ceil(n/4) quads.
@@ -529,10 +569,7 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
         }
         ECC_CUDA(ctx, cudaMalloc(&H.tex_d, sizeof(cudaTextureObject_t) * quads));
         ECC_CUDA(ctx, cudaMemcpyAsync(H.tex_d, H.tex_h.data(), sizeof(cudaTextureObject_t) * quads, cudaMemcpyHostToDevice, ctx->stream));
-        int rc = encode_map4(ctx, (CUtensorMap*)H.map_n, (float4*)H.pad_n, n_u + 1, n_v + 1, quads);
-        if (rc) return rc;
-        rc = encode_map4(ctx, (CUtensorMap*)H.map_t, (float4*)H.pad_t, n_v + 1, n_u + 1, quads);
-        if (rc) return rc;
+        H.map_cfg = -1;  // the tensor maps are encoded at the launch, for the window configuration chosen there
     }
     interleave4_kernel<<<dim3((n_u + 1 + 127) / 128, n_v + 1, nq), 128, 0, ctx->stream>>>(images_d, n, n_u, n_v, (float4*)H.lin, (float4*)H.pad_n);
     transpose4_kernel<<<dim3((n_u + 1 + 15) / 16, (n_v + 1 + 15) / 16, nq), dim3(16, 16), 0, ctx->stream>>>((const float4*)H.pad_n, n_u, n_v, (float4*)H.pad_t);
@@ -563,9 +600,13 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     P.claim = H.queue + 2;
     P.magic = 0x4B0000u;
     P.out = out_d;
+    // window configuration: a band of 32 t bins must fit the window height (plus the spread of the item's 8 angles)
+    static const int cfg_env = env_int("ECC_HYBRID4_CFG", -1);
+    const double t_spacing = std::sqrt((double)n_u * n_u + (double)n_v * n_v) / n_t;
+    const int cfg = cfg_env >= 0 ? cfg_env : (t_spacing <= 2.35 ? 1 : 0);
     P.split_items = -1;
     if (static_split) {
-        const int rcs = static_split_items(ctx, H, n_u, n_v, n_alpha, n_t, P.groups_a, P.groups_t, &P.split_items);
+        const int rcs = static_split_items(ctx, H, n_u, n_v, n_alpha, n_t, P.groups_a, P.groups_t, cfg, &P.split_items);
         if (rcs) return rcs;
     }
     P.mir = team_mirrors(ctx, out_d);
@@ -576,27 +617,11 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     static const int lane_map = env_int("ECC_HYBRID4_LANEMAP", 2);
     P.lane_map = lane_map;
     const int threads = (kWindowWarps + nt) * 32;
-#ifdef ECC_CONFLICT_PROBE
-    const size_t smem = (((size_t)kRows4 * kBoxW4 * 16 + 127) / 128 * 128) * kNBuf4 + 1024;
-#else
-    const size_t smem = (((size_t)kRows4 * kBoxW4 * 16 + 127) / 128 * 128) * kNBuf4;
-#endif
-    const CUtensorMap& mn = *(const CUtensorMap*)H.map_n;
-    const CUtensorMap& mt = *(const CUtensorMap*)H.map_t;
     const int slot = prof_begin(ctx, FAM_RADON);
-    if (threads <= 512 && ctas <= 2) {
-        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid4_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        radon_hybrid4_kernel<512, 2><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
-    } else if (threads <= 384 && ctas == 3) {
-        ECC_CUDA(ctx, cudaFuncSetAttribute(radon_hybrid4_kernel<384, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        radon_hybrid4_kernel<384, 3><<<ctx->sm_count * ctas, threads, smem, ctx->stream>>>(mn, mt, P);
-    } else {
-        prof_end(ctx, slot);
-        return fail(ctx, ECC_ERR_INVALID, "ECC_HYBRID4_NT / ECC_HYBRID4_CTAS: unsupported combination");
-    }
+    const int rcl = cfg == 1 ? launch_window_config<Win4Fine>(ctx, H, P, cfg, threads, ctas, n_u, n_v)
+                             : launch_window_config<Win4General>(ctx, H, P, cfg, threads, ctas, n_u, n_v);
     prof_end(ctx, slot);
-    ECC_CUDA(ctx, cudaGetLastError());
-    return ECC_OK;
+    return rcl;
 }
 
 }  // namespace eccb200
