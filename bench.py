@@ -268,10 +268,10 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": ("radon_hybrid4_kernel (bound by the two on-chip data pipes: texture + shared memory; " if args.radon.startswith("hybrid") else "radon_kernel (texture-unit bound; ") + "algorithmic tap bytes vs HBM copy peak)",
                          "achieved": radon_gbs, "peak": peak, "unit": "GB/s", "frac": radon_gbs / peak, "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 128-projection launch of this command under
-                         # ncu --set full (static split: profiles/ncu_radon_hybrid4_static_bench_r01.txt, 1987.0 + 330.0 MB;
+                         # ncu --set full (static split: profiles/ncu_radon_hybrid4_fine_bench_r01.txt, 1999.0 + 330.6 MB;
                          # run-time queue: profiles/ncu_radon_hybrid4_bench_r01b.txt, 1133.5 + 318.9 MB), scaled to the
                          # projections per launch of this run; only known for the C3 image size and the hybrid engines
-                         "traffic": ((2.3169e9 if args.radon == "hybrid-static" else 1.4524e9) / 128.0 * (hi - lo) * args.steps / max(radon_launches, 1)
+                         "traffic": ((2.3295e9 if args.radon == "hybrid-static" else 1.4524e9) / 128.0 * (hi - lo) * args.steps / max(radon_launches, 1)
                                      if (args.radon.startswith("hybrid") and args.workload == "c3") else None),
                          "samples_per_s": radon_gbs * 1e9 / 16.0,
                          "tex_rate_frac": (radon_gbs * 1e9 / 16.0) / 1.09e12,
@@ -282,7 +282,7 @@ def run_b200(args):
                          "note": "16 B per bilinear sample x %.4g samples per projection, on-chip traffic (hence frac > 1 against the "
                                  "HBM copy peak; DRAM moves 11-18 MB per projection); tex_rate_frac = samples/s over the measured tex2D rate of "
                                  "this GPU (1.09e12/s at 1965 MHz, profiles/tex_probe_r01.txt); ncu of a launch of this command: texture "
-                                 "data pipe 98 %% of peak, shared-memory pipe 82 %%, issue slots 61 %% (profiles/ncu_radon_hybrid4_static_bench_r01.txt)" % samples_per_proj},
+                                 "data pipe 98 %% of peak, shared-memory pipe 91 %%, issue slots 70 %% (profiles/ncu_radon_hybrid4_fine_bench_r01.txt)" % samples_per_proj},
             "roofline_pairs": {"bound": "hbm", "kernel": "pairs_kernel (L1/texture gather bound)", "achieved": pairs_gbs, "peak": peak,
                                "unit": "GB/s", "frac": pairs_gbs / peak, "kappa_samples": float(counts.sum()),
                                # random-gather rates of this pool's B200 (tools/gather_probe.cu, profiles/gather_probe_r01.txt):
