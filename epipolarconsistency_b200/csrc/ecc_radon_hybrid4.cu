@@ -27,7 +27,7 @@ constexpr int kLead4 = 2;  // window columns in front of the chunk
 // (2 = the TMA load of the next chunk runs under the current chunk's samples).
 //   Win4<16, 201, 1>  one 64 KB window: the general configuration (bands of up to 201 rows: t-bin spacing up to ~4.5 px).
 //   Win4<10, 137, 2>  two 30 KB windows in the SAME shared memory (the carve-out stays at 132 KB, the texture path keeps its
-//                     124 KB of L1TEX): for t-bin spacings up to ~2.35 px, where a band of 32 bins fits in 137 rows.
+//                     124 KB of L1TEX): for t-bin spacings up to 2.1 px (measured at 2.04 and 1.04), where a band of 32 bins fits in 137 rows.
 // Measured (C2 size, ms/projection, both pipes): 16/201/1 0.616; with two buffers 12/201 0.859, 8/201 0.785 (the second
 // buffer comes out of L1TEX: carve-out 164-228 KB), 8/169 0.605, 8/161..145 0.588, 6/193 0.604, 10/137 0.578.
 template <int CHUNK, int ROWS, int NBUF>
@@ -603,7 +603,7 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     // window configuration: a band of 32 t bins must fit the window height (plus the spread of the item's 8 angles)
     static const int cfg_env = env_int("ECC_HYBRID4_CFG", -1);
     const double t_spacing = std::sqrt((double)n_u * n_u + (double)n_v * n_v) / n_t;
-    const int cfg = cfg_env >= 0 ? cfg_env : (t_spacing <= 2.35 ? 1 : 0);
+    const int cfg = cfg_env >= 0 ? cfg_env : (t_spacing <= 2.1 ? 1 : 0);
     P.split_items = -1;
     if (static_split) {
         const int rcs = static_split_items(ctx, H, n_u, n_v, n_alpha, n_t, P.groups_a, P.groups_t, cfg, &P.split_items);
