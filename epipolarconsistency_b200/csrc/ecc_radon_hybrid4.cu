@@ -39,7 +39,11 @@ struct Win4 {
     static constexpr size_t smem = (buf_bytes + 127) / 128 * 128 * NBUF;
 };
 typedef Win4<16, 201, 1> Win4General;
-typedef Win4<10, 137, 2> Win4Fine;
+#ifndef ECC_FINE_CHUNK  // development knobs: -DECC_FINE_CHUNK=.. -DECC_FINE_ROWS=..
+#define ECC_FINE_CHUNK 10
+#define ECC_FINE_ROWS 137
+#endif
+typedef Win4<ECC_FINE_CHUNK, ECC_FINE_ROWS, 2> Win4Fine;
 
 struct Hybrid4Params {
     const cudaTextureObject_t* texs;  // one float4 texture per quad
