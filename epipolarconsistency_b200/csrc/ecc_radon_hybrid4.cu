@@ -30,20 +30,26 @@ constexpr int kLead4 = 2;  // window columns in front of the chunk
 //                     124 KB of L1TEX): for t-bin spacings up to 2.1 px (measured at 2.04 and 1.04), where a band of 32 bins fits in 137 rows.
 // Measured (C2 size, ms/projection, both pipes): 16/201/1 0.616; with two buffers 12/201 0.859, 8/201 0.785 (the second
 // buffer comes out of L1TEX: carve-out 164-228 KB), 8/169 0.605, 8/161..145 0.588, 6/193 0.604, 10/137 0.578.
-template <int CHUNK, int ROWS, int NBUF>
+template <int CHUNK, int ROWS, int NBUF, bool CHUNK_FALLBACK = false>
 struct Win4 {
     static constexpr int chunk = CHUNK, rows = ROWS, nbuf = NBUF, boxw = CHUNK + 4, max_chunks = 2048 / CHUNK;
+    // a chunk whose band of rows does not fit the window: false = the whole item goes through the texture unit,
+    // true = only that chunk's samples do (fetched by the window warps themselves, in sample order)
+    static constexpr bool chunk_fallback = CHUNK_FALLBACK;
     static_assert(ROWS % 8 == 1, "window height: 1 mod 8 keeps neighbouring columns one bank group apart");
     static_assert(max_chunks <= kWindowWarps * 32, "one window thread per chunk initialises the row tables");
     static constexpr size_t buf_bytes = (size_t)ROWS * boxw * 16;
     static constexpr size_t smem = (buf_bytes + 127) / 128 * 128 * NBUF;
 };
 typedef Win4<16, 201, 1> Win4General;
-#ifndef ECC_FINE_CHUNK  // development knobs: -DECC_FINE_CHUNK=.. -DECC_FINE_ROWS=..
+#ifndef ECC_FINE_CHUNK  // development knobs: -DECC_FINE_CHUNK=.. -DECC_FINE_ROWS=.. -DECC_FINE_CF=0|1
 #define ECC_FINE_CHUNK 10
 #define ECC_FINE_ROWS 137
 #endif
-typedef Win4<ECC_FINE_CHUNK, ECC_FINE_ROWS, 2> Win4Fine;
+#ifndef ECC_FINE_CF
+#define ECC_FINE_CF 0
+#endif
+typedef Win4<ECC_FINE_CHUNK, ECC_FINE_ROWS, 2, (ECC_FINE_CF != 0)> Win4Fine;
 
 struct Hybrid4Params {
     const cudaTextureObject_t* texs;  // one float4 texture per quad
@@ -335,7 +341,7 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
         }
         group_sync();
         if (n_chunks > 0 && !too_long && tid < n_chunks) {
-            if (win_lo[tid] <= win_hi[tid] && win_hi[tid] - win_lo[tid] + 1 > kRows4) s_fallback = 1;
+            if (!W::chunk_fallback && win_lo[tid] <= win_hi[tid] && win_hi[tid] - win_lo[tid] + 1 > kRows4) s_fallback = 1;
         }
         if (tid == 0 && too_long) s_fallback = 1;
         group_sync();
@@ -352,6 +358,7 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
                 const int kk = dir > 0 ? k : n_chunks - 1 - k;
                 const int lo = win_lo[kk], hi = win_hi[kk];
                 if (lo > hi) return;
+                if (W::chunk_fallback && hi - lo + 1 > kRows4) return;  // sampled through the texture unit instead
                 const unsigned b = (kNBuf4 == 2) ? (unsigned)(k & 1) : 0u;
                 const unsigned mb = mbar0 + 8u * b;
                 mbar_expect_tx(mb, buf_bytes);
@@ -369,14 +376,38 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
                     if (tid == 0) issue(k);
                 }
                 if (lo > hi) continue;
-                const unsigned b = (kNBuf4 == 2) ? (unsigned)(k & 1) : 0u;
-                if (b == 0) { mbar_wait(mbar0, phase0); phase0 ^= 1u; }
-                else { mbar_wait(mbar0 + 8u, phase1); phase1 ^= 1u; }
                 float lim = t_max;
                 if (k + 1 < n_chunks) {
                     const float edge = (float)(dir > 0 ? (j + 1) * kChunk4 : j * kChunk4) + 0.5f;
                     lim = fminf(t_max, (edge - op) * inv_dp);
                 }
+                if (W::chunk_fallback && hi - lo + 1 > kRows4) {
+                    // this chunk's band does not fit the window: its samples through the texture unit, same positions, same
+                    // order of additions; two samples (four fetches) in flight
+                    const cudaTextureObject_t tex = p.texs[B.quad];
+#pragma unroll 1
+                    while (t <= lim) {
+                        const float t1 = t + kStep;
+                        const bool two = t1 <= lim;
+                        const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
+                        const float pri1 = fmaf(t1, dp, op), sec1 = fmaf(t1, ds, os);
+                        const float4 a0 = tex2D<float4>(tex, vertical ? sec : pri, vertical ? pri : sec);
+                        const float4 b0 = tex2D<float4>(tex, vertical ? sec + offs : pri + offp, vertical ? pri + offp : sec + offs);
+                        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
+                        if (two) {
+                            a1 = tex2D<float4>(tex, vertical ? sec1 : pri1, vertical ? pri1 : sec1);
+                            b1 = tex2D<float4>(tex, vertical ? sec1 + offs : pri1 + offp, vertical ? pri1 + offp : sec1 + offs);
+                        }
+                        add4(sum, a0);
+                        add4(sumo, b0);
+                        if (two) { add4(sum, a1); add4(sumo, b1); }
+                        t = two ? t1 + kStep : t1;
+                    }
+                    continue;
+                }
+                const unsigned b = (kNBuf4 == 2) ? (unsigned)(k & 1) : 0u;
+                if (b == 0) { mbar_wait(mbar0, phase0); phase0 ^= 1u; }
+                else { mbar_wait(mbar0 + 8u, phase1); phase1 ^= 1u; }
                 const unsigned base = window_base + b * buf_stride - 16u * ((p.magic + (unsigned)(j * kChunk4 - kLead4)) * kRows4 + p.magic + (unsigned)lo);
 #pragma unroll 1
                 for (; t <= lim; t += kStep) {
