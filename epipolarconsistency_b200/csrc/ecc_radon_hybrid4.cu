@@ -7,9 +7,15 @@
 // (~14 instructions per sample), and the texture path fetches float4 texels (one fetch = four images, same
 // channel-sample rate of the texture unit, a quarter of the instructions).  Queue, chunking, row windows, fall-backs and
 // the sample set are those of ecc_radon_hybrid.cu; per image the arithmetic is identical, so are the results.
-//   window: [kBoxW columns][kRows rows][4 images] floats, fetched by ONE 4-D TMA box per chunk from an edge-replicated
+//   window: [chunk + 4 columns][rows][4 images] floats, fetched by ONE 4-D TMA box per chunk from an edge-replicated
 //           interleaved copy (transposed for near-horizontal lines); the innermost box dimension is the image quad
 //           (16 bytes), so no start coordinate needs an alignment (cf. the 16-byte rule found in tools/tma_probe.cu).
+//           The window's shape is a template parameter (Win4 below): one 64 KB window in general, two 30 KB windows --
+//           the next chunk's TMA load under the current chunk's samples -- where the t-bin spacing lets a band of 32
+//           bins fit 137 rows; never more shared memory than that, because the texture path lives on the rest as L1.
+//   queue:  two-ended at run time (ECC_INTERP_HYBRID), or a static split of every quad's items between the two paths,
+//           58-60 % of the samples to the window path (ECC_INTERP_HYBRID_STATIC: reproducible, batch-invariant).
+//   several GPUs: every finished bin is also stored into the other ranks' buffers (Mirrors, ecc_team.cu).
 #include <climits>
 #include <cmath>
 #include <cstdlib>

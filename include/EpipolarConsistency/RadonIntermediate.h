@@ -146,7 +146,7 @@ public:
     const NRRD::ImageView<float>& data() const { return m_raw_cpu; }
 
     /// Engine used by compute(): ECC_INTERP_TEXTURE (bit-identical to the reference's kernel, default),
-    /// ECC_INTERP_HYBRID_STATIC (same arithmetic through both sampling pipes, 2.4x faster, within 5e-5 of the peak,
+    /// ECC_INTERP_HYBRID_STATIC (same arithmetic through both sampling pipes, 2.5x faster, within 5e-5 of the peak,
     /// reproducible), ECC_INTERP_HYBRID (run-time work queue) or ECC_INTERP_EXACT (fp32 weights).
     void setInterpolation(int interp) { m_interp = interp; }
 
