@@ -207,7 +207,7 @@ def run_b200(args):
     ctx.profile_reset()
     ctx.profile_enable(True)
     ms_total, mean = timed(lambda: step(images, False), args.steps)
-    prof = {fam: ctx.profile_get(fam) for fam in ("radon", "pairs", "geometry", "reduce")}
+    prof = {fam: ctx.profile_get(fam) for fam in ("radon", "pairs", "geometry", "reduce", "stage")}
     ctx.profile_enable(False)
     clocks = sampler.summary()
     # ---- end to end through the C ABI with host buffers

@@ -1145,7 +1145,7 @@ int ecc_profile_get(ecc_context* ctx, const char* family, double* total_ms, long
 {
     if (!ctx || !family) return ECC_ERR_INVALID;
     Guard g(ctx);
-    static const char* names[FAM_COUNT] = {"radon", "pairs", "geometry", "reduce", "synth"};
+    static const char* names[FAM_COUNT] = {"radon", "pairs", "geometry", "reduce", "synth", "stage"};
     prof_collect(ctx);
     for (int f = 0; f < FAM_COUNT; f++)
         if (std::strcmp(family, names[f]) == 0) {

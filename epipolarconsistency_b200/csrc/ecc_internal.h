@@ -11,7 +11,7 @@
 namespace eccb200 {
 
 // Kernel families for the per-launch event profile.
-enum Family { FAM_RADON = 0, FAM_PAIRS, FAM_GEOMETRY, FAM_REDUCE, FAM_SYNTH, FAM_COUNT };
+enum Family { FAM_RADON = 0, FAM_PAIRS, FAM_GEOMETRY, FAM_REDUCE, FAM_SYNTH, FAM_STAGE, FAM_COUNT };
 
 struct ProfileSlot {
     cudaEvent_t start, stop;
@@ -178,8 +178,8 @@ struct ecc_context {
     // ---- profiling ----
     bool profiling = false;
     std::vector<eccb200::ProfileSlot> prof_slots;
-    double prof_ms[eccb200::FAM_COUNT] = {0, 0, 0, 0, 0};
-    long long prof_launches[eccb200::FAM_COUNT] = {0, 0, 0, 0, 0};
+    double prof_ms[eccb200::FAM_COUNT] = {};
+    long long prof_launches[eccb200::FAM_COUNT] = {};
 };
 
 namespace eccb200 {

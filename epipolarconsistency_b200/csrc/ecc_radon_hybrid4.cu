@@ -612,8 +612,14 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
         ECC_CUDA(ctx, cudaMemcpyAsync(H.tex_d, H.tex_h.data(), sizeof(cudaTextureObject_t) * quads, cudaMemcpyHostToDevice, ctx->stream));
         H.map_cfg = -1;  // the tensor maps are encoded at the launch, for the window configuration chosen there
     }
-    interleave4_kernel<<<dim3((n_u + 1 + 127) / 128, n_v + 1, nq), 128, 0, ctx->stream>>>(images_d, n, n_u, n_v, (float4*)H.lin, (float4*)H.pad_n);
-    transpose4_kernel<<<dim3((n_u + 1 + 15) / 16, (n_v + 1 + 15) / 16, nq), dim3(16, 16), 0, ctx->stream>>>((const float4*)H.pad_n, n_u, n_v, (float4*)H.pad_t);
+    {   // image staging: two kernels (+ the array copies below), profile family "stage"
+        const int s1 = prof_begin(ctx, FAM_STAGE);
+        interleave4_kernel<<<dim3((n_u + 1 + 127) / 128, n_v + 1, nq), 128, 0, ctx->stream>>>(images_d, n, n_u, n_v, (float4*)H.lin, (float4*)H.pad_n);
+        prof_end(ctx, s1);
+        const int s2 = prof_begin(ctx, FAM_STAGE);
+        transpose4_kernel<<<dim3((n_u + 1 + 15) / 16, (n_v + 1 + 15) / 16, nq), dim3(16, 16), 0, ctx->stream>>>((const float4*)H.pad_n, n_u, n_v, (float4*)H.pad_t);
+        prof_end(ctx, s2);
+    }
     for (int q = 0; q < nq; q++)
         ECC_CUDA(ctx, cudaMemcpy2DToArrayAsync(H.arrays[q], 0, 0, (const float4*)H.lin + (size_t)q * n_u * n_v, sizeof(float4) * n_u,
                                                sizeof(float4) * n_u, n_v, cudaMemcpyDeviceToDevice, ctx->stream));
