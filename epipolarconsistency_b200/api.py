@@ -25,17 +25,26 @@ class EccError(RuntimeError):
     pass
 
 
-def _ptr(x):
-    """Raw address of a numpy array / torch tensor (host or device), or None."""
+_F32, _F64, _I32, _I64, _U8 = "float32", "float64", "int32", "int64", "uint8"
+
+
+def _ptr(x, dtype=None):
+    """Raw address of a numpy array / torch tensor (host or device), or None.  dtype: the element type the C ABI reads or
+    writes through this pointer ("float32" images / dtrs / outputs, "float64" matrices, "int32" pair lists ...); a buffer
+    of another type would be reinterpreted silently, so it is refused."""
     if x is None:
         return None
     if isinstance(x, np.ndarray):
         if not x.flags["C_CONTIGUOUS"]:
             raise ValueError("array must be C-contiguous")
+        if dtype is not None and x.dtype != np.dtype(dtype):
+            raise TypeError(f"buffer of dtype {x.dtype} passed where the C ABI expects {dtype}")
         return x.ctypes.data
     if hasattr(x, "data_ptr"):
         if not x.is_contiguous():
             raise ValueError("tensor must be contiguous")
+        if dtype is not None and str(x.dtype).replace("torch.", "") != dtype:
+            raise TypeError(f"tensor of dtype {x.dtype} passed where the C ABI expects {dtype}")
         return x.data_ptr()
     raise TypeError(f"unsupported buffer type {type(x)}")
 
@@ -116,7 +125,7 @@ class Context:
         if Ps is not None:
             Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
             assert Ps.shape[0] == n
-        self._check(self.lib.ecc_preprocess(self.h, _ptr(images), n, n_u, n_v, C.addressof(params), _ptr(Ps)))
+        self._check(self.lib.ecc_preprocess(self.h, _ptr(images, _F32), n, n_u, n_v, C.addressof(params), _ptr(Ps, _F64)))
         return images
 
     # -- Radon
@@ -131,8 +140,8 @@ class Context:
             else:
                 import torch
                 out = torch.empty((n, n_t, n_alpha), dtype=torch.float32, device=images.device)
-        self._check(self.lib.ecc_radon_compute(self.h, _ptr(images), n, n_u, n_v, n_alpha, n_t, filter, post,
-                                               interp, _ptr(out)))
+        self._check(self.lib.ecc_radon_compute(self.h, _ptr(images, _F32), n, n_u, n_v, n_alpha, n_t, filter, post,
+                                               interp, _ptr(out, _F32)))
         return out
 
     def radon_num_samples(self, n_u, n_v, n_alpha, n_t, filter=FILTER_DERIVATIVE):
@@ -152,21 +161,21 @@ class Context:
         sa, st = self.radon_bin_sizes(n_u, n_v, n_alpha, n_t)
         self._dtrs_keepalive = dtrs  # borrowed by the library when on the device
         self._check(self.lib.ecc_set_radon_intermediates(
-            self.h, _ptr(dtrs), n, n_alpha, n_t, sa if step_alpha is None else step_alpha,
+            self.h, _ptr(dtrs, _F32), n, n_alpha, n_t, sa if step_alpha is None else step_alpha,
             st if step_t is None else step_t, n_u, n_v, int(is_derivative)))
 
     def set_projection_matrices(self, Ps):
         Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
-        self._check(self.lib.ecc_set_projection_matrices(self.h, _ptr(Ps), Ps.shape[0]))
+        self._check(self.lib.ecc_set_projection_matrices(self.h, _ptr(Ps, _F64), Ps.shape[0]))
 
     def update_projection_matrix(self, index, P):
         P = np.ascontiguousarray(P, np.float64).reshape(12)
-        self._check(self.lib.ecc_update_projection_matrix(self.h, int(index), _ptr(P)))
+        self._check(self.lib.ecc_update_projection_matrix(self.h, int(index), _ptr(P, _F64)))
 
     def get_derived_views(self, n_views):
         A = np.zeros((n_views, 12), np.float32)
         Cs = np.zeros((n_views, 4), np.float32)
-        self._check(self.lib.ecc_get_derived_views(self.h, _ptr(A), _ptr(Cs)))
+        self._check(self.lib.ecc_get_derived_views(self.h, _ptr(A, _F32), _ptr(Cs, _F32)))
         return A, Cs
 
     def set_object_radius(self, r):
@@ -189,19 +198,19 @@ class Context:
     # -- evaluation
     def evaluate(self, cost_image=None, want_mean=True):
         m = C.c_double()
-        self._check(self.lib.ecc_evaluate(self.h, _ptr(cost_image), C.byref(m) if want_mean else None))
+        self._check(self.lib.ecc_evaluate(self.h, _ptr(cost_image, _F32), C.byref(m) if want_mean else None))
         return m.value if want_mean else None
 
     def evaluate_range(self, begin, end, cost_image=None, want_sum=True):
         s = C.c_double()
-        self._check(self.lib.ecc_evaluate_range(self.h, int(begin), int(end), _ptr(cost_image),
+        self._check(self.lib.ecc_evaluate_range(self.h, int(begin), int(end), _ptr(cost_image, _F32),
                                                 C.byref(s) if want_sum else None))
         return s.value if want_sum else None
 
     def evaluate_indices(self, idx4, out=None, want_mean=True):
         n_pairs = idx4.shape[0]
         m = C.c_double()
-        self._check(self.lib.ecc_evaluate_indices(self.h, _ptr(idx4), n_pairs, _ptr(out),
+        self._check(self.lib.ecc_evaluate_indices(self.h, _ptr(idx4, _I32), n_pairs, _ptr(out, _F32),
                                                   C.byref(m) if want_mean else None))
         return m.value if want_mean else None
 
@@ -210,7 +219,7 @@ class Context:
         call with the same index / list / settings on.  Returns the mean."""
         P = np.ascontiguousarray(P, np.float64).reshape(12)
         m = C.c_double()
-        self._check(self.lib.ecc_update_and_evaluate(self.h, int(index), _ptr(P), _ptr(idx4), idx4.shape[0], _ptr(out), C.byref(m)))
+        self._check(self.lib.ecc_update_and_evaluate(self.h, int(index), _ptr(P, _F64), _ptr(idx4, _I32), idx4.shape[0], _ptr(out, _F32), C.byref(m)))
         return m.value
 
     def evaluate_batch(self, Ps_sets, idx4=None, out=None, want_means=True):
@@ -219,8 +228,8 @@ class Context:
         n_sets = Ps_sets.shape[0]
         n_pairs = 0 if idx4 is None else idx4.shape[0]
         means = np.zeros(n_sets, np.float64) if want_means else None
-        self._check(self.lib.ecc_evaluate_batch(self.h, _ptr(Ps_sets), n_sets, _ptr(idx4), n_pairs, _ptr(out),
-                                                _ptr(means)))
+        self._check(self.lib.ecc_evaluate_batch(self.h, _ptr(Ps_sets, _F64), n_sets, _ptr(idx4, _I32), n_pairs, _ptr(out, _F32),
+                                                _ptr(means, _F64)))
         return means
 
     def pair_signals(self, i, j, dtr_i=None, dtr_j=None):
@@ -233,20 +242,20 @@ class Context:
         m = n.value
         out = dict(kappas=np.zeros(m, np.float32), signal0=np.zeros(m, np.float32), signal1=np.zeros(m, np.float32),
                    lines0=np.zeros((m, 2), np.float32), lines1=np.zeros((m, 2), np.float32))
-        self._check(self.lib.ecc_pair_signals(self.h, i, j, dtr_i, dtr_j, m, _ptr(out["kappas"]), _ptr(out["signal0"]),
-                                              _ptr(out["signal1"]), _ptr(out["lines0"]), _ptr(out["lines1"]), C.byref(n),
+        self._check(self.lib.ecc_pair_signals(self.h, i, j, dtr_i, dtr_j, m, _ptr(out["kappas"], _F32), _ptr(out["signal0"], _F32),
+                                              _ptr(out["signal1"], _F32), _ptr(out["lines0"], _F32), _ptr(out["lines1"], _F32), C.byref(n),
                                               C.byref(w), C.byref(v)))
         out["weight"], out["value"] = w.value, v.value
         return out
 
     def pair_sample_counts(self, n_views):
         counts = np.zeros(n_views * (n_views - 1) // 2, np.int32)
-        self._check(self.lib.ecc_pair_sample_counts(self.h, _ptr(counts)))
+        self._check(self.lib.ecc_pair_sample_counts(self.h, _ptr(counts, _I32)))
         return counts
 
     def partition_pairs(self, n_parts):
         bounds = np.zeros(n_parts + 1, np.int64)
-        self._check(self.lib.ecc_partition_pairs(self.h, int(n_parts), _ptr(bounds)))
+        self._check(self.lib.ecc_partition_pairs(self.h, int(n_parts), _ptr(bounds, _I64)))
         return bounds
 
     # -- multi-GPU team (include/ecc_b200.h "Multi-GPU team"): peer-mapped blocks, no collective on the data path
@@ -255,14 +264,14 @@ class Context:
     def team_create(self, rank, world, n_total, n_alpha, n_t):
         """Allocates this rank's block; returns its handle (bytes) for the other processes."""
         handle = np.zeros(self.TEAM_HANDLE_BYTES, np.uint8)
-        self._check(self.lib.ecc_team_create(self.h, int(rank), int(world), int(n_total), int(n_alpha), int(n_t), _ptr(handle)))
+        self._check(self.lib.ecc_team_create(self.h, int(rank), int(world), int(n_total), int(n_alpha), int(n_t), _ptr(handle, _U8)))
         self._team_shape = (int(n_total), int(n_t), int(n_alpha))
         return handle.tobytes()
 
     def team_connect(self, handles):
         """handles: the world handles in rank order (bytes each)."""
         blob = np.frombuffer(b"".join(handles), np.uint8).copy()
-        self._check(self.lib.ecc_team_connect(self.h, _ptr(blob)))
+        self._check(self.lib.ecc_team_connect(self.h, _ptr(blob, _U8)))
 
     def team_connect_pointers(self, blocks):
         """blocks: the ranks' block addresses (team_block()[0]) when all ranks live in this process."""
@@ -293,7 +302,7 @@ class Context:
 
     def team_radon_compute(self, images, first, n_u, n_v, filter=FILTER_DERIVATIVE, post=POST_IDENTITY, interp=INTERP_TEXTURE):
         n_local = 0 if images is None else images.shape[0]
-        self._check(self.lib.ecc_team_radon_compute(self.h, _ptr(images) if n_local else None, int(first), n_local, n_u, n_v,
+        self._check(self.lib.ecc_team_radon_compute(self.h, _ptr(images, _F32) if n_local else None, int(first), n_local, n_u, n_v,
                                                     filter, post, interp))
 
     def team_set_radon_intermediates(self, n_u, n_v, is_derivative=True):
@@ -305,7 +314,7 @@ class Context:
 
     def team_evaluate(self, cost_image=None, want_mean=True):
         m = C.c_double()
-        self._check(self.lib.ecc_team_evaluate(self.h, _ptr(cost_image), C.byref(m) if want_mean else None))
+        self._check(self.lib.ecc_team_evaluate(self.h, _ptr(cost_image, _F32), C.byref(m) if want_mean else None))
         return m.value if want_mean else None
 
     def team_barrier(self):
@@ -315,8 +324,8 @@ class Context:
     def synth_projections(self, Ps, n_u, n_v, ellipsoids, images, cos_weight=True, zero_border=True):
         Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
         ell = np.ascontiguousarray(ellipsoids, np.float64).reshape(-1, 7)
-        self._check(self.lib.ecc_synth_projections(self.h, _ptr(Ps), Ps.shape[0], n_u, n_v, _ptr(ell), ell.shape[0],
-                                                   int(cos_weight), int(zero_border), _ptr(images)))
+        self._check(self.lib.ecc_synth_projections(self.h, _ptr(Ps, _F64), Ps.shape[0], n_u, n_v, _ptr(ell, _F64), ell.shape[0],
+                                                   int(cos_weight), int(zero_border), _ptr(images, _F32)))
         return images
 
     # -- instrumentation

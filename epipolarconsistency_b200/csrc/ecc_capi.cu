@@ -183,21 +183,6 @@ int upload_and_derive(ecc_context* ctx, const double* Ps, size_t count, double**
                                ctx->object_radius, radii_d);
 }
 
-// Batch-mode buffers live outside the context struct's main set so that the current matrices stay valid.
-struct BatchBuffers {
-    double* Ps_d = nullptr;
-    float* Cs_d = nullptr;
-    float* A_d = nullptr;
-    size_t cap = 0;
-    float* radii_d = nullptr;
-    size_t radii_cap = 0;
-};
-std::map<ecc_context*, BatchBuffers>& batch_buffers()
-{
-    static std::map<ecc_context*, BatchBuffers> m;
-    return m;
-}
-
 }  // namespace
 
 extern "C" {
@@ -246,12 +231,7 @@ void ecc_destroy(ecc_context* ctx)
         cudaStreamDestroy(ctx->copy_stream);
         for (int b = 0; b < 2; b++) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_consumed[b]); }
     }
-    auto it = batch_buffers().find(ctx);
-    if (it != batch_buffers().end()) {
-        cudaFree(it->second.Ps_d); cudaFree(it->second.Cs_d); cudaFree(it->second.A_d); cudaFree(it->second.radii_d);
-        batch_buffers().erase(it);
-    }
-    void* bufs[] = {ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, (void*)ctx->dtr_ptrs_d, ctx->vals_d, ctx->partials_d,
+    void* bufs[] = {ctx->batch.Ps_d, ctx->batch.Cs_d, ctx->batch.A_d, ctx->batch.radii_d, ctx->batch.params_d, ctx->batch.base_d, ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, (void*)ctx->dtr_ptrs_d, ctx->vals_d, ctx->partials_d,
                     ctx->sums_d, ctx->idx_d, ctx->counts_d, ctx->img_stage_d, ctx->out_stage_d, ctx->cost_d};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -334,6 +314,10 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
         ECC_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
         ECC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
     }
+    // the chunks grow: size the quad kernel's staging once for the largest one instead of at every growth step
+    if ((interp == ECC_INTERP_HYBRID || interp == ECC_INTERP_HYBRID_STATIC) && filter == ECC_FILTER_DERIVATIVE && n_images >= 3 &&
+        (rc = radon_hybrid4_reserve(ctx, n_u, n_v, chunk)))
+        return rc;
     int k = 0, want = first_chunk;
     for (int first = 0; first < n_images; k++) {
         int n = (n_images - first < want) ? n_images - first : want;
@@ -959,7 +943,7 @@ int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, cons
         if (ctx->n_dtrs < ctx->n_views) return fail(ctx, ECC_ERR_STATE, "all-pairs evaluation needs one dtr per projection matrix");
         L.n_pairs = n * (n - 1) / 2;
     }
-    BatchBuffers& B = batch_buffers()[ctx];
+    BatchBuffers& B = ctx->batch;
     // every set gets the object radius the reference would derive from that set's first matrix
     if (B.radii_cap < (size_t)n_sets) {
         ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -73,17 +73,22 @@ struct Mirrors {
 struct Team {
     int rank = 0, world = 0;  // world == 0: no team
     int n_total = 0, n_alpha = 0, n_t = 0;
-    size_t block_bytes = 0, vals_offset = 0, dtrs_offset = 0;
+    size_t block_bytes = 0, vals_offset = 0, vals_bytes = 0, dtrs_offset = 0;
     void* block = nullptr;            // own block (cudaMalloc)
     std::vector<void*> bases;         // [world] block of every rank in this process's address space (own included)
     std::vector<void*> opened;        // the ones mapped with cudaIpcOpenMemHandle
     unsigned** flag_tables_d = nullptr;  // [world] device table of the ranks' flag arrays
     unsigned* status_d = nullptr;     // set by a barrier that timed out
     unsigned epoch = 0;
+    unsigned evaluations = 0;         // ecc_team_evaluate calls so far: evaluation k uses value buffer k & 1 (see vals())
     bool connected = false;
     bool mirror_radon = false;        // while ecc_team_radon_compute runs: Radon kernels mirror their stores
     float* dtrs() const { return (float*)((char*)block + dtrs_offset); }
-    float* vals() const { return (float*)((char*)block + vals_offset); }
+    // Two value buffers, used alternately: a rank that has left evaluation k may already publish the values of evaluation
+    // k+1 into its peers while they still sum / scatter / download those of k (nothing orders a peer's reads of k before
+    // this rank's next stores otherwise); it cannot reach k+2 -- the buffer of k again -- before every peer has arrived at
+    // the barrier of k+1, i.e. has finished reading k.
+    float* vals(unsigned evaluation) const { return (float*)((char*)block + vals_offset + (evaluation & 1u) * vals_bytes); }
 };
 
 // ecc_update_and_evaluate: the {replace one matrix, evaluate a pair list} step of tracking loops, recorded once as a CUDA
@@ -98,6 +103,21 @@ struct TrackGraph {
     size_t pinned_bytes = 0;
     bool failed = false;         // capture did not work here: stay on the plain path
     long long replays = 0;
+};
+
+// ecc_evaluate_batch: the K matrix sets of a launch and what is derived from them; separate from the context's current
+// matrices, which stay valid across a batched call.
+struct BatchBuffers {
+    double* Ps_d = nullptr;
+    float* Cs_d = nullptr;
+    float* A_d = nullptr;
+    size_t cap = 0;
+    float* radii_d = nullptr;
+    size_t radii_cap = 0;
+    double* params_d = nullptr;   // ecc_evaluate_batch_params: parameter vectors and base matrices
+    size_t params_cap = 0;
+    double* base_d = nullptr;
+    size_t base_cap = 0;
 };
 
 }  // namespace eccb200
@@ -174,6 +194,7 @@ struct ecc_context {
     eccb200::Hybrid4Stage hybrid4;
     eccb200::Team team;
     eccb200::TrackGraph track;
+    eccb200::BatchBuffers batch;
 
     // ---- profiling ----
     bool profiling = false;
@@ -263,6 +284,7 @@ void free_hybrid(ecc_context* ctx);
 int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d,
                          bool static_split = false);
 void free_hybrid4(ecc_context* ctx);
+int radon_hybrid4_reserve(ecc_context* ctx, int n_u, int n_v, int n_images);
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
 
 // ---- multi-GPU team (ecc_team.cu) ----

@@ -232,6 +232,8 @@ int ensure_pool(ecc_context* ctx, int n_u, int n_v, int count)
 {
     ImagePool& P = ctx->pool;
     if (P.n_u == n_u && P.n_v == n_v && P.count >= count) return ECC_OK;
+    // launches queued earlier on the stream may still sample the arrays that are about to go
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free_image_pool(ctx);
     P.n_u = n_u;
     P.n_v = n_v;

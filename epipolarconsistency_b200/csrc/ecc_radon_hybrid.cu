@@ -421,6 +421,7 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
     const int pitch_n = (n_u + 1 + 3) & ~3, pitch_t = (n_v + 1 + 3) & ~3;
     if (H.n_u != n_u || H.n_v != n_v || H.count < n) {
         const int count = n > H.count ? n : H.count;
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the staging that is about to go
         free_hybrid(ctx);
         ECC_CUDA(ctx, cudaMalloc(&H.pad_n, sizeof(float) * (size_t)count * (n_v + 1) * pitch_n));
         ECC_CUDA(ctx, cudaMalloc(&H.pad_t, sizeof(float) * (size_t)count * (n_u + 1) * pitch_t));

@@ -575,42 +575,56 @@ int launch_window_config(ecc_context* ctx, Hybrid4Stage& H, const Hybrid4Params&
     return ECC_OK;
 }
 
+// Staging for nq quads of n_u x n_v images (grows, never shrinks; sized once per call chain by radon_hybrid4_reserve).
+static int ensure_hybrid4(ecc_context* ctx, int n_u, int n_v, int nq)
+{
+    Hybrid4Stage& H = ctx->hybrid4;
+    if (H.n_u == n_u && H.n_v == n_v && H.quads >= nq) return ECC_OK;
+    const int quads = (H.n_u == n_u && H.n_v == n_v && H.quads > nq) ? H.quads : nq;
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the staging that is about to go
+    free_hybrid4(ctx);
+    H.n_u = n_u;
+    H.n_v = n_v;
+    const size_t px = (size_t)n_u * n_v, pxp = (size_t)(n_u + 1) * (n_v + 1);
+    ECC_CUDA(ctx, cudaMalloc(&H.lin, sizeof(float4) * px * quads));
+    ECC_CUDA(ctx, cudaMalloc(&H.pad_n, sizeof(float4) * pxp * quads));
+    ECC_CUDA(ctx, cudaMalloc(&H.pad_t, sizeof(float4) * pxp * quads));
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+    for (int k = 0; k < quads; k++) {
+        cudaArray_t arr = nullptr;
+        ECC_CUDA(ctx, cudaMallocArray(&arr, &desc, n_u, n_v));
+        H.arrays.push_back(arr);
+        cudaResourceDesc res = {};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td = {};
+        td.normalizedCoords = 0;
+        td.filterMode = cudaFilterModeLinear;
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex = 0;
+        ECC_CUDA(ctx, cudaCreateTextureObject(&tex, &res, &td, nullptr));
+        H.tex_h.push_back(tex);
+        H.quads = k + 1;
+    }
+    ECC_CUDA(ctx, cudaMalloc(&H.tex_d, sizeof(cudaTextureObject_t) * quads));
+    ECC_CUDA(ctx, cudaMemcpyAsync(H.tex_d, H.tex_h.data(), sizeof(cudaTextureObject_t) * quads, cudaMemcpyHostToDevice, ctx->stream));
+    H.map_cfg = -1;  // the tensor maps are encoded at the launch, for the window configuration chosen there
+    return ECC_OK;
+}
+
+// Sizes the staging once for launches of up to n images (callers that feed a data set in growing chunks).
+int radon_hybrid4_reserve(ecc_context* ctx, int n_u, int n_v, int n) { return ensure_hybrid4(ctx, n_u, n_v, (n + 3) / 4); }
+
 // n images (device, dense) -> their Radon intermediates; works on ceil(n/4) quads.
 int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d,
                          bool static_split)
 {
     Hybrid4Stage& H = ctx->hybrid4;
     const int nq = (n + 3) / 4;
-    if (H.n_u != n_u || H.n_v != n_v || H.quads < nq) {
-        const int quads = nq > H.quads ? nq : H.quads;
-        free_hybrid4(ctx);
-        H.n_u = n_u;
-        H.n_v = n_v;
-        const size_t px = (size_t)n_u * n_v, pxp = (size_t)(n_u + 1) * (n_v + 1);
-        ECC_CUDA(ctx, cudaMalloc(&H.lin, sizeof(float4) * px * quads));
-        ECC_CUDA(ctx, cudaMalloc(&H.pad_n, sizeof(float4) * pxp * quads));
-        ECC_CUDA(ctx, cudaMalloc(&H.pad_t, sizeof(float4) * pxp * quads));
-        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
-        for (int k = 0; k < quads; k++) {
-            cudaArray_t arr = nullptr;
-            ECC_CUDA(ctx, cudaMallocArray(&arr, &desc, n_u, n_v));
-            H.arrays.push_back(arr);
-            cudaResourceDesc res = {};
-            res.resType = cudaResourceTypeArray;
-            res.res.array.array = arr;
-            cudaTextureDesc td = {};
-            td.normalizedCoords = 0;
-            td.filterMode = cudaFilterModeLinear;
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-            td.readMode = cudaReadModeElementType;
-            cudaTextureObject_t tex = 0;
-            ECC_CUDA(ctx, cudaCreateTextureObject(&tex, &res, &td, nullptr));
-            H.tex_h.push_back(tex);
-            H.quads = k + 1;
-        }
-        ECC_CUDA(ctx, cudaMalloc(&H.tex_d, sizeof(cudaTextureObject_t) * quads));
-        ECC_CUDA(ctx, cudaMemcpyAsync(H.tex_d, H.tex_h.data(), sizeof(cudaTextureObject_t) * quads, cudaMemcpyHostToDevice, ctx->stream));
-        H.map_cfg = -1;  // the tensor maps are encoded at the launch, for the window configuration chosen there
+    {
+        const int rce = ensure_hybrid4(ctx, n_u, n_v, nq);
+        if (rce) return rce;
     }
     {   // image staging: two kernels (+ the array copies below), profile family "stage"
         const int s1 = prof_begin(ctx, FAM_STAGE);

@@ -3,7 +3,7 @@
 // the path has one real exchange step (every GPU needs all Radon intermediates before it scores its
 // share of the pairs) and a final reduction.  Both used to be NCCL calls after the kernels (all-gather of 146 MB per
 // rank at C3 / 8 GPUs, two all-reduces).  Here every rank owns one device block
-//        [ flags | pair values, n(n-1)/2 floats | Radon intermediates of ALL projections ]
+//        [ flags | pair values, 2 x n(n-1)/2 floats (used alternately) | Radon intermediates of ALL projections ]
 // mapped into every other rank's address space (CUDA IPC between the per-GPU processes), and
 //   * the Radon kernels store each finished bin into ALL blocks (one local + world-1 NVLink peer stores per bin; a bin
 //     costs ~2300 samples, so the stores are free and the exchange rides under the line integration tile by tile),
@@ -190,7 +190,8 @@ int ecc_team_create(ecc_context* ctx, int rank, int world, int n_total, int n_al
     T.n_t = n_t;
     const size_t pairs = (size_t)n_total * (n_total - 1) / 2;
     T.vals_offset = kFlagBytes;
-    T.dtrs_offset = T.vals_offset + round512(sizeof(float) * (pairs ? pairs : 1));
+    T.vals_bytes = round512(sizeof(float) * (pairs ? pairs : 1));
+    T.dtrs_offset = T.vals_offset + 2 * T.vals_bytes;
     T.block_bytes = T.dtrs_offset + round512(sizeof(float) * (size_t)n_total * n_t * n_alpha);
     ECC_CUDA(ctx, cudaMalloc(&T.block, T.block_bytes));
     ECC_CUDA(ctx, cudaMemset(T.block, 0, T.dtrs_offset));  // flags and values
@@ -316,25 +317,26 @@ int ecc_team_evaluate(ecc_context* ctx, float* cost_image, double* mean)
     std::vector<long long> bounds(T.world + 1);
     if ((rc = ecc_partition_pairs(ctx, T.world, bounds.data()))) return rc;
     const long long lo = bounds[T.rank], hi = bounds[T.rank + 1];
+    float* const vals = T.vals(T.evaluations++);  // this evaluation's value buffer (every rank makes the same sequence of calls)
     if (hi > lo) {
         L.pair_begin = lo;
         L.n_pairs = hi - lo;
         L.mode_items = total;  // as the single-GPU job computes it (ecc_evaluate_range)
-        L.vals_d = T.vals() + lo;
+        L.vals_d = vals + lo;
         L.image_d = nullptr;
         if ((rc = launch_pairs(ctx, L))) return rc;
-        if ((rc = team_publish(ctx, T.vals() + lo, sizeof(float) * (size_t)(hi - lo)))) return rc;
+        if ((rc = team_publish(ctx, vals + lo, sizeof(float) * (size_t)(hi - lo)))) return rc;
     }
     if ((rc = team_barrier(ctx))) return rc;
     // every rank now holds all values: same fixed-order sum, same cost image everywhere
     size_t scap = ctx->sums_cap * sizeof(double);
     if ((rc = ensure_bytes(ctx, (void**)&ctx->sums_d, &scap, sizeof(double)))) return rc;
     ctx->sums_cap = scap / sizeof(double);
-    if (total > 0 && (rc = launch_sum_sets(ctx, T.vals(), total, 1, ctx->sums_d))) return rc;
+    if (total > 0 && (rc = launch_sum_sets(ctx, vals, total, 1, ctx->sums_d))) return rc;
     const bool img_dev = cost_image && is_device_pointer(cost_image);
     const bool host_image = cost_image && !img_dev;
     if (img_dev && total > 0) {
-        scatter_cost_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(T.vals(), total, (int)n, cost_image);
+        scatter_cost_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(vals, total, (int)n, cost_image);
         ECC_CUDA(ctx, cudaGetLastError());
     }
     const size_t need = 16 + (host_image ? sizeof(float) * (size_t)total : 0);
@@ -345,7 +347,7 @@ int ecc_team_evaluate(ecc_context* ctx, float* cost_image, double* mean)
     *sum_h = 0.0;
     if (total > 0) ECC_CUDA(ctx, cudaMemcpyAsync(sum_h, ctx->sums_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ECC_CUDA(ctx, cudaMemcpyAsync(status_h, T.status_d, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-    if (host_image && total > 0) ECC_CUDA(ctx, cudaMemcpyAsync(vals_h, T.vals(), sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_image && total > 0) ECC_CUDA(ctx, cudaMemcpyAsync(vals_h, vals, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
     ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (*status_h) return fail(ctx, ECC_ERR_STATE, "team barrier timed out: a rank did not arrive");
     if (host_image) {

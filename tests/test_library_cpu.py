@@ -87,3 +87,23 @@ def test_camera_intrinsics_and_similarity_models_host():
     assert np.allclose(z, [np.sin(0.01 * -1) * 0 + np.sin(-0.01), -np.sin(0.02) * np.cos(-0.01), np.cos(0.02) * np.cos(-0.01)], atol=1e-12)
     want = (H @ P.reshape(4, 3).T @ T).T.reshape(12)
     assert np.allclose(api.camera_similarity_2d3d(P, x), want, rtol=1e-13, atol=1e-13)
+
+
+def test_buffer_dtypes_are_checked_before_they_reach_the_abi():
+    """The C ABI reads raw addresses: a default int64 index array or float64 images would be reinterpreted silently
+    (round-1 advisor finding).  The binding refuses them."""
+    import pytest
+    assert api._ptr(np.zeros(4, np.float32), "float32")
+    assert api._ptr(None, "float32") is None
+    with pytest.raises(TypeError):
+        api._ptr(np.zeros((3, 4)), "float32")           # float64 images / dtrs
+    with pytest.raises(TypeError):
+        api._ptr(np.zeros((3, 4), np.int64), "int32")   # numpy's default integer type as a pair list
+    with pytest.raises(TypeError):
+        api._ptr(np.zeros(12, np.float32), "float64")   # single-precision matrices
+    with pytest.raises(ValueError):
+        api._ptr(np.zeros((4, 4), np.float32)[:, ::2], "float32")
+    import torch
+    with pytest.raises(TypeError):
+        api._ptr(torch.zeros(4, dtype=torch.float64), "float32")
+    assert api._ptr(torch.zeros(4, dtype=torch.int32), "int32")
