@@ -46,6 +46,7 @@ SIGNATURES = {
     "ecc_evaluate_batch": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
     "ecc_pair_signals": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ecc_pair_maps": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp]),
     "ecc_pair_sample_counts": (C.c_int, [c_ctx, c_vp]),
     "ecc_partition_pairs": (C.c_int, [c_ctx, C.c_int, c_vp]),
     "ecc_team_create": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),

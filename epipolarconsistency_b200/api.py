@@ -248,6 +248,13 @@ class Context:
         out["weight"], out["value"] = w.value, v.value
         return out
 
+    def pair_maps(self, idx4=None, n_views=None):
+        """The reference's K01 records (16 floats per pair) as the pair kernels compute them; all pairs when idx4 is None."""
+        n_pairs = n_views * (n_views - 1) // 2 if idx4 is None else idx4.shape[0]
+        K = np.zeros((n_pairs, 16), np.float32)
+        self._check(self.lib.ecc_pair_maps(self.h, _ptr(idx4, _I32), 0 if idx4 is None else n_pairs, _ptr(K, _F32)))
+        return K
+
     def pair_sample_counts(self, n_views):
         counts = np.zeros(n_views * (n_views - 1) // 2, np.int32)
         self._check(self.lib.ecc_pair_sample_counts(self.h, _ptr(counts, _I32)))

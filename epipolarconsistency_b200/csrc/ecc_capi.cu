@@ -161,6 +161,7 @@ int fill_launch(ecc_context* ctx, PairLaunch& L)
     L.mode_items = 0;
     L.defer_finalize = 0;
     L.partials_d = nullptr;
+    L.corr_sums_d = nullptr;
     return ECC_OK;
 }
 
@@ -1040,6 +1041,35 @@ int ecc_pair_signals(ecc_context* ctx, int p0, int p1, int dtr0, int dtr1, int c
         if ((rc = ecc_evaluate_indices(ctx, idx_h, 1, &v, nullptr))) return rc;
         *value = (double)v;
     }
+    return ECC_OK;
+}
+
+int ecc_pair_maps(ecc_context* ctx, const int* idx4, int n_pairs, float* K01s)
+{
+    if (!ctx || !K01s) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    PairLaunch L;
+    int rc = fill_launch(ctx, L);
+    if (rc) return rc;
+    const long long n = ctx->n_views;
+    if (idx4) {
+        if (n_pairs < 0) return fail(ctx, ECC_ERR_INVALID, "ecc_pair_maps: bad argument");
+        if (n_pairs == 0) return ECC_OK;
+        if ((rc = check_indices(ctx, idx4, n_pairs))) return rc;
+        if ((rc = stage_indices(ctx, idx4, n_pairs, &L.idx4_d))) return rc;
+        L.n_pairs = n_pairs;
+    } else {
+        L.n_pairs = n * (n - 1) / 2;
+        if (L.n_pairs == 0) return ECC_OK;
+    }
+    const size_t bytes = sizeof(float) * 16 * (size_t)L.n_pairs;
+    if (is_device_pointer(K01s)) return launch_pair_maps(ctx, L, K01s);
+    size_t cap = ctx->partials_cap * sizeof(float);
+    if ((rc = ensure_bytes(ctx, (void**)&ctx->partials_d, &cap, bytes))) return rc;
+    ctx->partials_cap = cap / sizeof(float);
+    if ((rc = launch_pair_maps(ctx, L, ctx->partials_d))) return rc;
+    ECC_CUDA(ctx, cudaMemcpyAsync(K01s, ctx->partials_d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ECC_OK;
 }
 

@@ -109,6 +109,21 @@ __host__ __device__ inline void make_pair_maps(float half_nu, float half_nv, con
     pm.dkappa = (dkappa <= 0.f) ? 2.f * pm.kappa_max / num_samples : dkappa;
 }
 
+// K0[7] of the reference's record: the angle under which the two sources see each other from the reference point
+// (EpipolarConsistencyCommon.hxx:139-140); unused downstream, kept for the launcher-compatible K01 output.
+__host__ __device__ inline float pair_angle(const float* C0, const float* C1)
+{
+    const float b01 = C0[0] * C1[1] - C0[1] * C1[0];
+    const float b02 = C0[0] * C1[2] - C0[2] * C1[0];
+    const float b03 = C0[0] * C1[3] - C0[3] * C1[0];
+    const float b12 = C0[1] * C1[2] - C0[2] * C1[1];
+    const float b13 = C0[1] * C1[3] - C0[3] * C1[1];
+    const float b23 = C0[2] * C1[3] - C0[3] * C1[2];
+    const float s2 = sqrtf(b12 * b12 + b02 * b02 + b01 * b01);
+    const float s3 = sqrtf(b03 * b03 + b13 * b13 + b23 * b23);
+    return -2.0f * atan2f(-0.5f * s3, s2 / s3);
+}
+
 // kappa of sample m: (m + 1/2) dkappa, in the form nvcc gives the reference's
 // "dkappa*0.5f+dkappa*idx_y" (EpipolarConsistencyRadonIntermediate.cu:194,260): one fused multiply-add.
 __host__ __device__ inline float kappa_of_sample(float dkappa, int m)

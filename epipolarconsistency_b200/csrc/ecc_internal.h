@@ -250,6 +250,7 @@ struct PairLaunch {
     int defer_finalize;  // split launches: leave the partial sums for launch_finalize_sum
     int splits;          // set by launch_pairs: CTAs per pair (CTA-per-pair launches)
     float* partials_d;   // [items][splits][3] when splits > 1
+    float* corr_sums_d;  // correlation variant, nullable: the reference launcher's six sums per pair (forces splits = 1)
     // outputs
     float* vals_d;   // n_sets*n_pairs
     float* image_d;  // all-pairs: n_views*n_views cost image or null (only with n_sets==1)
@@ -261,6 +262,9 @@ int launch_pairs(ecc_context* ctx, const PairLaunch& L, PairLaunch* resolved = n
 int launch_finalize_sum(ecc_context* ctx, const PairLaunch& resolved, double* sum_out, float* vals_out);
 int fill_pair_launch(ecc_context* ctx, PairLaunch& L);  // everything that depends on the context state only (ecc_capi.cu)
 int launch_pair_counts(ecc_context* ctx, const PairLaunch& L, int* counts_d);
+// K01s_d [n_pairs][16]: the reference's K01 record of every pair of the launch (ecc_pairs.cu: pair_maps_kernel)
+int launch_pair_maps(ecc_context* ctx, const PairLaunch& L, float* K01s_d);
+int launch_fill(ecc_context* ctx, float* dst_d, size_t count, size_t stride, float value);  // dst[k * stride] = value, k < count
 // one pair (L.idx4_d[0..3]): rec_d [sample_cap][13] floats, head_d [2] ints zeroed before the launch (ecc_pairs.cu: pair_signals_kernel)
 int launch_pair_signals(ecc_context* ctx, const PairLaunch& L, float* rec_d, int* head_d);
 int launch_sum_sets(ecc_context* ctx, const float* vals_d, long long n_pairs, int n_sets,

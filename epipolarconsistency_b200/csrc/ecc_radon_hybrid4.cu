@@ -42,7 +42,9 @@ struct Win4 {
     // a chunk whose band of rows does not fit the window: false = the whole item goes through the texture unit,
     // true = only that chunk's samples do (fetched by the window warps themselves, in sample order)
     static constexpr bool chunk_fallback = CHUNK_FALLBACK;
+#ifndef ECC_ANY_ROWS  // development: other residues of the window height (the bank-group offset between neighbouring columns)
     static_assert(ROWS % 8 == 1, "window height: 1 mod 8 keeps neighbouring columns one bank group apart");
+#endif
     static_assert(max_chunks <= kWindowWarps * 32, "one window thread per chunk initialises the row tables");
     static constexpr size_t buf_bytes = (size_t)ROWS * boxw * 16;
     static constexpr size_t smem = (buf_bytes + 127) / 128 * 128 * NBUF;
@@ -127,11 +129,74 @@ __device__ __forceinline__ void bin_texture4(cudaTextureObject_t tex, const BinL
     res.w = (sum.w - sumo.w) * kStep;
 }
 
+// ---- packed fp32 pairs (sm_100: add / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2) ----------------------------------------
+// The window path's per-image filter arithmetic is the same eight IEEE operations for each of the four interleaved
+// images; Blackwell executes them two images per instruction.  Each lane of a packed operation is the separately rounded
+// fp32 operation (round to nearest), so the results are those of the scalar code bit for bit -- what changes is the
+// number of issue slots: 16 instead of 32 per sample position.  -DECC_F32X2=0 keeps the scalar form (A/B, same bits).
+#ifndef ECC_F32X2
+#define ECC_F32X2 1
+#endif
+#ifndef ECC_WINDOW_UNROLL  // unroll factor of the window path's sample loop (2: the packed running sums ping-pong between
+#define ECC_WINDOW_UNROLL 2  // register pairs instead of being moved back after every sample)
+#endif
+constexpr int kWindowUnroll = ECC_WINDOW_UNROLL;
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void acc2(f32x2& a, f32x2 b)  // a += b in place (keeps the running sum in its register pair)
+{
+    asm("add.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Running sums of a line for the four images of a quad, as the window path keeps them.
+#if ECC_F32X2 == 1
+struct Acc4 {
+    f32x2 xy, zw;
+};
+__device__ __forceinline__ Acc4 acc_zero() { Acc4 a; a.xy = pk(0.f, 0.f); a.zw = a.xy; return a; }
+__device__ __forceinline__ void add4(Acc4& s, const float4& v) { s.xy = add2(s.xy, pk(v.x, v.y)); s.zw = add2(s.zw, pk(v.z, v.w)); }
+__device__ __forceinline__ Sum4 acc_unpack(const Acc4& a) { Sum4 r; unpk(a.xy, r.x, r.y); unpk(a.zw, r.z, r.w); return r; }
+#else
+typedef Sum4 Acc4;
+__device__ __forceinline__ Acc4 acc_zero() { Acc4 a = {0.f, 0.f, 0.f, 0.f}; return a; }
+__device__ __forceinline__ Sum4 acc_unpack(const Acc4& a) { return a; }
+#endif
+
 // One sample position applied to the four images of the window: position -> cell and fractions -> weights once
 // (ecc_radon_hybrid.cu: sample_window has the derivation), four 16-byte loads, then per image
 // v00 + (w10 (v10-v00) + w01 (v01-v00) + w11 (v11-v00)) / 256.
 template <int kRows4>
-__device__ __forceinline__ void sample_window4(unsigned base, float pri, float sec, Sum4& acc)
+__device__ __forceinline__ void sample_window4(unsigned base, float pri, float sec, Acc4& acc)
 {
     const float Ps = fmaf(pri, 256.f, -127.5f);
     const float Ss = fmaf(sec, 256.f, -127.5f);
@@ -143,6 +208,40 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
 #else
     const unsigned addr = base + (((Pi >> 8) * kRows4 + (Si >> 8)) << 4);
 #endif
+    const unsigned w11 = (a * b + 128u) >> 8;
+    const float f11 = __uint2float_rn(w11), f10 = __uint2float_rn(a - w11), f01 = __uint2float_rn(b - w11);
+#if ECC_F32X2
+    f32x2 v00a, v00b, v01a, v01b, v10a, v10b, v11a, v11b;  // a = images 0, 1; b = images 2, 3
+    asm volatile(
+        "ld.shared.v2.b64 {%0, %1}, [%8];\n"
+        "ld.shared.v2.b64 {%2, %3}, [%8+16];\n"
+        "ld.shared.v2.b64 {%4, %5}, [%8+%9];\n"
+        "ld.shared.v2.b64 {%6, %7}, [%8+%10];\n"
+        : "=l"(v00a), "=l"(v00b), "=l"(v01a), "=l"(v01b), "=l"(v10a), "=l"(v10b), "=l"(v11a), "=l"(v11b)
+        : "r"(addr), "n"(kRows4 * 16), "n"(kRows4 * 16 + 16));  // the next column: one window height further
+    const f32x2 p10 = pk(f10, f10), p01 = pk(f01, f01), p11 = pk(f11, f11), scale = pk(0.00390625f, 0.00390625f);
+    f32x2 t = mul2(p10, sub2(v10a, v00a));
+    t = fma2(p01, sub2(v01a, v00a), t);
+    t = fma2(p11, sub2(v11a, v00a), t);
+#if ECC_F32X2 == 1
+    acc2(acc.xy, fma2(t, scale, v00a));
+#else  // packed filter, scalar running sums
+    float r0, r1, r2, r3;
+    unpk(fma2(t, scale, v00a), r0, r1);
+    acc.x += r0;
+    acc.y += r1;
+#endif
+    t = mul2(p10, sub2(v10b, v00b));
+    t = fma2(p01, sub2(v01b, v00b), t);
+    t = fma2(p11, sub2(v11b, v00b), t);
+#if ECC_F32X2 == 1
+    acc2(acc.zw, fma2(t, scale, v00b));
+#else
+    unpk(fma2(t, scale, v00b), r2, r3);
+    acc.z += r2;
+    acc.w += r3;
+#endif
+#else
     float4 v00, v01, v10, v11;
     asm volatile(
         "ld.shared.v4.f32 {%0, %1, %2, %3}, [%16];\n"
@@ -152,8 +251,6 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
         : "=f"(v00.x), "=f"(v00.y), "=f"(v00.z), "=f"(v00.w), "=f"(v01.x), "=f"(v01.y), "=f"(v01.z), "=f"(v01.w), "=f"(v10.x),
           "=f"(v10.y), "=f"(v10.z), "=f"(v10.w), "=f"(v11.x), "=f"(v11.y), "=f"(v11.z), "=f"(v11.w)
         : "r"(addr), "n"(kRows4 * 16), "n"(kRows4 * 16 + 16));  // the next column: one window height further
-    const unsigned w11 = (a * b + 128u) >> 8;
-    const float f11 = __uint2float_rn(w11), f10 = __uint2float_rn(a - w11), f01 = __uint2float_rn(b - w11);
 #define ECC_ONE(c)                                                              \
     {                                                                           \
         float t = f10 * (v10.c - v00.c);                                        \
@@ -163,6 +260,7 @@ __device__ __forceinline__ void sample_window4(unsigned base, float pri, float s
     }
     ECC_ONE(x) ECC_ONE(y) ECC_ONE(z) ECC_ONE(w)
 #undef ECC_ONE
+#endif
 }
 
 struct Item4 {
@@ -358,7 +456,7 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
             const CUtensorMap* map = vertical ? &map_n : &map_t;
             float t = live ? L.t : 3.0e38f;
             const float t_max = live ? ref_last_sample(L.t, L.t_max) : -3.0e38f;
-            Sum4 sum = {0.f, 0.f, 0.f, 0.f}, sumo = {0.f, 0.f, 0.f, 0.f};
+            Acc4 sum = acc_zero(), sumo = acc_zero();
             // issue the load of chunk k (traversal order) into buffer k % kNBuf4
             auto issue = [&](int k) {
                 const int kk = dir > 0 ? k : n_chunks - 1 - k;
@@ -415,17 +513,18 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
                 if (b == 0) { mbar_wait(mbar0, phase0); phase0 ^= 1u; }
                 else { mbar_wait(mbar0 + 8u, phase1); phase1 ^= 1u; }
                 const unsigned base = window_base + b * buf_stride - 16u * ((p.magic + (unsigned)(j * kChunk4 - kLead4)) * kRows4 + p.magic + (unsigned)lo);
-#pragma unroll 1
+#pragma unroll kWindowUnroll
                 for (; t <= lim; t += kStep) {
                     const float pri = fmaf(t, dp, op), sec = fmaf(t, ds, os);
                     sample_window4<kRows4>(base, pri, sec, sum);
                     sample_window4<kRows4>(base, pri + offp, sec + offs, sumo);
                 }
             }
-            result.x = (sum.x - sumo.x) * kStep;
-            result.y = (sum.y - sumo.y) * kStep;
-            result.z = (sum.z - sumo.z) * kStep;
-            result.w = (sum.w - sumo.w) * kStep;
+            const Sum4 sa = acc_unpack(sum), so = acc_unpack(sumo);
+            result.x = (sa.x - so.x) * kStep;
+            result.y = (sa.y - so.y) * kStep;
+            result.z = (sa.z - so.z) * kStep;
+            result.w = (sa.w - so.w) * kStep;
         }
         if (in_range) {
             if (L.valid && (fallback || !safe)) bin_texture4(p.texs[B.quad], L, result);

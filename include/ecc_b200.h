@@ -220,6 +220,13 @@ int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, cons
 int ecc_pair_signals(ecc_context* ctx, int p0, int p1, int dtr0, int dtr1, int capacity, float* kappas, float* signal0,
                      float* signal1, float* lines0, float* lines1, int* n_samples, double* weight, double* value);
 
+/* The reference's K01 record of every pair (EpipolarConsistencyCommon.hxx:92-149, what kernelEpipolarConsistencyComputeK01
+ * leaves in K01s, EpipolarConsistencyRadonIntermediate.cu:13-67): 16 floats per pair = K0[0..5] (3x2 col-major map from
+ * (cos kappa, sin kappa) to the epipolar line in view 0, image-centre origin), K0[6] baseline distance, K0[7] angle,
+ * K1[0..5], K1[6] dkappa, K1[7] kappa_max -- computed on the device with the current matrices and settings, exactly the
+ * values the pair kernels work with.  idx4 [h|d] nullable: all pairs in get_ij order.  K01s [h|d]: n_pairs * 16 floats. */
+int ecc_pair_maps(ecc_context* ctx, const int* idx4, int n_pairs, float* K01s);
+
 /* Number of kappa samples each pair takes (the work measure for equal-work partitioning), in
  * get_ij order; counts: n(n-1)/2 ints, host. */
 int ecc_pair_sample_counts(ecc_context* ctx, int* counts);

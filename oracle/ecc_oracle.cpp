@@ -214,6 +214,19 @@ int oracle_max_threads(void)
 #endif
 }
 
+// Sets the OpenMP team size of the oracle's loops (bench.py's CPU legs: torchrun exports OMP_NUM_THREADS=1 to its ranks,
+// which would time the reference arm on one core); returns the resulting omp_get_max_threads().
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 // EpipolarConsistencyCommon.hxx:52-79 -- row-major enumeration of the strict upper triangle.
 void oracle_get_ij(int k, int n, int* i, int* j)
 {

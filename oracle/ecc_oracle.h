@@ -96,6 +96,7 @@ void oracle_project_ellipsoids(const double* P, int n_u, int n_v, const double* 
                                int n_ell, int cos_weight, int zero_border, float* img);
 
 int oracle_max_threads(void);
+int oracle_set_threads(int n);  /* OpenMP threads for the oracle's loops; returns the resulting maximum */
 
 #ifdef __cplusplus
 }

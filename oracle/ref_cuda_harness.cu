@@ -86,8 +86,8 @@ struct RefMetric {
 
 extern "C" {
 
-// Radon intermediates of n images with the reference kernel.  Host pointers.  ms (nullable): GPU time of
-// the launcher calls only (texture set-up excluded), via CUDA events.
+// Radon intermediates of n images with the reference kernel.  Host or device pointers (cudaMemcpyDefault).  ms (nullable):
+// GPU time of the launcher calls only (texture set-up excluded), via CUDA events.
 int ref_cuda_radon(const float* images_h, int n_images, int n_u, int n_v, int n_alpha, int n_t, int filter,
                    int post, float* dtrs_h, float* ms)
 {
@@ -100,7 +100,7 @@ int ref_cuda_radon(const float* images_h, int n_images, int n_u, int n_v, int n_
     CK(cudaEventCreate(&e1));
     float total = 0.f;
     for (int k = 0; k < n_images; k++) {
-        CK(cudaMemcpy(img_d, images_h + img * k, sizeof(float) * img, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(img_d, images_h + img * k, sizeof(float) * img, cudaMemcpyDefault));
         ArrayTex t;
         if (make_array_texture(img_d, n_u, n_v, false, t)) return -1;
         CK(cudaEventRecord(e0));
@@ -110,7 +110,7 @@ int ref_cuda_radon(const float* images_h, int n_images, int n_u, int n_v, int n_
         float m = 0.f;
         CK(cudaEventElapsedTime(&m, e0, e1));
         total += m;
-        CK(cudaMemcpy(dtrs_h + dtr * k, out_d, sizeof(float) * dtr, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(dtrs_h + dtr * k, out_d, sizeof(float) * dtr, cudaMemcpyDefault));
         free_array_texture(t);
     }
     if (ms) *ms = total;
@@ -119,6 +119,12 @@ int ref_cuda_radon(const float* images_h, int n_images, int n_u, int n_v, int n_
     cudaFree(img_d);
     cudaFree(out_d);
     return 0;
+}
+
+int ref_cuda_radon_any(const void* images, int n_images, int n_u, int n_v, int n_alpha, int n_t, int filter, int post,
+                       void* dtrs, float* ms)
+{
+    return ref_cuda_radon((const float*)images, n_images, n_u, n_v, n_alpha, n_t, filter, post, (float*)dtrs, ms);
 }
 
 // Metric object: dtrs become array textures exactly like RadonIntermediate::getTexture() (normalised).
@@ -134,7 +140,7 @@ void* ref_cuda_metric_create(const float* dtrs_h, int n_dtrs, int n_alpha, int n
     std::vector<cudaTextureObject_t> handles(n_dtrs);
     M->dtrs.resize(n_dtrs);
     for (int k = 0; k < n_dtrs; k++) {
-        cudaMemcpy(tmp_d, dtrs_h + dtr * k, sizeof(float) * dtr, cudaMemcpyHostToDevice);
+        cudaMemcpy(tmp_d, dtrs_h + dtr * k, sizeof(float) * dtr, cudaMemcpyDefault);  // host or device dtrs
         if (make_array_texture(tmp_d, n_alpha, n_t, true, M->dtrs[k])) return nullptr;
         handles[k] = M->dtrs[k].tex;
     }
@@ -142,6 +148,12 @@ void* ref_cuda_metric_create(const float* dtrs_h, int n_dtrs, int n_alpha, int n
     cudaMalloc(&M->tex_d, sizeof(cudaTextureObject_t) * n_dtrs);
     cudaMemcpy(M->tex_d, handles.data(), sizeof(cudaTextureObject_t) * n_dtrs, cudaMemcpyHostToDevice);
     return M;
+}
+
+void* ref_cuda_metric_create_any(const void* dtrs, int n_dtrs, int n_alpha, int n_t, float step_alpha, float step_t, int n_u,
+                                 int n_v, int is_derivative)
+{
+    return ref_cuda_metric_create((const float*)dtrs, n_dtrs, n_alpha, n_t, step_alpha, step_t, n_u, n_v, is_derivative);
 }
 
 void ref_cuda_metric_destroy(void* h)
@@ -240,6 +252,16 @@ double ref_cuda_metric_evaluate(void* h, const int* idx4, int n_pairs, float rad
         }
     }
     return pairs ? sum / pairs : 0.0;
+}
+
+// The K01 records the reference's kernelEpipolarConsistencyComputeK01 left on the device at the last evaluate call
+// (16 floats per pair, EpipolarConsistencyCommon.hxx:92-149).  Returns the number of records copied.
+int ref_cuda_metric_get_k01(void* h, float* K01s_h, int n_pairs)
+{
+    RefMetric* M = (RefMetric*)h;
+    if (!M || !M->K01s_d || (size_t)n_pairs * 16 > M->k01_cap) return -1;
+    CK(cudaMemcpy(K01s_h, M->K01s_d, sizeof(float) * 16 * (size_t)n_pairs, cudaMemcpyDeviceToHost));
+    return n_pairs;
 }
 
 // evaluate() with useCorrelation(true): the launcher accumulates six floats per pair (five weighted sums + the pair

@@ -58,8 +58,20 @@ def oracle():
                                              C.c_double, C.c_double, _f64p]
     L.oracle_project_ellipsoids.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_int, _f32p]
     L.oracle_max_threads.restype = C.c_int
+    L.oracle_set_threads.argtypes = [C.c_int]
+    L.oracle_set_threads.restype = C.c_int
     _oracle = L
     return L
+
+
+def use_all_host_cores():
+    """All host cores this process may run on for the oracle's OpenMP loops, whatever OMP_NUM_THREADS says (torchrun sets
+    it to 1 for its ranks).  Returns the thread count in effect."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return oracle().oracle_set_threads(cores)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -218,6 +230,13 @@ def ref_cuda():
     L.ref_cuda_metric_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                            C.POINTER(C.c_float)]
     L.ref_cuda_metric_evaluate.restype = C.c_double
+    if hasattr(L, "ref_cuda_radon_any"):  # host or device pointers (torch tensors)
+        L.ref_cuda_radon_any.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.POINTER(C.c_float)]
+        L.ref_cuda_metric_create_any.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_cuda_metric_create_any.restype = C.c_void_p
+    if hasattr(L, "ref_cuda_metric_get_k01"):
+        L.ref_cuda_metric_get_k01.argtypes = [C.c_void_p, _f32p, C.c_int]
     if hasattr(L, "ref_cuda_metric_evaluate_corr"):
         L.ref_cuda_metric_evaluate_corr.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
         L.ref_cuda_metric_evaluate_corr.restype = C.c_double
@@ -226,8 +245,19 @@ def ref_cuda():
 
 
 def ref_cuda_radon(images, n_alpha, n_t, filter=0, post=0):
-    """Radon intermediates by the reference CUDA kernel.  Returns (dtrs, gpu_ms)."""
+    """Radon intermediates by the reference CUDA kernel.  Returns (dtrs, gpu_ms).  images: numpy array (host) or a
+    contiguous float32 torch cuda tensor (then the dtrs come back as a cuda tensor)."""
     L = ref_cuda()
+    if hasattr(images, "data_ptr"):
+        import torch
+        assert images.is_cuda and images.is_contiguous() and images.dtype == torch.float32
+        n, n_v, n_u = images.shape
+        out = torch.empty((n, n_t, n_alpha), dtype=torch.float32, device=images.device)
+        ms = C.c_float()
+        torch.cuda.synchronize()
+        rc = L.ref_cuda_radon_any(images.data_ptr(), n, n_u, n_v, n_alpha, n_t, filter, post, out.data_ptr(), C.byref(ms))
+        assert rc == 0
+        return out, ms.value
     images = np.ascontiguousarray(images, np.float32)
     n, n_v, n_u = images.shape
     out = np.zeros((n, n_t, n_alpha), np.float32)
@@ -242,11 +272,19 @@ class RefCudaMetric:
 
     def __init__(self, Ps, dtrs, n_u, n_v, is_derivative=True):
         self.L = ref_cuda()
-        dtrs = np.ascontiguousarray(dtrs, np.float32)
-        m, n_t, n_alpha = dtrs.shape
         diag = np.sqrt(float(n_u) ** 2 + float(n_v) ** 2)
-        self.h = self.L.ref_cuda_metric_create(dtrs, m, n_alpha, n_t, np.float32(np.pi / n_alpha),
-                                               np.float32(diag / n_t), n_u, n_v, int(is_derivative))
+        if hasattr(dtrs, "data_ptr"):  # contiguous float32 torch cuda tensor
+            import torch
+            assert dtrs.is_cuda and dtrs.is_contiguous() and dtrs.dtype == torch.float32
+            m, n_t, n_alpha = dtrs.shape
+            torch.cuda.synchronize()
+            self.h = self.L.ref_cuda_metric_create_any(dtrs.data_ptr(), m, n_alpha, n_t, np.float32(np.pi / n_alpha),
+                                                       np.float32(diag / n_t), n_u, n_v, int(is_derivative))
+        else:
+            dtrs = np.ascontiguousarray(dtrs, np.float32)
+            m, n_t, n_alpha = dtrs.shape
+            self.h = self.L.ref_cuda_metric_create(dtrs, m, n_alpha, n_t, np.float32(np.pi / n_alpha),
+                                                   np.float32(diag / n_t), n_u, n_v, int(is_derivative))
         assert self.h
         self.set_matrices(Ps)
 
@@ -268,6 +306,12 @@ class RefCudaMetric:
             mean = self.L.ref_cuda_metric_evaluate(self.h, idx4.ctypes.data_as(C.c_void_p), idx4.shape[0], radius,
                                                    dkappa, out.ctypes.data_as(C.c_void_p), C.byref(ms))
         return mean, out, ms.value
+
+    def k01(self, n_pairs):
+        """The K01 records (n_pairs, 16) the reference's own kernel computed in the last evaluate call."""
+        K = np.zeros((n_pairs, 16), np.float32)
+        assert self.L.ref_cuda_metric_get_k01(self.h, K, n_pairs) == n_pairs
+        return K
 
     def evaluate_corr(self, radius, dkappa, idx4=None):
         """The reference's correlation variant (useCorrelation(true)).  Returns (mean, out)."""

@@ -14,8 +14,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "facade_check")
 
 
-def build():
-    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp")], check=True, stdout=subprocess.DEVNULL)
+def build(target="facade_check"):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), target], check=True, stdout=subprocess.DEVNULL)
+
+
+def test_launcher_symbols_have_the_reference_signatures():
+    """The reference's unmodified .cpp files link against two C++ symbols (EpipolarConsistencyRadonIntermediate.cpp:16-37,
+    RadonIntermediate.cpp:12); libecc_b200.so must export them with exactly those (mangled) signatures."""
+    lib = os.path.join(ROOT, "epipolarconsistency_b200", "lib", "libecc_b200.so")
+    syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    # _Z19epipolarConsistencyiiiPciiffiPfS0_iPiS0_S0_ffbbS0_ : (int,int,int,char*,int,int,float,float,int,float*,float*,int,int*,float*,float*,float,float,bool,bool,float*)
+    assert " T _Z19epipolarConsistencyiiiPciiffiPfS0_iPiS0_S0_ffbbS0_" in syms
+    # _Z25computeDerivLineIntegralsyiiiiiiPf : (cudaTextureObject_t = unsigned long long,int,int,int,int,int,int,float*)
+    assert " T _Z25computeDerivLineIntegralsyiiiiiiPf" in syms
+    build("launcher_swap_check")  # the reference's declarations, verbatim, link against the library
+
+
+@pytest.mark.gpu
+def test_launcher_swap_gives_the_abi_results(tmp_path):
+    """INTEGRATION.md option B, compiled and run: the reference's call sequence through its own two launcher symbols
+    (cudaArray textures, device handle table, K01s / out / out_corr buffers) gives the C ABI's bits."""
+    build("launcher_swap_check")
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "launcher_swap_check")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK launcher swap" in r.stdout, r.stdout + r.stderr
 
 
 def test_facade_builds_and_cpu_checks(tmp_path):

@@ -75,7 +75,7 @@ def test_radon_texture_vs_reference_cuda(ctx, scene):
         pytest.skip("oracle/_ref/libecc_ref_cuda.so not present")
     ref, _ = ol.ref_cuda_radon(scene["imgs"][:4], scene["n_a"], scene["n_t"])
     got = ctx.radon_compute(scene["imgs"][:4], scene["n_a"], scene["n_t"], interp=api.INTERP_TEXTURE)
-    assert peak_err(got, ref) < RADON_TOL
+    assert np.array_equal(got, ref)  # the texture engine takes the executed reference's samples in its order: same bits
     # the oracle's texture model is pinned by the same comparison
     assert peak_err(scene["dtr_tex"][:4], ref) < ORACLE_TEX_RADON_TOL
 
@@ -274,6 +274,33 @@ def test_all_pairs_texture_vs_oracle_tex8(ctx, scene):
     assert abs(mean - want_mean) / want_mean < ORACLE_TEX_PAIR_TOL
 
 
+def compare_with_racy_reference(got_v, runs_v, K_ours, K_ref, label):
+    """Per-pair comparison with the reference CUDA path, whose all-pairs kernel zeroes out[] from INSIDE the accumulating
+    kernel (EpipolarConsistencyRadonIntermediate.cu:182-189,248-255): atomicAdds that land before that
+    store are lost, so a reference value can only be too LOW, differently from run to run.  runs_v: (runs, pairs) reference
+    values.  Every pair beyond the 1e-3 tolerance must be EXPLAINED: either ours is the higher value (the reference lost
+    updates), or the two implementations did not work with the same K0/K1 maps for that pair (K01 records differ in some
+    bit: the metric is a sum of squared interpolation residuals, one ulp in a line coefficient flips 1/256 weight steps).
+    Returns (ok mask, text)."""
+    ref_max, ref_min = runs_v.max(axis=0), runs_v.min(axis=0)
+    rel = rel_err(got_v, ref_max)
+    ok = rel < PAIR_TOL_REF
+    used = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15]  # K0[7] (an angle nothing reads) left out
+    k_same = np.all(K_ours[:, used].view(np.uint32) == K_ref[:, used].view(np.uint32), axis=1)
+    spread = (ref_max - ref_min) / np.maximum(ref_max, 1e-30)
+    lines = [f"{label}: {len(got_v)} pairs, {int((~ok).sum())} beyond {PAIR_TOL_REF:g} (max {rel.max():.3g}, median {np.median(rel):.3g}); "
+             f"K01 records bit-identical for {int(k_same.sum())} pairs; reference run-to-run spread: max {spread.max():.3g}, "
+             f"{int((spread > 1e-6).sum())} pairs above 1e-6"]
+    for k in np.nonzero(~ok)[0]:
+        lines.append(f"  pair {k}: ours {got_v[k]:.9g} ref max {ref_max[k]:.9g} min {ref_min[k]:.9g} rel {rel[k]:.3g} "
+                     f"{'ours>ref' if got_v[k] > ref_max[k] else 'OURS<REF'} K01 {'same' if k_same[k] else 'differs'}")
+    text = "\n".join(lines)
+    print(text)
+    unexplained = ~ok & ~(got_v > ref_max) & k_same
+    assert not unexplained.any(), text
+    return ok, text
+
+
 def test_all_pairs_texture_vs_reference_cuda(ctx, scene):
     if ol.ref_cuda() is None:
         pytest.skip("oracle/_ref/libecc_ref_cuda.so not present")
@@ -281,17 +308,14 @@ def test_all_pairs_texture_vs_reference_cuda(ctx, scene):
     setup_metric(ctx, scene, scene["dtr_tex"], api.INTERP_TEXTURE)
     cost = np.zeros((n, n), np.float32)
     mean = ctx.evaluate(cost)
+    K_ours = ctx.pair_maps(n_views=n)
     ref = ol.RefCudaMetric(scene["Ps"], scene["dtr_tex"], scene["n_u"], scene["n_v"])
-    # The reference kernel zeroes out[] from inside the accumulating kernel: atomicAdds
-    # that land before that store are lost, so single pairs can come out too LOW, differently from run to run.
-    # Lost updates only ever lower a value: the element-wise maximum over repeated runs is the race-free result.
-    runs = [ref.evaluate(ctx.get_object_radius(), 0.0)[1] for _ in range(8)]
-    ref_out = np.maximum.reduce(runs)
-    got_v, ref_v = pair_values(cost, n), pair_values(ref_out, n)
-    rel = rel_err(got_v, ref_v)
-    ok = rel < PAIR_TOL_REF
-    assert ok.mean() >= 0.9, rel
-    assert np.all(ok | (got_v > ref_v)), rel  # any remaining outlier is a reference pair that lost updates
+    runs = np.stack([pair_values(ref.evaluate(ctx.get_object_radius(), 0.0)[1], n) for _ in range(8)])
+    K_ref = ref.k01(n * (n - 1) // 2)
+    got_v = pair_values(cost, n)
+    ok, text = compare_with_racy_reference(got_v, runs, K_ours, K_ref, "45-pair scene")
+    ref_v = runs.max(axis=0)
+    assert ok.mean() >= 0.95, text
     assert abs(mean - ref_v[ok].mean() * 1.0) / mean < 1e-2
     assert abs(got_v[ok].mean() - ref_v[ok].mean()) / ref_v[ok].mean() < SUM_TOL
     # pin the oracle's texture model against the reference CUDA path as well
@@ -871,3 +895,126 @@ def test_radon_hybrid_static_other_filters_are_the_texture_engine(ctx, scene):
         a = ctx.radon_compute(im, 96, 80, filter=filt, interp=api.INTERP_HYBRID_STATIC)
         b = ctx.radon_compute(im, 96, 80, filter=filt, interp=api.INTERP_TEXTURE)
         assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------
+# north_star's tolerances at BASELINE's full size (1240x960 -> 768x768), directly against the reference's own CUDA kernels
+# and against the CPU float path (round-1 verdict, "next round" item 1)
+# ---------------------------------------------------------------------------------------------------
+BENCH_ELL = np.array([[0.0, 0.0, 0.0, 80.0, 60.0, 70.0, 1.0], [20.0, -10.0, 5.0, 25.0, 30.0, 20.0, 0.6], [-25.0, 15.0, -10.0, 20.0, 22.0, 28.0, -0.5],
+                      [5.0, 30.0, 20.0, 22.0, 20.0, 24.0, 0.8], [-10.0, -30.0, -25.0, 30.0, 21.0, 20.0, -0.7]])  # bench.py's phantom
+
+
+def c3_views(select):
+    """Views of the C3 trajectory (496 on a 200 deg arc, 1240x960, 0.308 mm) by index."""
+    return api.make_circular_trajectory(496, 750.0, 1200.0, 1240, 960, 200.0, 0.308)[select]
+
+
+def test_radon_full_size_every_engine_directly_vs_reference_cuda(ctx):
+    """(a) The engine bench.py times (ECC_INTERP_HYBRID_STATIC, fine double-buffered windows at this bin spacing) and the
+    run-time-queue hybrid, DIRECTLY against the reference's radonDerivative kernel (RadonIntermediate.cu:31-143) at the
+    BASELINE size: every bin within 1e-4 of the peak; the texture engine bit for bit.  Four clean phantom projections
+    (the bench's data) and four with noise on top (rough everywhere, so that a misplaced sample shows)."""
+    import torch
+    if ol.ref_cuda() is None or not hasattr(ol.ref_cuda(), "ref_cuda_radon_any"):
+        pytest.skip("oracle/_ref/libecc_ref_cuda.so not present")
+    n, n_u, n_v, n_a, n_t = 8, 1240, 960, 768, 768
+    Ps = c3_views(np.arange(0, 496, 62))
+    imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
+    ctx.synth_projections(Ps, n_u, n_v, BENCH_ELL, imgs)
+    g = torch.Generator(device="cuda").manual_seed(31)
+    imgs[4:] += 0.05 * torch.rand(imgs[4:].shape, device="cuda", generator=g)
+    ref, _ = ol.ref_cuda_radon(imgs, n_a, n_t)
+    peak = float(ref.abs().max())
+    tex = ctx.radon_compute(imgs, n_a, n_t, interp=api.INTERP_TEXTURE)
+    assert torch.equal(tex, ref), f"texture engine vs reference kernel: {float((tex - ref).abs().max()) / peak:.3g} of the peak"
+    for name, interp in (("hybrid-static", api.INTERP_HYBRID_STATIC), ("hybrid", api.INTERP_HYBRID)):
+        got = ctx.radon_compute(imgs, n_a, n_t, interp=interp)
+        err = (got - ref).abs().amax(dim=(1, 2)) / peak
+        print(f"{name} vs reference CUDA kernel, max |diff| / peak per projection: {[float('%.3g' % e) for e in err]}")
+        assert float(err.max()) < RADON_TOL, name
+        assert torch.equal(got == 0, ref == 0), name  # lines that miss the image: exactly zero in both
+    # the static split: the same bits again, also through the chunked host-image path the end-to-end bench uses
+    a = ctx.radon_compute(imgs, n_a, n_t, interp=api.INTERP_HYBRID_STATIC)
+    b = torch.from_numpy(ctx.radon_compute(imgs.cpu().numpy(), n_a, n_t, interp=api.INTERP_HYBRID_STATIC)).cuda()
+    assert torch.equal(a, b)
+
+
+def test_pairs_full_size_vs_reference_cuda_with_explained_outliers(ctx):
+    """(b) 64 full-size intermediates of the C3 trajectory (32 neighbouring views: long pencils up to 9000 kappa samples,
+    and 32 spread over the arc), dkappa 0.01 deg: per pair within 1e-3 of the reference CUDA path for >= 99.5 % of the
+    pairs, every pair beyond that explained (see compare_with_racy_reference), summed metric within 1e-4."""
+    import torch
+    if ol.ref_cuda() is None or not hasattr(ol.ref_cuda(), "ref_cuda_metric_get_k01"):
+        pytest.skip("oracle/_ref/libecc_ref_cuda.so not present")
+    n_u, n_v, n_a, n_t = 1240, 960, 768, 768
+    sel = np.array(list(range(200, 232)) + list(range(3, 496, 16))[:32])
+    sel.sort()
+    n = len(sel)
+    Ps = c3_views(sel)
+    imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
+    ctx.synth_projections(Ps, n_u, n_v, BENCH_ELL, imgs)
+    dtrs = ctx.radon_compute(imgs, n_a, n_t, interp=api.INTERP_TEXTURE)  # = the reference kernel's bits (test above)
+    del imgs
+    dk = float(np.deg2rad(0.01))
+    ctx.set_interpolation(api.INTERP_TEXTURE)
+    ctx.set_object_radius(0.0)
+    ctx.set_epipolar_plane_step(dk)
+    ctx.set_projection_matrices(Ps)
+    ctx.set_radon_intermediates(dtrs, n_u, n_v, True)
+    cost = np.zeros((n, n), np.float32)
+    mean = ctx.evaluate(cost)
+    K_ours = ctx.pair_maps(n_views=n)
+    counts = ctx.pair_sample_counts(n)
+    assert counts.max() == 9000 and counts.min() < 2000  # both kinds of pencil are in the scene
+    ref = ol.RefCudaMetric(Ps, dtrs, n_u, n_v)
+    radius = ctx.get_object_radius()
+    runs = np.stack([pair_values(ref.evaluate(radius, dk)[1], n) for _ in range(8)])
+    K_ref = ref.k01(n * (n - 1) // 2)
+    ref.close()
+    got_v = pair_values(cost, n)
+    ok, text = compare_with_racy_reference(got_v, runs, K_ours, K_ref, "64 full-size views, dkappa 0.01 deg")
+    assert ok.mean() >= 0.995, text
+    ref_v = runs.max(axis=0)
+    assert rel_err(got_v, ref_v).max() < 1e-2, text  # even a pair that lost updates in all eight runs lost few
+    assert abs(got_v[ok].mean() - ref_v[ok].mean()) / ref_v[ok].mean() < SUM_TOL
+    assert abs(mean - ref_v.mean()) / mean < SUM_TOL
+
+
+def test_default_pipeline_full_size_vs_cpu_float_path(ctx):
+    """(c) north_star: summed metric within 1e-4 relative of the CPU float path.  The bench's default pipeline (static-split
+    hybrid Radon engine + texture-unit pair lookups: 1.8 fixed-point weights in both stages) on a fine scene -- 12
+    full-size views, dkappa 0.01 deg -- against the oracle's exact-fp32 path in both stages; and the exact-weight engines
+    against the same number.  SURVEY.md Appendix C predicted up to 3e-4 for the quantised weights on coarser grids."""
+    import torch
+    n, n_u, n_v, n_a, n_t = 12, 1240, 960, 768, 768
+    Ps = c3_views(np.arange(0, 496, 42)[:n])
+    imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
+    ctx.synth_projections(Ps, n_u, n_v, BENCH_ELL, imgs)
+    imgs_h = imgs.cpu().numpy()
+    dk = float(np.deg2rad(0.01))
+    ol.use_all_host_cores()
+    want_dtr = np.stack([ol.radon(im, n_a, n_t, interp=ol.INTERP_EXACT) for im in imgs_h])
+    want_mean, want, _ = ol.ecc(Ps, want_dtr, n_u, n_v, dkappa=dk, interp=ol.INTERP_EXACT)
+    want_v = pair_values(want, n)
+    results = {}
+    for name, radon_interp, pair_interp in (("default (hybrid-static + texture)", api.INTERP_HYBRID_STATIC, api.INTERP_TEXTURE),
+                                            ("texture + texture", api.INTERP_TEXTURE, api.INTERP_TEXTURE),
+                                            ("exact + exact", api.INTERP_EXACT, api.INTERP_EXACT)):
+        dtrs = ctx.radon_compute(imgs, n_a, n_t, interp=radon_interp)
+        ctx.set_interpolation(pair_interp)
+        ctx.set_object_radius(0.0)
+        ctx.set_epipolar_plane_step(dk)
+        ctx.set_projection_matrices(Ps)
+        ctx.set_radon_intermediates(dtrs, n_u, n_v, True)
+        cost = np.zeros((n, n), np.float32)
+        mean = ctx.evaluate(cost)
+        bins = float(np.abs(dtrs.cpu().numpy() - want_dtr).max() / np.abs(want_dtr).max())
+        results[name] = (abs(mean - want_mean) / want_mean, float(rel_err(pair_values(cost, n), want_v).max()), bins)
+        print(f"{name}: summed metric {results[name][0]:.3g}, worst pair {results[name][1]:.3g}, worst bin {bins:.3g} of the peak (vs oracle exact fp32)")
+    assert results["exact + exact"][0] < SUM_TOL and results["exact + exact"][1] < PAIR_TOL_EXACT and results["exact + exact"][2] < RADON_TOL
+    # quantised weights (the reference CUDA path's numerics) against the CPU float path: the sum agrees to 1e-4, single
+    # pairs and bins differ by the quantisation (SURVEY.md Appendix C), which is why north_star compares those with the CUDA path
+    assert results["default (hybrid-static + texture)"][0] < SUM_TOL
+    assert results["texture + texture"][0] < SUM_TOL
+    assert abs(results["default (hybrid-static + texture)"][0] - results["texture + texture"][0]) < 2e-5
