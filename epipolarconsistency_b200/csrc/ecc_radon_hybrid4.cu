@@ -131,14 +131,21 @@ __device__ __forceinline__ void bin_texture4(cudaTextureObject_t tex, const BinL
 
 // ---- packed fp32 pairs (sm_100: add / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2) ----------------------------------------
 // The window path's per-image filter arithmetic is the same eight IEEE operations for each of the four interleaved
-// images; Blackwell executes them two images per instruction.  Each lane of a packed operation is the separately rounded
-// fp32 operation (round to nearest), so the results are those of the scalar code bit for bit -- what changes is the
-// number of issue slots: 16 instead of 32 per sample position.  -DECC_F32X2=0 keeps the scalar form (A/B, same bits).
+// images; Blackwell executes them two images per instruction.  Each half of a packed operation is the separately rounded
+// fp32 operation (round to nearest), so the results are those of the scalar code bit for bit (checked: same checksums as
+// the scalar build for every split) -- what changes is the number of issue slots per sample position.
+//   ECC_F32X2 = 0  scalar (round 1): 113 instructions per loop iteration (two positions x four images)
+//   ECC_F32X2 = 1  filter AND running sums packed: 90 (ptxas moves the 64-bit running sums back after every sample)
+//   ECC_F32X2 = 2  filter packed, running sums scalar: 86 -- the default
+// Measured on B200 (C2 size, ms/projection, run-time queue / window warps only; tools/radon_ab.sh, profiles/radon_ab_r02.txt):
+//   scalar 0.564 / 0.898,  mode 1 0.575 / 0.927,  mode 2 0.560 / 0.889.
+// A quarter fewer instructions buy under 1 %: the window path is bound by shared-memory wavefronts (4 x LDS.128 per
+// position, 1.39 wavefronts per conflict-free one), not by issue slots.
 #ifndef ECC_F32X2
-#define ECC_F32X2 1
+#define ECC_F32X2 2
 #endif
-#ifndef ECC_WINDOW_UNROLL  // unroll factor of the window path's sample loop (2: the packed running sums ping-pong between
-#define ECC_WINDOW_UNROLL 2  // register pairs instead of being moved back after every sample)
+#ifndef ECC_WINDOW_UNROLL  // unroll factor of the window path's sample loop (2 changes nothing measurable: 0.561 / 0.893)
+#define ECC_WINDOW_UNROLL 1
 #endif
 constexpr int kWindowUnroll = ECC_WINDOW_UNROLL;
 typedef unsigned long long f32x2;

@@ -75,3 +75,48 @@ int ref_nrrd_save(const char* path, const float* data, int w, int h, const char*
 }
 
 }  // extern "C"
+
+// ---- pre-processing pieces the reference keeps in headers: the separable Gaussian low-pass
+// (HeaderOnly/NRRD/nrrd_lowpass.hxx: gaussianKernel :18-33, convolve2D :46-79 incl. its tap range -k .. k-1, lowpass2D :186-192)
+// and the feathering weight weighting() (LibEpipolarConsistency/EpipolarConsistencyCommon.hxx:30-35).  PreProccess.cpp itself
+// needs GetSet and Eigen and cannot be compiled here; its four border loops are restated below around the reference's own
+// weighting(), expression for expression (Gui/PreProccess.cpp:88-108).
+#include <NRRD/nrrd_lowpass.hxx>
+
+extern "C" {
+
+int ref_gaussian_kernel(double sigma, int k, double* out)
+{
+    std::vector<double> g = NRRD::gaussianKernel(sigma, k);
+    for (size_t i = 0; i < g.size(); i++) out[i] = g[i];
+    return (int)g.size();
+}
+
+// In place, exactly what PreProccess::process calls (Gui/PreProccess.cpp:139-140).
+void ref_lowpass2d(float* data, int w, int h, double sigma, int k)
+{
+    NRRD::ImageView<float> img(w, h, 1, data);
+    NRRD::lowpass2D(img, sigma, k);
+}
+
+float ref_weighting(float x) { return weighting(x); }
+
+// zero[4] / feather[4]: left, right, bottom, top (Gui/PreProccess.cpp:88-108)
+void ref_border(float* data, int w, int h, const int* zero, const int* feather)
+{
+    NRRD::ImageView<float> img(w, h, 1, data);
+    for (int y = 0; y < img.size(1); y++)
+        for (int b = 0; b < zero[0] + feather[0]; b++)
+            img.pixel(b, y, 0) *= b <= zero[0] ? 0 : (float)weighting(1 - (float)(b - zero[0]) / feather[0]);
+    for (int y = 0; y < img.size(1); y++)
+        for (int b = 1; b <= zero[1] + feather[1]; b++)
+            img.pixel(img.size(0) - b, y, 0) *= b <= zero[1] ? 0 : (float)weighting(1 - (float)(b - zero[1]) / feather[1]);
+    for (int b = 1; b <= zero[2] + feather[2]; b++)
+        for (int x = 0; x < img.size(0); x++)
+            img.pixel(x, img.size(1) - b, 0) *= b <= zero[2] ? 0 : (float)weighting(1 - (float)(b - zero[2]) / feather[2]);
+    for (int b = 0; b < zero[3] + feather[3]; b++)
+        for (int x = 0; x < img.size(0); x++)
+            img.pixel(x, b, 0) *= b <= zero[3] ? 0 : (float)weighting(1 - (float)(b - zero[3]) / feather[3]);
+}
+
+}  // extern "C"

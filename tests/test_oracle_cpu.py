@@ -259,3 +259,48 @@ def test_preprocess_restatement_invariants():
     assert abs(u0 - 0.5 * n_u) < 1e-6 and abs(v0 - 0.5 * n_v) < 1e-6 and abs(fu - f_traj) < 1e-9 * fu
     w = ol.preprocess(np.ones((n_v, n_u), np.float32), sigma=0.0, zero=(0, 0, 0, 0), P=P)
     assert abs(w[n_v // 2, n_u // 2] - 1.0) < 1e-6 and w[0, 0] < w[n_v // 2, n_u // 2]
+
+
+# ---- pre-processing (row N3) pinned by the reference's own headers ----------------------------------------------------------
+PRE_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_preprocess_vectors.npz")
+
+
+def test_preprocess_oracle_pinned_by_reference_headers():
+    """tests/golden/ref_preprocess_vectors.npz holds outputs of the reference's NRRD::gaussianKernel / lowpass2D and of its
+    weighting() inside the border loops of PreProccess::process (generator: tests/golden/make_ref_preprocess_vectors.py).
+    The numpy restatement in oracle_lib reproduces them BIT FOR BIT: same taps (-k .. k-1: the last tap is missing in the
+    reference), same clamping, fp64 sums stored as float, fp32 feathering weights."""
+    g = np.load(PRE_GOLDEN)
+    for q, (sigma, k) in enumerate(g["kernel_cases"]):
+        k = int(k)
+        kern = np.exp(-0.5 * (np.arange(-k, k + 1) / sigma) ** 2)
+        kern /= kern.sum()
+        assert np.allclose(kern, g[f"kernel_{q}"], rtol=1e-15, atol=0)
+    for x, y in zip(g["weighting_x"], g["weighting_y"]):
+        assert ol._feather(x) == y
+    assert g["weighting_y"][0] == 0 and g["weighting_y"][50] == 1 and g["weighting_y"][-1] == 0
+    img = g["lowpass_in"]
+    for q, (sigma, k) in enumerate(g["lowpass_cases"]):
+        got = ol.preprocess(img, zero=(0, 0, 0, 0), feather=(0, 0, 0, 0), sigma=float(sigma), k=int(k))
+        want = g[f"lowpass_out_{q}"]
+        # the border "zero = 0, feather = 0" still clears nothing; what is left is the low-pass alone
+        assert np.array_equal(got, want), float(np.abs(got - want).max())
+    bimg = g["border_in"]
+    for q, (zero, feather) in enumerate(g["border_cases"]):
+        got = ol.preprocess(bimg, zero=tuple(int(z) for z in zero), feather=tuple(int(f) for f in feather), sigma=0.0)
+        assert np.array_equal(got, g[f"border_out_{q}"]), q
+
+
+def test_preprocess_golden_matches_live_reference_build():
+    """Where oracle/_ref is built (this container), the committed vectors are what the reference's headers give today."""
+    R = ol.ref_host()
+    if R is None or not hasattr(R, "ref_lowpass2d"):
+        import pytest
+        pytest.skip("oracle/_ref/libecc_ref_host.so (with the pre-processing entry points) not built")
+    import ctypes as C
+    g = np.load(PRE_GOLDEN)
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    R.ref_lowpass2d.argtypes = [f32p, C.c_int, C.c_int, C.c_double, C.c_int]
+    work = g["lowpass_in"].copy()
+    R.ref_lowpass2d(work, work.shape[1], work.shape[0], 1.84, 5)
+    assert np.array_equal(work, g["lowpass_out_0"])
