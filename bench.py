@@ -178,7 +178,7 @@ def perturbed_sets(api, Ps, K, rng, sigma_px=0.5, sigma_mm=0.5, sigma_deg=0.2):
     x[:, :, 4:7] = rng.normal(0, sigma_mm, (K, n, 3))
     x[:, :, 7:10] = np.deg2rad(rng.normal(0, sigma_deg, (K, n, 3)))
     x[0] = 0.0
-    sets = np.stack([np.stack([api.camera_similarity_2d3d(Ps[i], x[k, i]) for i in range(n)]) for k in range(K)])
+    sets = np.stack([np.stack([api.model_camera_similarity_2d3d(Ps[i], x[k, i]) for i in range(n)]) for k in range(K)])
     return sets, x
 
 
@@ -450,7 +450,7 @@ def run_batch(B):
 
     def step_host(i):
         if use_params:  # K x n parameter vectors in, expanded to matrices on the device
-            return pipe.evaluate_batch_params(B.Ps, params[i % 3]) if hasattr(pipe, "evaluate_batch_params") else ctx.evaluate_batch_params(B.Ps, params[i % 3])
+            return pipe.evaluate_batch_params(B.Ps, params[i % 3])
         return pipe.evaluate_batch(batches[i % 3][0])
 
     for i in range(B.warmup):

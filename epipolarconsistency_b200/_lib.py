@@ -47,6 +47,12 @@ SIGNATURES = {
     "ecc_pair_signals": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ecc_pair_maps": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp]),
+    "ecc_model_similarity_2d": (None, [c_vp, c_vp]),
+    "ecc_model_similarity_3d": (None, [c_vp, c_vp]),
+    "ecc_model_transform": (None, [c_vp, c_vp, c_vp, c_vp]),
+    "ecc_model_camera_similarity_2d3d": (None, [c_vp, c_vp, c_vp]),
+    "ecc_evaluate_batch_params": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "ecc_model_expand": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "ecc_pair_sample_counts": (C.c_int, [c_ctx, c_vp]),
     "ecc_partition_pairs": (C.c_int, [c_ctx, C.c_int, c_vp]),
     "ecc_team_create": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),

@@ -232,6 +232,36 @@ class Context:
                                                 _ptr(means, _F64)))
         return means
 
+    def evaluate_batch_params(self, base_Ps, params, view_to_param=None, idx4=None, out=None, want_means=True):
+        """Batched mode fed with parameter vectors: params (K, m, 11) model instances (ModelCameraSimilarity2D3D) applied to
+        the base matrices (n, 12) -- None = the current set -- on the device.  view_to_param (n,) int32: instance of a set
+        that moves view v, negative = none; None = one instance per view (m == n, ModelFDCT).  Returns the K means."""
+        if isinstance(params, np.ndarray):
+            params = np.ascontiguousarray(params, np.float64)
+        K, m = params.shape[0], params.shape[1]
+        if base_Ps is not None and isinstance(base_Ps, np.ndarray):
+            base_Ps = np.ascontiguousarray(base_Ps, np.float64).reshape(-1, 12)
+        if view_to_param is not None and isinstance(view_to_param, np.ndarray):
+            view_to_param = np.ascontiguousarray(view_to_param, np.int32)
+        n_pairs = 0 if idx4 is None else idx4.shape[0]
+        means = np.zeros(K, np.float64) if want_means else None
+        self._check(self.lib.ecc_evaluate_batch_params(self.h, _ptr(base_Ps, _F64), _ptr(params, _F64), K, m, _ptr(view_to_param, _I32),
+                                                       _ptr(idx4, _I32), n_pairs, _ptr(out, _F32), _ptr(means, _F64)))
+        return means
+
+    def model_expand(self, base_Ps, params, view_to_param=None, n_views=None):
+        """The matrices (K, n, 12) the device expands from params (K, m, 11): see evaluate_batch_params."""
+        params = np.ascontiguousarray(params, np.float64)
+        K, m = params.shape[0], params.shape[1]
+        if base_Ps is not None:
+            base_Ps = np.ascontiguousarray(base_Ps, np.float64).reshape(-1, 12)
+            n_views = base_Ps.shape[0]
+        if view_to_param is not None:
+            view_to_param = np.ascontiguousarray(view_to_param, np.int32)
+        out = np.zeros((K, n_views, 12), np.float64)
+        self._check(self.lib.ecc_model_expand(self.h, _ptr(base_Ps, _F64), _ptr(params, _F64), K, m, _ptr(view_to_param, _I32), _ptr(out, _F64)))
+        return out
+
     def pair_signals(self, i, j, dtr_i=None, dtr_j=None):
         """evaluateForImagePair (EpipolarConsistencyRadonIntermediate.cpp:324-393): the redundant signals of one pair in
         ascending kappa.  Returns dict(kappas, signal0, signal1, lines0, lines1, weight, value)."""
@@ -399,6 +429,32 @@ def camera_similarity_2d3d(P, x):
     P and the result are 12 doubles, column-major 3x4."""
     P = np.asarray(P, np.float64).reshape(4, 3).T
     return (similarity_2d(x[:4]) @ P @ similarity_3d(x[4:])).T.reshape(12)
+
+
+def model_similarity_2d(x):
+    """ModelSimilarity2D::getInstance as the LIBRARY computes it on host and device (own sine / cosine, no fused
+    multiply-add; similarity_2d above is the independent numpy restatement).  Returns 3x3."""
+    x = np.ascontiguousarray(x, np.float64).reshape(4)
+    H = np.zeros(9, np.float64)
+    _lib.load().ecc_model_similarity_2d(_ptr(x), _ptr(H))
+    return H.reshape(3, 3).T.copy()
+
+
+def model_similarity_3d(x):
+    """ModelSimilarity3D::getInstance as the library computes it.  Returns 4x4."""
+    x = np.ascontiguousarray(x, np.float64).reshape(7)
+    T = np.zeros(16, np.float64)
+    _lib.load().ecc_model_similarity_3d(_ptr(x), _ptr(T))
+    return T.reshape(4, 4).T.copy()
+
+
+def model_camera_similarity_2d3d(P, x):
+    """ModelCameraSimilarity2D3D::getInstance as the library computes it on host and device: 12 doubles, column-major."""
+    P = np.ascontiguousarray(P, np.float64).reshape(12)
+    x = np.ascontiguousarray(x, np.float64).reshape(11)
+    out = np.zeros(12, np.float64)
+    _lib.load().ecc_model_camera_similarity_2d3d(_ptr(P), _ptr(x), _ptr(out))
+    return out
 
 
 def derive_views_host(Ps):

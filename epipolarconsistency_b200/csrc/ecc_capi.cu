@@ -925,18 +925,16 @@ int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const 
     return ECC_OK;
 }
 
-int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, const int* idx4, int n_pairs, float* out,
-                       double* means)
+}  // extern "C"
+
+// Batched evaluation, common parts: the pair list of the launch ...
+int eccb200::batch_begin(ecc_context* ctx, const int* idx4, int n_pairs, PairLaunch& L, const char* who)
 {
-    if (!ctx) return ECC_ERR_INVALID;
-    Guard g(ctx);
-    if (!Ps_sets || n_sets < 1) return fail(ctx, ECC_ERR_INVALID, "ecc_evaluate_batch: bad argument");
-    PairLaunch L;
     int rc = fill_launch(ctx, L);
     if (rc) return rc;
     const long long n = ctx->n_views;
     if (idx4) {
-        if (n_pairs < 1) return fail(ctx, ECC_ERR_INVALID, "ecc_evaluate_batch: empty pair list");
+        if (n_pairs < 1) return fail(ctx, ECC_ERR_INVALID, std::string(who) + ": empty pair list");
         if ((rc = check_indices(ctx, idx4, n_pairs))) return rc;
         if ((rc = stage_indices(ctx, idx4, n_pairs, &L.idx4_d))) return rc;
         L.n_pairs = n_pairs;
@@ -944,16 +942,42 @@ int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, cons
         if (ctx->n_dtrs < ctx->n_views) return fail(ctx, ECC_ERR_STATE, "all-pairs evaluation needs one dtr per projection matrix");
         L.n_pairs = n * (n - 1) / 2;
     }
+    return ECC_OK;
+}
+
+// ... room for the derived views of n_sets matrix sets (every set gets the object radius the reference would derive from
+// that set's first matrix) ...
+int eccb200::batch_reserve(ecc_context* ctx, int n_sets, bool want_matrices)
+{
     BatchBuffers& B = ctx->batch;
-    // every set gets the object radius the reference would derive from that set's first matrix
+    const size_t count = (size_t)n_sets * ctx->n_views;
     if (B.radii_cap < (size_t)n_sets) {
         ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (B.radii_d) cudaFree(B.radii_d);
         B.radii_d = nullptr;
+        B.radii_cap = 0;
         ECC_CUDA(ctx, cudaMalloc(&B.radii_d, sizeof(float) * n_sets));
         B.radii_cap = n_sets;
     }
-    if ((rc = upload_and_derive(ctx, Ps_sets, (size_t)n_sets * n, &B.Ps_d, &B.Cs_d, &B.A_d, &B.cap, (int)n, B.radii_d))) return rc;
+    if (B.cap < count || (want_matrices && !B.Ps_d)) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (B.Ps_d) cudaFree(B.Ps_d);
+        if (B.Cs_d) cudaFree(B.Cs_d);
+        if (B.A_d) cudaFree(B.A_d);
+        B.Ps_d = nullptr; B.Cs_d = nullptr; B.A_d = nullptr; B.cap = 0;
+        ECC_CUDA(ctx, cudaMalloc(&B.Ps_d, sizeof(double) * 12 * count));
+        ECC_CUDA(ctx, cudaMalloc(&B.Cs_d, sizeof(float) * 4 * count));
+        ECC_CUDA(ctx, cudaMalloc(&B.A_d, sizeof(float) * 12 * count));
+        B.cap = count;
+    }
+    return ECC_OK;
+}
+
+// ... and launch, sums, downloads once the batch buffers hold the derived views of all sets.
+int eccb200::batch_finish(ecc_context* ctx, PairLaunch& L, int n_sets, float* out, double* means)
+{
+    BatchBuffers& B = ctx->batch;
+    int rc;
     L.radii_d = B.radii_d;
     L.Cs_d = B.Cs_d;
     L.PinvTs_d = B.A_d;
@@ -988,6 +1012,26 @@ int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, cons
         if (host_out) std::memcpy(out, vals_h, sizeof(float) * items);
     }
     return ECC_OK;
+}
+
+extern "C" {
+
+int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, const int* idx4, int n_pairs, float* out,
+                       double* means)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (!Ps_sets || n_sets < 1) return fail(ctx, ECC_ERR_INVALID, "ecc_evaluate_batch: bad argument");
+    PairLaunch L;
+    int rc = batch_begin(ctx, idx4, n_pairs, L, "ecc_evaluate_batch");
+    if (rc) return rc;
+    if ((rc = batch_reserve(ctx, n_sets, true))) return rc;
+    BatchBuffers& B = ctx->batch;
+    const size_t count = (size_t)n_sets * ctx->n_views;
+    ECC_CUDA(ctx, cudaMemcpyAsync(B.Ps_d, Ps_sets, sizeof(double) * 12 * count, cudaMemcpyDefault, ctx->stream));
+    if ((rc = launch_derive_views(ctx, B.Ps_d, (int)count, B.A_d, B.Cs_d, ctx->n_views, ctx->n_u, ctx->n_v, ctx->object_radius, B.radii_d)))
+        return rc;
+    return batch_finish(ctx, L, n_sets, out, means);
 }
 
 int ecc_pair_signals(ecc_context* ctx, int p0, int p1, int dtr0, int dtr1, int capacity, float* kappas, float* signal0,

@@ -275,6 +275,11 @@ int launch_derive_views(ecc_context* ctx, const double* Ps_d, int n, float* Pinv
                         int views_per_set = 0, int n_u = 0, int n_v = 0, double fixed_radius = 0.0,
                         float* radii_d = nullptr);
 
+// ---- batched evaluation, the parts ecc_evaluate_batch and ecc_evaluate_batch_params share (ecc_capi.cu) ----
+int batch_begin(ecc_context* ctx, const int* idx4, int n_pairs, PairLaunch& L, const char* who);
+int batch_reserve(ecc_context* ctx, int n_sets, bool want_matrices);
+int batch_finish(ecc_context* ctx, PairLaunch& L, int n_sets, float* out, double* means);
+
 // ---- launchers (ecc_radon.cu) ----
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
                 int n_alpha, int n_t, int filter, int post, int interp, float* out_d);

@@ -140,6 +140,20 @@ class ShardedPipeline:
         bounds = shard_bounds(K, self.world)
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         mine = self.c.evaluate_batch(Ps_sets[lo:hi], idx4=idx4) if hi > lo else np.zeros(0, np.float64)
+        return self._gather_means(mine, bounds)
+
+    def evaluate_batch_params(self, base_Ps, params, view_to_param=None, idx4=None):
+        """The same with PARAMETER VECTORS (K, m, 11) instead of matrices: each rank expands its block of sets to matrices on
+        its own device (ecc_evaluate_batch_params); only the K means travel."""
+        K = params.shape[0]
+        bounds = shard_bounds(K, self.world)
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        mine = (self.c.evaluate_batch_params(base_Ps, params[lo:hi], view_to_param=view_to_param, idx4=idx4)
+                if hi > lo else np.zeros(0, np.float64))
+        return self._gather_means(mine, bounds)
+
+    def _gather_means(self, mine, bounds):
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
         if self.world == 1:
             return np.asarray(mine, np.float64)
         import torch

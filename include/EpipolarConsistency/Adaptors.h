@@ -5,6 +5,10 @@
 //   EpipolarConsistency::SingleImageMotion      LibEpipolarConsistency/Gui/SingleImageMotion.h:13-92
 //   EpipolarConsistency::Registration           LibEpipolarConsistency/Gui/Registration.h:13-93
 //   EpipolarConsistency::Registration3D3D       tools/Registration/Registration3D3D.hxx:13-115
+//   Geometry::ModelFDCT                          tools/FDCTMotionCorrection/ModelFDCT.hxx:26-62 (one 2D/3D similarity per view)
+//   EpipolarConsistency::FDCTMoCo                LibEpipolarConsistency/Gui/FDCTMotionCorrection.hxx:13-98
+// The models are evaluated by the library (ecc_model_*: one fp64 operation sequence for host and device), so that a matrix
+// built here is bit for bit the matrix the device expands from the same parameter vector (evaluateBatchParams).
 // Same class names, constructor arguments (minus the LibOpterix parameter-model reference: LibOpterix/NLopt are the
 // optimiser shell, out of scope) and evaluate() semantics.  What the B200 path adds is what the reference's loops
 // lack: a changed view re-derives ONE matrix instead of all, only the pairs that involve the
@@ -14,6 +18,8 @@
 #define ECC_FACADE_ADAPTORS_H
 
 #include <cmath>
+#include <set>
+#include <stdexcept>
 #include <vector>
 
 #include "EpipolarConsistencyRadonIntermediate.h"
@@ -40,22 +46,8 @@ struct Homography3D {
 template <class PM>
 inline PM transformProjection(const Homography2D& H, const PM& P, const Homography3D& T)
 {
-    double HP[12];
-    const double* p = P.data();
-    for (int c = 0; c < 4; c++)
-        for (int r = 0; r < 3; r++) {
-            double s = 0;
-            for (int k = 0; k < 3; k++) s += H(r, k) * p[k + 3 * c];
-            HP[r + 3 * c] = s;
-        }
     PM out = P;
-    double* o = out.data();
-    for (int c = 0; c < 4; c++)
-        for (int r = 0; r < 3; r++) {
-            double s = 0;
-            for (int k = 0; k < 4; k++) s += HP[r + 3 * k] * T(k, c);
-            o[r + 3 * c] = s;
-        }
+    ecc_model_transform(H.data(), P.data(), T.data(), out.data());
     return out;
 }
 
@@ -65,17 +57,8 @@ struct ModelSimilarity2D {
     ModelSimilarity2D() : current_values(4, 0.0) {}
     Homography2D getInstance() const
     {
-        const std::vector<double>& x = current_values;
         Homography2D H;
-        if (x[2] != 0) {
-            H(0, 0) = +std::cos(x[2]); H(0, 1) = -std::sin(x[2]);
-            H(1, 0) = +std::sin(x[2]); H(1, 1) = +std::cos(x[2]);
-        }
-        H(0, 2) = x[0];
-        H(1, 2) = x[1];
-        if (x[3] != 0)
-            for (int r = 0; r < 2; r++)
-                for (int c = 0; c < 2; c++) H(r, c) *= (1.0 + x[3]);
+        ecc_model_similarity_2d(current_values.data(), H.m);
         return H;
     }
 };
@@ -86,34 +69,8 @@ struct ModelSimilarity3D {
     ModelSimilarity3D() : current_values(7, 0.0) {}
     Homography3D getInstance() const
     {
-        const std::vector<double>& x = current_values;
         Homography3D T;
-        if (x[3] != 0 || x[4] != 0 || x[5] != 0) {
-            const double cx = std::cos(x[3]), sx = std::sin(x[3]), cy = std::cos(x[4]), sy = std::sin(x[4]);
-            const double cz = std::cos(x[5]), sz = std::sin(x[5]);
-            const double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};  // row-major
-            const double Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
-            const double Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
-            double A[9], R[9];
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) {
-                    A[3 * r + c] = 0;
-                    for (int k = 0; k < 3; k++) A[3 * r + c] += Rx[3 * r + k] * Ry[3 * k + c];
-                }
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) {
-                    R[3 * r + c] = 0;
-                    for (int k = 0; k < 3; k++) R[3 * r + c] += A[3 * r + k] * Rz[3 * k + c];
-                }
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) T(r, c) = R[3 * r + c];
-        }
-        T(0, 3) = x[0];
-        T(1, 3) = x[1];
-        T(2, 3) = x[2];
-        if (x[6] != 0)
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) T(r, c) *= (1.0 + x[6]);
+        ecc_model_similarity_3d(current_values.data(), T.m);
         return T;
     }
 };
@@ -121,10 +78,41 @@ struct ModelSimilarity3D {
 /// P' = H2D * P * T3D; parameter vector = the four 2D parameters followed by the seven 3D ones.
 class ModelCameraSimilarity2D3D {
     ProjectionMatrix P;
+    std::set<int> active_parameters;  // LibOpterix::ParameterModel::active_parameters (LibOpterix/ParameterModel.hxx:60-66)
 
 public:
     std::vector<double> current_values;
-    explicit ModelCameraSimilarity2D3D(const ProjectionMatrix& _P) : P(_P), current_values(11, 0.0) {}
+    /// All eleven parameters active.
+    explicit ModelCameraSimilarity2D3D(const ProjectionMatrix& _P) : P(_P), current_values(11, 0.0)
+    {
+        for (int i = 0; i < 11; i++) active_parameters.insert(i);
+    }
+    /// As the reference's constructor (ModelCameraSimilarity2D3D.hxx:60-63): the set of parameters an optimiser may change.
+    ModelCameraSimilarity2D3D(const ProjectionMatrix& _P, const std::set<int>& _active) : P(_P), active_parameters(_active), current_values(11, 0.0)
+    {
+        for (std::set<int>::const_iterator it = _active.begin(); it != _active.end(); ++it)
+            if (*it < 0 || *it >= 11) throw std::invalid_argument("Parametrization::Model: Set of active parameters contains invalid indices.");
+    }
+    int numberOfParameters() const { return 11; }
+    int numberOfParametersActive() const { return (int)active_parameters.size(); }
+    const std::set<int>& activeParameters() const { return active_parameters; }
+    /// Active entries of current_values (ParameterModel::restrict, LibOpterix/ParameterModel.hxx:89-96).
+    std::vector<double> restrict() const
+    {
+        std::vector<double> x;
+        for (std::set<int>::const_iterator it = active_parameters.begin(); it != active_parameters.end(); ++it) x.push_back(current_values[*it]);
+        return x;
+    }
+    /// Writes x_active into the active entries (ParameterModel::expand, LibOpterix/ParameterModel.hxx:98-108).
+    std::vector<double>& expand(const double* x_active = 0x0)
+    {
+        if (x_active) {
+            int a = 0;
+            for (std::set<int>::const_iterator it = active_parameters.begin(); it != active_parameters.end(); ++it, ++a) current_values[*it] = x_active[a];
+        }
+        return current_values;
+    }
+    const ProjectionMatrix& getOriginalProjectionMatrix() const { return P; }
     void setOriginalProjectionMatrix(const ProjectionMatrix& _P)
     {
         P = _P;
@@ -149,6 +137,62 @@ public:
         ModelCameraSimilarity2D3D tmp(P);
         tmp.current_values = x;
         return tmp.getInstance();
+    }
+};
+
+/// Parametrization of motion correction for FDCT (tools/FDCTMotionCorrection/ModelFDCT.hxx:9-64): every projection gets
+/// its own instance of the stencil model; the raw parameter vector stacks the ACTIVE parameters view by view.
+struct ModelFDCT {
+    ModelCameraSimilarity2D3D stencil;  //< All projection matrices will abide to this model
+    int n_active;                       //< Number of active parameters in stencil
+    int n_proj;                         //< Number of projections
+    std::vector<double> params;         //< Raw parameter vector (remains constant)
+    std::vector<double> params_delta;   //< Raw parameter vector plus those currently being changed
+    std::vector<ProjectionMatrix> trajectory;  //< current estimate of the trajectory
+
+    explicit ModelFDCT(const ModelCameraSimilarity2D3D& _stencil) : stencil(_stencil), n_active(_stencil.numberOfParametersActive()), n_proj(0) {}
+
+    /// Apply parameter vector for view i.  If view < 0, all parameters will be updated (ModelFDCT.hxx:26-62).
+    std::vector<ProjectionMatrix>& applyModel(int view, const double* delta, const std::vector<ProjectionMatrix>& Ps)
+    {
+        stack(view, delta, (int)Ps.size());
+        if ((int)trajectory.size() != n_proj) trajectory.resize(n_proj);
+        for (int i = 0; i < n_proj; i++) {
+            ModelCameraSimilarity2D3D HTi = stencil;
+            HTi.setOriginalProjectionMatrix(Ps[i]);
+            HTi.expand(&params_delta[(size_t)i * n_active]);
+            trajectory[i] = HTi.getInstance();
+        }
+        return trajectory;
+    }
+
+    /// The same parameter stacking, expanded to the eleven model parameters per view: the input of the device-side
+    /// expansion (MetricRadonIntermediate::evaluateBatchParams, FDCTMoCo::evaluateTrajectories).  Appends n_proj * 11 doubles.
+    void appendExpanded(int view, const double* delta, int n_views, std::vector<double>& out)
+    {
+        stack(view, delta, n_views);
+        for (int i = 0; i < n_proj; i++) {
+            ModelCameraSimilarity2D3D HTi = stencil;
+            HTi.current_values.assign(11, 0.0);
+            const std::vector<double>& x = HTi.expand(&params_delta[(size_t)i * n_active]);
+            out.insert(out.end(), x.begin(), x.end());
+        }
+    }
+
+private:
+    void stack(int view, const double* delta, int n_views)
+    {
+        n_proj = n_views;
+        const size_t len = (size_t)n_proj * n_active;
+        if (params.size() != len) params.assign(len, 0.0);
+        params_delta.assign(len, 0.0);
+        if (delta) {
+            if (view < 0)
+                for (size_t i = 0; i < len; i++) params_delta[i] = delta[i];
+            else
+                for (int i = 0; i < n_active; i++) params_delta[(size_t)view * n_active + i] = delta[i];
+        }
+        for (size_t i = 0; i < len; i++) params_delta[i] += params[i];
     }
 };
 
@@ -358,6 +402,47 @@ public:
         std::vector<std::vector<ProjectionMatrix> > sets;
         for (size_t k = 0; k < Ts.size(); k++) sets.push_back(transformed(Ts[k]));
         return ecc.evaluateBatch(sets, &indices);
+    }
+};
+
+/// Motion correction of an FDCT trajectory (Gui/FDCTMotionCorrection.hxx:13-98): as SingleImageMotion, the cost of a
+/// candidate matrix for the input image is the mean over ALL pairs (the reference's evaluate() returns ecc->evaluate()).
+/// What the B200 path adds: K candidate parameter vectors of a ModelFDCT -- each n x n_active doubles, the whole
+/// trajectory perturbed -- scored in ONE launch, expanded to matrices on the device (BASELINE config C4).
+class FDCTMoCo : public SingleImageMotion {
+public:
+    FDCTMoCo(std::vector<ProjectionMatrix> _Ps, std::vector<RadonIntermediate*> _dtrs, int _input_index = 0)
+        : SingleImageMotion(_Ps, _dtrs, _input_index)
+    {}
+
+    /// Means over all pairs for K candidate parameter vectors (candidates[k]: n * model.n_active doubles, view by view, as
+    /// ModelFDCT::applyModel(-1, ...) takes them), applied to the initial matrices.  One launch; no matrix is built on the host.
+    std::vector<double> evaluateTrajectories(Geometry::ModelFDCT& model, const std::vector<std::vector<double> >& candidates)
+    {
+        std::vector<double> params;
+        const int n = (int)Ps.size();
+        for (size_t k = 0; k < candidates.size(); k++) model.appendExpanded(-1, candidates[k].data(), n, params);
+        return ecc->evaluateBatchParams(Ps, params, n);
+    }
+
+    /// The same for candidates of ONE view's parameters (view = input index unless given): the n-1 pairs with that view.
+    std::vector<double> evaluateViewCandidates(Geometry::ModelFDCT& model, const std::vector<std::vector<double> >& candidates, int view = -1)
+    {
+        if (view < 0) view = input_index;
+        const int n = (int)Ps.size();
+        std::vector<double> params;
+        for (size_t k = 0; k < candidates.size(); k++) {
+            Geometry::ModelCameraSimilarity2D3D one = model.stencil;
+            one.current_values.assign(11, 0.0);
+            const std::vector<double>& x = one.expand(candidates[k].data());
+            params.insert(params.end(), x.begin(), x.end());
+        }
+        std::vector<int> map(n, -1);
+        map[view] = 0;
+        std::vector<Eigen::Vector4i> idx;
+        for (int i = 0; i < n; i++)
+            if (i != view) idx.push_back(Eigen::Vector4i(view, i, view, i));
+        return ecc->evaluateBatchParams(Ps, params, 1, map, &idx);
     }
 };
 

@@ -213,6 +213,32 @@ public:
         return means;
     }
 
+    /// NEW: the same, fed with PARAMETER VECTORS: K * m instances of ModelCameraSimilarity2D3D (11 doubles each, `params`)
+    /// applied to the base matrices on the device (ecc_evaluate_batch_params).  view_to_param (n entries or empty): which of
+    /// a set's m instances moves view v, negative = none; empty = one instance per view (m == n, Geometry::ModelFDCT).
+    /// Results equal evaluateBatch() of the matrices the host models hand out, without building or uploading them.
+    std::vector<double> evaluateBatchParams(const std::vector<ProjectionMatrix>& base, const std::vector<double>& params, int m,
+                                            const std::vector<int>& view_to_param = std::vector<int>(),
+                                            const std::vector<Eigen::Vector4i>* _indices = 0x0, float* out = 0x0)
+    {
+        const int K = m > 0 ? (int)(params.size() / ((size_t)11 * m)) : 0;
+        std::vector<double> means(K, 0.0);
+        if (K == 0) return means;
+        pushSettings();
+        std::vector<double> flat(12 * base.size());
+        for (size_t i = 0; i < base.size(); i++) std::memcpy(&flat[12 * i], base[i].data(), sizeof(double) * 12);
+        std::vector<int> idx;
+        if (_indices) {
+            idx.resize(4 * _indices->size());
+            for (size_t i = 0; i < _indices->size(); i++)
+                for (int k = 0; k < 4; k++) idx[4 * i + k] = (*_indices)[i].data()[k];
+        }
+        chk(ecc_evaluate_batch_params(ctx, base.empty() ? 0x0 : flat.data(), params.data(), K, m, view_to_param.empty() ? 0x0 : view_to_param.data(),
+                                      _indices ? idx.data() : 0x0, _indices ? (int)_indices->size() : 0, out, means.data()),
+            "ecc_evaluate_batch_params");
+        return means;
+    }
+
     /// Visualisation helper of the reference (EpipolarConsistencyRadonIntermediate.cpp:324-393): that code samples on
     /// the CPU with its own texel mapping.  Here: the pair's metric value from the GPU path; sample vectors are not filled.
     /// The two redundant signals of pair (i, j) for plotting, in ascending kappa (EpipolarConsistencyRadonIntermediate.cpp

@@ -208,6 +208,32 @@ int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const 
 int ecc_evaluate_batch(ecc_context* ctx, const double* Ps_sets, int n_sets, const int* idx4,
                        int n_pairs, float* out, double* means);
 
+/* ---- Perturbation models of the correction loops, expanded on the device ------------------------------------------
+ * A model instance is 11 doubles: ModelCameraSimilarity2D3D (LibProjectiveGeometry/Models/ModelCameraSimilarity2D3D.hxx:89-92),
+ * P' = H2D(x[0..3]) * P * T3D(x[4..10]) with x[0..3] = translation u, v, 2D rotation, 2D scale (ModelSimilarity2D.hxx:52-72)
+ * and x[4..10] = translation X, Y, Z, rotation about X, Y, Z (R = Rx Ry Rz), 3D scale (ModelSimilarity3D.hxx:64-87).
+ * The four host functions and the device expansion execute the same fp64 operation sequence (own sine / cosine, no fused
+ * multiply-add): the matrices of ecc_model_expand / ecc_evaluate_batch_params are bit for bit those of
+ * ecc_model_camera_similarity_2d3d.  H: 3x3, T: 4x4, P: 3x4, all column-major. */
+void ecc_model_similarity_2d(const double* x4, double* H);
+void ecc_model_similarity_3d(const double* x7, double* T);
+void ecc_model_transform(const double* H, const double* P, const double* T, double* P_out);
+void ecc_model_camera_similarity_2d3d(const double* P, const double* x11, double* P_out);
+
+/* Batched mode fed with PARAMETER VECTORS instead of matrices: n_sets * m model instances (params, [h|d], 11 doubles each)
+ * applied to the n base matrices (base_Ps [h|d], n*12 doubles, NULL = the context's current set; n = its size).
+ * view_to_param [h|d] (n ints, nullable): which of a set's m instances moves view v, negative = the view keeps its base
+ * matrix; NULL = every view has its own instance (m == n: ModelFDCT::applyModel, tools/FDCTMotionCorrection/ModelFDCT.hxx:26-62).
+ * m = 1 with a map covers the other loops: one moving view (Gui/SingleImageMotion.h:84-90, Gui/FDCTMotionCorrection.hxx:91-97),
+ * one transform for a group of views (tools/Registration/Registration3D3D.hxx).  One kernel expands the matrices in
+ * registers, derives pinv^T / source positions / each set's automatic object radius, then the sets are scored as by
+ * ecc_evaluate_batch -- with the same results as ecc_evaluate_batch fed with the host-expanded matrices. */
+int ecc_evaluate_batch_params(ecc_context* ctx, const double* base_Ps, const double* params, int n_sets, int m,
+                              const int* view_to_param, const int* idx4, int n_pairs, float* out, double* means);
+/* The expanded matrices themselves (Ps_out [h|d]: n_sets * n * 12 doubles), computed by the same device kernel. */
+int ecc_model_expand(ecc_context* ctx, const double* base_Ps, const double* params, int n_sets, int m,
+                     const int* view_to_param, double* Ps_out);
+
 /* evaluateForImagePair (EpipolarConsistencyRadonIntermediate.cpp:324-393, "visualization only"): the two redundant
  * signals of ONE pair, sampled on the device with the metric's own lookup (the reference walks them on the CPU with
  * RadonIntermediate::sample, whose texel mapping differs slightly from the metric's).  Entries are in

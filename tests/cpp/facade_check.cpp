@@ -215,6 +215,59 @@ static int run_gpu(const char* tmpdir)
         if (std::fabs(rm[0] - id) > 1e-6 * id || std::fabs(rm[1] - moved) > 1e-6 * moved) return fail("Registration3D3D candidates vs sequential");
         if (!(moved > id)) return fail("Registration3D3D: a displaced source must score worse");
     }
+    {   // FDCTMoCo + ModelFDCT: per-view parameter stacking, K trajectories per launch expanded on the device
+        std::set<int> active;
+        active.insert(0);   // translation u
+        active.insert(1);   // translation v
+        active.insert(4);   // translation X
+        active.insert(8);   // rotation about Y
+        Geometry::ModelCameraSimilarity2D3D stencil(Ps[0], active);
+        Geometry::ModelFDCT model(stencil);
+        if (model.n_active != 4) return fail("ModelFDCT n_active");
+        std::vector<std::vector<double> > cands(3, std::vector<double>((size_t)n * 4, 0.0));
+        for (int i = 0; i < n; i++) {  // candidate 1: every view moved a little, differently; candidate 2: view 3 only
+            cands[1][4 * i + 0] = 0.3 * (i % 3) - 0.2;
+            cands[1][4 * i + 1] = 0.1 * i;
+            cands[1][4 * i + 2] = 0.5 - 0.2 * i;
+            cands[1][4 * i + 3] = 0.001 * (i + 1);
+        }
+        cands[2][4 * 3 + 0] = 2.5;
+        cands[2][4 * 3 + 3] = -0.004;
+        FDCTMoCo moco(Ps, dtrs, 3);
+        moco.getMetricPtr().setObjectRadius(0).setEpipolarPlaneStep(0);
+        const std::vector<double> batch = moco.evaluateTrajectories(model, cands);
+        // the reference's way: matrices on the host (applyModel), one full evaluation per candidate
+        MetricRadonIntermediate seq(Ps, dtrs);
+        double one_by_one[3];
+        for (int k = 0; k < 3; k++) {
+            const std::vector<ProjectionMatrix>& traj = model.applyModel(-1, cands[k].data(), Ps);
+            seq.setProjectionMatrices(traj);
+            one_by_one[k] = seq.evaluate();
+        }
+        std::printf("fdct %.12g %.12g %.12g %.12g %.12g %.12g\n", batch[0], batch[1], batch[2], one_by_one[0], one_by_one[1], one_by_one[2]);
+        for (int k = 0; k < 3; k++)
+            if (std::fabs(batch[k] - one_by_one[k]) > 1e-12 * std::fabs(one_by_one[k])) return fail("FDCTMoCo: device-expanded trajectories vs host models, one by one");
+        if (!(batch[1] > batch[0] && batch[2] > batch[0])) return fail("FDCTMoCo: a perturbed trajectory must score worse");
+        // applyModel(view, delta): only that view changes, by exactly the stencil model
+        const double d3[4] = {2.5, 0.0, 0.0, -0.004};
+        const std::vector<ProjectionMatrix>& t3 = model.applyModel(3, d3, Ps);
+        Geometry::ModelCameraSimilarity2D3D single(Ps[3], active);
+        single.expand(d3);
+        const ProjectionMatrix want3 = single.getInstance();
+        for (int q = 0; q < 12; q++)
+            if (t3[3].data()[q] != want3.data()[q] || t3[2].data()[q] != Ps[2].data()[q]) return fail("ModelFDCT::applyModel(view)");
+        // candidates for one view: the n-1 pairs with it, = SingleImageMotion::evaluateCandidates of the host-built matrices
+        std::vector<std::vector<double> > vc(2, std::vector<double>(4, 0.0));
+        vc[1][0] = 2.5;
+        vc[1][3] = -0.004;
+        const std::vector<double> by_params = moco.evaluateViewCandidates(model, vc);
+        std::vector<ProjectionMatrix> mats;
+        mats.push_back(Ps[3]);
+        mats.push_back(want3);
+        const std::vector<double> by_mats = moco.evaluateCandidates(mats);
+        std::printf("fdctview %.12g %.12g %.12g %.12g\n", by_params[0], by_params[1], by_mats[0], by_mats[1]);
+        if (std::fabs(by_params[0] - by_mats[0]) > 1e-12 * by_mats[0] || std::fabs(by_params[1] - by_mats[1]) > 1e-12 * by_mats[1]) return fail("FDCTMoCo::evaluateViewCandidates vs evaluateCandidates");
+    }
     {   // PreProccess facade: defaults clear the border and feather 16 px; cosine weight 1 at the principal point
         NRRD::Image<float> im(n_u, n_v);
         for (int i = 0; i < im.length(); i++) ((float*)im)[i] = 5.f;

@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     rank, world, port, out_dir, engine = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5]
+    mode = sys.argv[6] if len(sys.argv) > 6 else "steps"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = port
     import torch
@@ -34,6 +35,26 @@ def main():
         ctx.set_interpolation(api.INTERP_TEXTURE)
         ctx.set_epipolar_plane_step(S["dkappa"])
         interp = {"texture": api.INTERP_TEXTURE, "hybrid": api.INTERP_HYBRID, "hybrid-static": api.INTERP_HYBRID_STATIC}[engine]
+        if mode == "loop":
+            # optimiser loop: intermediates once, then evaluation after evaluation with other matrices and NO Radon barrier in
+            # between; the ranks drift apart on purpose
+            import time
+            from test_gpu_team import loop_sets
+            full = pipe.radon_allgather(local, n, n_a, n_t, interp=interp)
+            ctx.set_radon_intermediates(full, n_u, n_v, True)
+            sets = loop_sets(S)
+            costs = [torch.zeros((n, n), dtype=torch.float32, device="cuda") for _ in sets]
+            loop_means = []
+            for k, P in enumerate(sets):
+                if (k + rank) % 3 == 0:
+                    time.sleep(0.05)
+                ctx.set_projection_matrices(P)
+                loop_means.append(pipe.evaluate_all_pairs(n, costs[k]))  # device cost image: only the stream orders its reads
+            torch.cuda.synchronize()
+            assert pipe._team_key is not None, f"team transport not used: {pipe.team_error}"
+            np.savez(os.path.join(out_dir, f"loop{rank}.npz"), means=np.array(loop_means), costs=np.stack([c.cpu().numpy() for c in costs]))
+            dist.barrier()
+            return
         means = []
         for step in range(2):  # twice: the second step overwrites buffers the peers have read
             src = local if step == 0 else S["imgs"][lo:hi]  # device images, then host images

@@ -29,6 +29,9 @@ class StubCompute:
     def evaluate_batch(self, Ps_sets, idx4=None):
         return np.array([float(P[0, 0]) * 2.0 + 1.0 for P in Ps_sets], np.float64)  # a set's "mean" = a function of the set
 
+    def evaluate_batch_params(self, base_Ps, params, view_to_param=None, idx4=None):
+        return np.array([float(x[0, 0]) * 3.0 - 1.0 for x in params], np.float64)  # a set's "mean" = a function of its parameters
+
     def evaluate_range(self, lo, hi, cost_image=None, want_sum=True):
         pairs = [(i, j) for i in range(self.n) for j in range(i + 1, self.n)][lo:hi]
         s = 0.0
@@ -102,6 +105,8 @@ def _worker(rank, world, port, n_total, results, mode="nccl"):
         if mode == "batch":
             sets = np.arange(7 * n_total * 12, dtype=np.float64).reshape(7, n_total, 12)  # K = 7 sets: ragged over 2 ranks
             extra = pipe.evaluate_batch(sets).tolist()
+            params = np.arange(7 * n_total * 11, dtype=np.float64).reshape(7, n_total, 11)  # the same with parameter vectors
+            extra = (extra, pipe.evaluate_batch_params(None, params).tolist())
         elif mode != "nccl":
             extra = (pipe.transport, pipe.team_error, compute.connected_with, compute.destroyed)
         results[rank] = (full[:, 0, 0].tolist(), mean, cost.numpy().copy(), extra)
@@ -166,5 +171,7 @@ def test_world2_batched_sets_are_sharded_and_gathered():
     n_total = 4
     res = _run(n_total, mode="batch")
     want = [float(k * n_total * 12) * 2.0 + 1.0 for k in range(7)]
+    want_params = [float(k * n_total * 11) * 3.0 - 1.0 for k in range(7)]
     for rank in (0, 1):
-        assert res[rank][3] == want  # every rank ends with all K means, in set order
+        assert res[rank][3][0] == want  # every rank ends with all K means, in set order
+        assert res[rank][3][1] == want_params  # and so for sets given as parameter vectors

@@ -88,23 +88,28 @@ def test_team_threads_bit_identical_to_single_gpu(world):
             c.close()
 
 
-def test_team_back_to_back_evaluations_with_changing_matrices():
-    """An optimiser loop: the intermediates stay, the matrices change, ecc_team_evaluate is called again and again with no
-    Radon barrier in between.  A rank that is ahead publishes the values of evaluation k+1 into its peers while they may
-    still be summing those of evaluation k: the two alternating value buffers keep them apart (round-1 advisor finding).
-    Every evaluation on every rank must be the single-GPU result bit for bit, also when the ranks drift apart."""
-    import time
-    import torch
-    from epipolarconsistency_b200.distributed import shard_bounds
-    S = make_scene()
-    n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
-    world, steps = 3, 7
+def loop_sets(S, steps=7):
+    """Matrix sets of an optimiser loop over the team scene: step k = view k shifted by k pixels in u (row0 += k * row2,
+    column-major 3x4)."""
     sets = []
-    for k in range(steps):  # step k: view k shifted by k pixels in u (row0 += k * row2, column-major 3x4)
+    for k in range(steps):
         P = S["Ps"].copy()
         for c in range(4):
             P[k, 0 + 3 * c] += float(k) * P[k, 2 + 3 * c]
         sets.append(P)
+    return sets
+
+
+def test_team_back_to_back_evaluations_with_changing_matrices(tmp_path):
+    """An optimiser loop: the intermediates stay, the matrices change, ecc_team_evaluate is called again and again with no
+    Radon barrier in between.  A rank that is ahead publishes the values of evaluation k+1 into its peers while they may
+    still be summing those of evaluation k: the two alternating value buffers keep them apart (round-1 advisor finding).
+    Every evaluation on every rank must be the single-GPU result bit for bit, also when the ranks drift apart (the workers
+    sleep at different steps).  Ranks are processes, as in the bench (tests/team_worker.py, mode "loop")."""
+    world = 3
+    S = make_scene()
+    n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
+    sets = loop_sets(S)
     one = api.Context()
     try:
         dtrs = one.radon_compute(S["imgs"], n_a, n_t, interp=api.INTERP_TEXTURE)
@@ -118,54 +123,25 @@ def test_team_back_to_back_evaluations_with_changing_matrices():
             want.append((one.evaluate(cost), cost))
     finally:
         one.close()
-    n_dev = torch.cuda.device_count()
-    ctxs = [api.Context(r % n_dev, stream=None) for r in range(world)]
-    try:
-        for r, c in enumerate(ctxs):
-            c.team_create(r, world, n, n_a, n_t)
-        blocks = [c.team_block()[0] for c in ctxs]
-        for c in ctxs:
-            c.team_connect_pointers(blocks)
-        bounds = shard_bounds(n, world)
-        got = [[None] * steps for _ in range(world)]
-        errors = []
-
-        def run(r):
-            try:
-                c = ctxs[r]
-                torch.cuda.set_device(r % n_dev)
-                c.set_interpolation(api.INTERP_TEXTURE)
-                c.set_epipolar_plane_step(S["dkappa"])
-                lo, hi = bounds[r], bounds[r + 1]
-                c.team_radon_compute(S["imgs"][lo:hi], lo, n_u, n_v, interp=api.INTERP_TEXTURE)
-                c.team_set_radon_intermediates(n_u, n_v, True)
-                for k in range(steps):
-                    if (k + r) % 3 == 0:
-                        time.sleep(0.02)  # let the ranks drift apart on the host
-                    c.set_projection_matrices(sets[k])
-                    # device cost image: nothing but the stream orders this rank's reads against its peers' next stores
-                    cost = torch.zeros((n, n), dtype=torch.float32, device=f"cuda:{r % n_dev}")
-                    mean = c.team_evaluate(cost)
-                    got[r][k] = (mean, cost)
-                c.synchronize()
-            except Exception as e:  # noqa: BLE001
-                errors.append((r, repr(e)))
-
-        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join(timeout=180)
-        assert not errors, errors
-        for r in range(world):
-            for k in range(steps):
-                mean, cost = got[r][k]
-                assert mean == want[k][0], f"rank {r} step {k}: mean {mean} vs {want[k][0]}"
-                assert np.array_equal(cost.cpu().numpy(), want[k][1]), f"rank {r} step {k}: cost image differs"
-        assert want[3][0] > want[0][0]
-    finally:
-        for c in ctxs:
-            c.close()
+    port = str(_free_port())
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "team_worker.py"), str(r), str(world), port, str(tmp_path), "texture", "loop"],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    logs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+            out += "\n[timeout]"
+        logs.append(out)
+    assert all(p.returncode == 0 for p in procs), "\n----\n".join(logs)
+    for r in range(world):
+        res = np.load(os.path.join(tmp_path, f"loop{r}.npz"))
+        for k in range(len(sets)):
+            assert res["means"][k] == want[k][0], f"rank {r} step {k}: mean {res['means'][k]} vs {want[k][0]}"
+            assert np.array_equal(res["costs"][k], want[k][1]), f"rank {r} step {k}: cost image differs"
+    assert want[3][0] > want[0][0]
 
 
 def _free_port():

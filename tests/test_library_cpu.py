@@ -107,3 +107,27 @@ def test_buffer_dtypes_are_checked_before_they_reach_the_abi():
     with pytest.raises(TypeError):
         api._ptr(torch.zeros(4, dtype=torch.float64), "float32")
     assert api._ptr(torch.zeros(4, dtype=torch.int32), "int32")
+
+
+def test_library_models_match_numpy_and_are_exact_where_the_reference_branches():
+    """ecc_model_*: the perturbation models as the library computes them on host and device (own fp64 sine / cosine, no
+    fused multiply-add) against the independent numpy restatements (libm): within an ulp over six decades of angle; exact
+    identity for zero parameters (the reference's `if (x != 0)` branches, ModelSimilarity2D.hxx:60-70, ModelSimilarity3D.hxx:73-85)."""
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for scale in (1e-6, 1e-3, 0.1, 1.0, 10.0, 1000.0):
+        for a in rng.uniform(-scale, scale, 300):
+            H = api.model_similarity_2d([0, 0, a, 0])
+            worst = max(worst, abs(H[0, 0] - np.cos(a)), abs(H[1, 0] - np.sin(a)), abs(H[0, 1] + np.sin(a)))
+    assert worst <= 1.5 * np.finfo(np.float64).eps
+    assert np.array_equal(api.model_similarity_2d([0, 0, 0, 0]), np.eye(3))
+    assert np.array_equal(api.model_similarity_3d([0] * 7), np.eye(4))
+    for _ in range(50):
+        x = rng.normal(0, 1, 11) * [2, 2, 0.3, 0.05, 5, 5, 5, 0.3, 0.3, 0.3, 0.05]
+        assert np.allclose(api.model_similarity_2d(x[:4]), api.similarity_2d(x[:4]), rtol=1e-14, atol=1e-15)
+        assert np.allclose(api.model_similarity_3d(x[4:]), api.similarity_3d(x[4:]), rtol=1e-14, atol=1e-15)
+    Ps = ol.circular_trajectory(3, 750, 1200, 640, 480, 200, 0.8)
+    x = [1.5, -2.0, 0.01, 0.02, 3.0, -1.0, 2.0, 0.02, -0.01, 0.03, 0.01]
+    got, want = api.model_camera_similarity_2d3d(Ps[1], x), api.camera_similarity_2d3d(Ps[1], x)
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    assert np.array_equal(api.model_camera_similarity_2d3d(Ps[1], [0] * 11), Ps[1])
