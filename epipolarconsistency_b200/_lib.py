@@ -30,6 +30,9 @@ SIGNATURES = {
     "ecc_device_alloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(c_vp)]),
     "ecc_device_free": (C.c_int, [c_ctx, c_vp]),
     "ecc_copy": (C.c_int, [c_ctx, c_vp, c_vp, C.c_size_t]),
+    "ecc_texture_create": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(c_vp)]),
+    "ecc_texture_destroy": (C.c_int, [c_ctx, C.c_ulonglong, c_vp]),
+    "ecc_texture_readback": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, c_vp]),
     "ecc_set_projection_matrices": (C.c_int, [c_ctx, c_vp, C.c_int]),
     "ecc_update_projection_matrix": (C.c_int, [c_ctx, C.c_int, c_vp]),
     "ecc_get_derived_views": (C.c_int, [c_ctx, c_vp, c_vp]),

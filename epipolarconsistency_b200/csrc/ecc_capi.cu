@@ -1147,21 +1147,30 @@ int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds)
         std::memcpy(bounds, ctx->partition_bounds.data(), sizeof(long long) * (n_parts + 1));
         return ECC_OK;
     }
-    std::vector<int> counts((size_t)total);
-    if (total) {
-        int rc = ecc_pair_sample_counts(ctx, counts.data());
-        if (rc) return rc;
-    }
-    double all = 0;
-    for (long long k = 0; k < total; k++) all += counts[k] + 16;  // +16: fixed per-pair cost (K0/K1 maps)
+    // counts, running sum and cuts stay on the device: one small download instead of one int per pair (an optimiser changes
+    // the matrices every step, so this runs every step on every rank)
+    if (n_parts > 1023) return fail(ctx, ECC_ERR_INVALID, "ecc_partition_pairs: too many parts");
+    Guard g(ctx);
     bounds[0] = 0;
-    double run = 0;
-    int part = 1;
-    for (long long k = 0; k < total && part < n_parts; k++) {
-        run += counts[k] + 16;
-        while (part < n_parts && run >= all * part / n_parts) bounds[part++] = k + 1;
+    for (int p = 1; p <= n_parts; p++) bounds[p] = total;
+    if (total > 0) {
+        PairLaunch L;
+        int rc = fill_launch(ctx, L);
+        if (rc) return rc;
+        L.n_pairs = total;
+        size_t cap = ctx->counts_cap * sizeof(int);
+        // [counts | bounds] in one buffer (bounds 8-byte aligned behind the counts)
+        const size_t counts_bytes = round_up(sizeof(int) * (size_t)total, 16);
+        if ((rc = ensure_bytes(ctx, (void**)&ctx->counts_d, &cap, counts_bytes + sizeof(long long) * (n_parts + 1)))) return rc;
+        ctx->counts_cap = cap / sizeof(int);
+        long long* bounds_d = (long long*)((char*)ctx->counts_d + counts_bytes);
+        if ((rc = launch_pair_counts(ctx, L, ctx->counts_d))) return rc;
+        if ((rc = launch_partition(ctx, ctx->counts_d, total, n_parts, bounds_d))) return rc;
+        if ((rc = ensure_pinned(ctx, sizeof(long long) * (n_parts + 1)))) return rc;
+        ECC_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_h, bounds_d, sizeof(long long) * (n_parts + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::memcpy(bounds, ctx->pinned_h, sizeof(long long) * (n_parts + 1));
     }
-    while (part <= n_parts) bounds[part++] = total;
     ctx->partition_key = key;
     ctx->partition_bounds.assign(bounds, bounds + n_parts + 1);
     return ECC_OK;

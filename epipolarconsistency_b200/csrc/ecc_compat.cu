@@ -176,3 +176,60 @@ void epipolarConsistency(int n_x, int n_y, int num_dtrs, char* dtrs_d, int n_alp
     if (!use_corr && out_corr_d && (rc = launch_fill(ctx, out_corr_d, (size_t)pairs, 1, 1.0f))) die(ctx, "epipolarConsistency", rc);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) die(ctx, "epipolarConsistency", ECC_ERR_CUDA);
 }
+
+// ---- the reference's texture wrapper for callers without a CUDA toolchain (the C++ facade's UtilsCuda::BindlessTexture2D) -------
+extern "C" {
+
+int ecc_texture_create(ecc_context* ctx, const float* image, int w, int h, int normalized, int interpolate, unsigned long long* tex_out,
+                       void** array_out)
+{
+    if (!ctx || !image || !tex_out || !array_out || w < 1 || h < 1) return ECC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+    cudaArray_t arr = nullptr;
+    ECC_CUDA(ctx, cudaMallocArray(&arr, &desc, w, h));
+    cudaError_t e = cudaMemcpy2DToArrayAsync(arr, 0, 0, image, sizeof(float) * w, sizeof(float) * w, h, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return cuda_fail(ctx, e, "cudaMemcpy2DToArrayAsync", __FILE__, __LINE__);
+    }
+    cudaResourceDesc res = {};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaTextureDesc td = {};
+    td.normalizedCoords = normalized ? 1 : 0;
+    td.filterMode = interpolate ? cudaFilterModeLinear : cudaFilterModePoint;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return cuda_fail(ctx, e, "cudaCreateTextureObject", __FILE__, __LINE__);
+    }
+    *tex_out = (unsigned long long)tex;
+    *array_out = (void*)arr;
+    return ECC_OK;
+}
+
+int ecc_texture_destroy(ecc_context* ctx, unsigned long long tex, void* array)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (tex) ECC_CUDA(ctx, cudaDestroyTextureObject((cudaTextureObject_t)tex));
+    if (array) ECC_CUDA(ctx, cudaFreeArray((cudaArray_t)array));
+    return ECC_OK;
+}
+
+int ecc_texture_readback(ecc_context* ctx, void* array, int w, int h, float* out)
+{
+    if (!ctx || !array || !out || w < 1 || h < 1) return ECC_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ECC_CUDA(ctx, cudaMemcpy2DFromArrayAsync(out, sizeof(float) * w, (cudaArray_t)array, 0, 0, sizeof(float) * w, h, cudaMemcpyDefault, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ECC_OK;
+}
+
+}  // extern "C"

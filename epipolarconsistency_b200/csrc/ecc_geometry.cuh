@@ -124,11 +124,21 @@ __host__ __device__ inline float pair_angle(const float* C0, const float* C1)
     return -2.0f * atan2f(-0.5f * s3, s2 / s3);
 }
 
-// kappa of sample m: (m + 1/2) dkappa, in the form nvcc gives the reference's
-// "dkappa*0.5f+dkappa*idx_y" (EpipolarConsistencyRadonIntermediate.cu:194,260): one fused multiply-add.
+// kappa of sample m: (m + 1/2) dkappa, with the roundings of the reference's compiled kernel.  Its source reads
+// "dkappa*0.5f+dkappa*idx_y" (EpipolarConsistencyRadonIntermediate.cu:194,260); nvcc 12.9 turns that into
+//     FMUL t = dkappa * float(idx_y);   FFMA kappa = dkappa * 0.5 + t
+// (cuobjdump of oracle/_ref/ecc_ri.o, kernelEpipolarCosistency at 0x0390/0x03a0): the product with the sample index is
+// rounded on its own.  Round 1 had guessed the other fusion, fma(dkappa, m, dkappa/2), which is an ulp off for about a
+// third of the samples -- invisible in the sums, but enough to move a texture coordinate across a 1/256 weight step where
+// an intermediate is steep (found at BASELINE size: 2 of 1830 pairs off by 0.5 % in ONE sample each, tools/pair_outlier_probe.py).
 __host__ __device__ inline float kappa_of_sample(float dkappa, int m)
 {
-    return fmaf(dkappa, (float)m, dkappa * 0.5f);
+#ifdef __CUDA_ARCH__
+    return fmaf(dkappa, 0.5f, __fmul_rn(dkappa, (float)m));
+#else
+    const float t = dkappa * (float)m;
+    return fmaf(dkappa, 0.5f, t);
+#endif
 }
 
 // Number of kappa samples a pair takes: m = 0,1,... while kappa_of_sample(m) < kappa_max and m < cap.

@@ -267,6 +267,8 @@ int launch_pair_maps(ecc_context* ctx, const PairLaunch& L, float* K01s_d);
 int launch_fill(ecc_context* ctx, float* dst_d, size_t count, size_t stride, float value);  // dst[k * stride] = value, k < count
 // one pair (L.idx4_d[0..3]): rec_d [sample_cap][13] floats, head_d [2] ints zeroed before the launch (ecc_pairs.cu: pair_signals_kernel)
 int launch_pair_signals(ecc_context* ctx, const PairLaunch& L, float* rec_d, int* head_d);
+// equal-work cut of counts_d[0..total) (+16 per pair) into n_parts ranges, on the device: bounds_d [n_parts + 1]
+int launch_partition(ecc_context* ctx, const int* counts_d, long long total, int n_parts, long long* bounds_d);
 int launch_sum_sets(ecc_context* ctx, const float* vals_d, long long n_pairs, int n_sets,
                     double* sums_d);
 // radii_d (nullable): entry s receives the automatic object radius of set s (views_per_set matrices per set),

@@ -46,6 +46,12 @@ protected:
     std::vector<double> element_spacing;
     T* data;
 
+    static void clampCell(int& i, double& f, int n)
+    {
+        if (i < 0) { i = 0; f = 0; }
+        if (i > n - 2) { f = 1.0; i = n - 2; }
+    }
+
 public:
     std::map<std::string, std::string> meta_info;             // "key:=value" lines
     mutable std::map<std::string, std::string> nrrd_header;   // extra "field: value" lines
@@ -78,6 +84,19 @@ public:
     bool operator!() const { return data == 0x0 || length() <= 0; }
     T& pixel(int x, int y, int z = 0) { return data[x + (size_t)y * dim[0] + (size_t)z * dim[0] * dim[1]]; }
     const T& pixel(int x, int y, int z = 0) const { return data[x + (size_t)y * dim[0] + (size_t)z * dim[0] * dim[1]]; }
+
+    /// Bilinear lookup at a continuous pixel position, edges clamped: the CPU sampling of the reference's views
+    /// (HeaderOnly/NRRD/nrrd_image_view.hxx:159-166,189-210; 2-D images: the xy-bilinear branch).  A position left of pixel 0
+    /// reads pixel 0, one right of pixel n-2 reads pixel n-1 (cell n-2 with weight 1).
+    double operator()(double x, double y) const
+    {
+        int ix = (int)x, iy = (int)y;
+        double fx = x - ix, fy = y - iy;
+        clampCell(ix, fx, dim[0]);
+        clampCell(iy, fy, dim[1]);
+        if (fx == 0 && fy == 0) return pixel(ix, iy);
+        return (1.0 - fy) * ((1.0 - fx) * pixel(ix, iy) + fx * pixel(ix + 1, iy)) + fy * ((1.0 - fx) * pixel(ix, iy + 1) + fx * pixel(ix + 1, iy + 1));
+    }
 
     bool save(const std::string& path) const
     {

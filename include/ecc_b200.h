@@ -152,6 +152,16 @@ int ecc_device_alloc(ecc_context* ctx, size_t bytes, void** ptr);
 int ecc_device_free(ecc_context* ctx, void* ptr);
 int ecc_copy(ecc_context* ctx, void* dst, const void* src, size_t bytes);
 
+/* UtilsCuda::BindlessTexture2D<float> for callers without a CUDA toolchain (LibUtilsCuda/CudaBindlessTexture.h:18-33, .cpp:17-67):
+ * a CUDA array holding a copy of the w x h image [h|d] and a texture object over it -- clamp addressing, linear or point
+ * filter, normalised or pixel coordinates.  tex is a cudaTextureObject_t, array a cudaArray_t.  The metric path does not
+ * need them (its textures sit over the linear intermediates); they exist for code that reads `->tex` / `->array`. */
+int ecc_texture_create(ecc_context* ctx, const float* image, int w, int h, int normalized, int interpolate,
+                       unsigned long long* tex, void** array);
+int ecc_texture_destroy(ecc_context* ctx, unsigned long long tex, void* array);
+/* BindlessTexture2D::readback: the image held by the array, out [h|d] w*h floats. */
+int ecc_texture_readback(ecc_context* ctx, void* array, int w, int h, float* out);
+
 /* setProjectionMatrices (EpipolarConsistencyRadonIntermediate.cpp:134-163): pseudo-inverse
  * transposes and source positions are derived on the device in fp64 and stored as fp32. */
 int ecc_set_projection_matrices(ecc_context* ctx, const double* Ps, int n);

@@ -463,7 +463,11 @@ double oracle_ecc(const double* Ps, int n_views, const float* dtrs, int n_dtrs, 
         int m = 0;
         // .cu:192-197 / :258-263 kappa grid; .cu:86-113 +/- kappa
         for (; m < sample_cap; m++) {
-            const float kappa = fmaf(dk, (float)m, dk * 0.5f);
+            // "dkappa*0.5f+dkappa*idx_y" as the reference's kernel EXECUTES it (nvcc 12.9, sm_100; cuobjdump of
+            // oracle/_ref/ecc_ri.o: FMUL t = dkappa * idx_y, FFMA kappa = dkappa * 0.5 + t): the product with the sample
+            // index is rounded on its own
+            const float kappa_t = dk * (float)m;
+            const float kappa = fmaf(dk, 0.5f, kappa_t);
             if (kappa >= kmax) break;
             float s, c;
             sincos_model(kappa, fast_sincos, &s, &c);

@@ -71,7 +71,12 @@ void free_array_texture(ArrayTex& t)
     t = ArrayTex();
 }
 
+typedef void (*LauncherFn)(int, int, int, char*, int, int, float, float, int, float*, float*, int, int*, float*, float*, float, float, bool, bool,
+                           float*);
+
 struct RefMetric {
+    LauncherFn launcher = nullptr;       // diagnostics: another implementation of the launcher's signature (null = the reference's)
+    std::vector<float*> linear;          // diagnostics: dtrs kept in linear memory when the textures are pitch2D
     int n_views = 0, n_dtrs = 0, n_alpha = 0, n_t = 0, n_u = 0, n_v = 0;
     float step_alpha = 0, step_t = 0;
     bool is_derivative = true;
@@ -156,10 +161,53 @@ void* ref_cuda_metric_create_any(const void* dtrs, int n_dtrs, int n_alpha, int 
     return ref_cuda_metric_create((const float*)dtrs, n_dtrs, n_alpha, n_t, step_alpha, step_t, n_u, n_v, is_derivative);
 }
 
+// Diagnostics: the same metric object with its dtr textures over pitched LINEAR memory (cudaResourceTypePitch2D, what
+// libecc_b200 samples) instead of CUDA arrays -- to tell texture-type effects from arithmetic effects.
+void* ref_cuda_metric_create_pitch2d(const void* dtrs, int n_dtrs, int n_alpha, int n_t, float step_alpha, float step_t, int n_u, int n_v,
+                                     int is_derivative)
+{
+    RefMetric* M = new RefMetric();
+    M->n_dtrs = n_dtrs; M->n_alpha = n_alpha; M->n_t = n_t; M->n_u = n_u; M->n_v = n_v;
+    M->step_alpha = step_alpha; M->step_t = step_t; M->is_derivative = is_derivative != 0;
+    const size_t dtr = (size_t)n_alpha * n_t;
+    std::vector<cudaTextureObject_t> handles(n_dtrs);
+    M->dtrs.resize(n_dtrs);
+    for (int k = 0; k < n_dtrs; k++) {
+        float* lin = nullptr;
+        if (cudaMalloc(&lin, sizeof(float) * dtr) != cudaSuccess) return nullptr;
+        cudaMemcpy(lin, (const float*)dtrs + dtr * k, sizeof(float) * dtr, cudaMemcpyDefault);
+        M->linear.push_back(lin);
+        cudaResourceDesc res;
+        memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypePitch2D;
+        res.res.pitch2D.devPtr = lin;
+        res.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+        res.res.pitch2D.width = n_alpha;
+        res.res.pitch2D.height = n_t;
+        res.res.pitch2D.pitchInBytes = sizeof(float) * n_alpha;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.normalizedCoords = 1;
+        td.filterMode = cudaFilterModeLinear;
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.readMode = cudaReadModeElementType;
+        if (cudaCreateTextureObject(&M->dtrs[k].tex, &res, &td, NULL) != cudaSuccess) return nullptr;
+        handles[k] = M->dtrs[k].tex;
+    }
+    cudaMalloc(&M->tex_d, sizeof(cudaTextureObject_t) * n_dtrs);
+    cudaMemcpy(M->tex_d, handles.data(), sizeof(cudaTextureObject_t) * n_dtrs, cudaMemcpyHostToDevice);
+    return M;
+}
+
+// Diagnostics: run evaluate() through ANOTHER function with the launcher's signature (e.g. libecc_b200's own
+// epipolarConsistency symbol) on this object's textures and buffers; null restores the reference's launcher.
+void ref_cuda_metric_set_launcher(void* h, void* fn) { ((RefMetric*)h)->launcher = (LauncherFn)fn; }
+
 void ref_cuda_metric_destroy(void* h)
 {
     RefMetric* M = (RefMetric*)h;
     if (!M) return;
+    for (float* p : M->linear) cudaFree(p);
     for (auto& t : M->dtrs) free_array_texture(t);
     cudaFree(M->tex_d); cudaFree(M->Cs_d); cudaFree(M->PinvTs_d); cudaFree(M->K01s_d); cudaFree(M->out_d);
     cudaFree(M->corr_d); cudaFree(M->idx_d);
@@ -225,9 +273,10 @@ double ref_cuda_metric_evaluate(void* h, const int* idx4, int n_pairs, float rad
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    epipolarConsistency(M->n_u, M->n_v, M->n_dtrs, (char*)M->tex_d, M->n_alpha, M->n_t, M->step_alpha, M->step_t, n,
-                        M->Cs_d, M->PinvTs_d, all ? 0 : pairs, all ? nullptr : M->idx_d, M->K01s_d, M->out_d, radius,
-                        dkappa, M->is_derivative, false, M->corr_d);
+    (M->launcher ? M->launcher : (LauncherFn)epipolarConsistency)(M->n_u, M->n_v, M->n_dtrs, (char*)M->tex_d, M->n_alpha, M->n_t, M->step_alpha,
+                                                                   M->step_t, n, M->Cs_d, M->PinvTs_d, all ? 0 : pairs,
+                                                                   all ? nullptr : M->idx_d, M->K01s_d, M->out_d, radius, dkappa,
+                                                                   M->is_derivative, false, M->corr_d);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float m = 0.f;

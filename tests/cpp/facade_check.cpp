@@ -123,6 +123,65 @@ static int run_gpu(const char* tmpdir)
     }
     ecc_device_free(ctx, dev);
     if (!dtrs[0]->isDerivative() || dtrs[0]->getRadonBinNumber(1) != n_t || dtrs[0]->getOriginalImageSize(0) != n_u) return fail("dtr props");
+    {   // the constructors above only staged their images (one batched launch when the first result is asked for); an
+        // object computed on its own, the reference's way, has the same bits (static-split engine: batch invariant)
+        RadonIntermediate::setDeferredCompute(false);  // runs the staged batch
+        RadonIntermediate alone(images[3], n_a, n_t, RadonIntermediate::Derivative, RadonIntermediate::Identity);
+        RadonIntermediate::setDeferredCompute(true);
+        alone.readback();
+        dtrs[3]->readback();
+        if (std::memcmp((const float*)alone.data(), (const float*)dtrs[3]->data(), sizeof(float) * n_a * n_t) != 0) return fail("deferred batch vs single computation");
+        dtrs[3]->clearRawData();
+        // RadonIntermediateFunction::compute (Gui/ComputeRadonIntermediate.hxx:70-83): same dtr, meta side effects on the IMAGE
+        RadonIntermediateFunction fn;
+        fn.number_of_bins.angle = n_a;
+        fn.number_of_bins.distance = n_t;
+        double mm = 0.308;
+        RadonIntermediate* via_fn = fn.compute(images[3], &Ps[3], &mm);
+        via_fn->readback();
+        if (std::memcmp((const float*)alone.data(), (const float*)via_fn->data(), sizeof(float) * n_a * n_t) != 0) return fail("RadonIntermediateFunction::compute data");
+        delete via_fn;
+        if (images[3].meta_info["Original Image/Pixel Spacing"] != "0.308") return fail("meta: pixel spacing");
+        const std::string pm = images[3].meta_info["Original Image/Projection Matrix"];
+        if (pm.empty() || pm[0] != '[' || pm.substr(pm.size() - 2) != "] " || pm != ProjTable::toString(Ps[3])) return fail("meta: projection matrix");
+        if (ProjTable::stringToProjectionMatrix(pm)(1, 2) == 0.0) return fail("meta: projection matrix round trip");
+        std::printf("metapm %s\n", pm.c_str());
+        // BindlessTexture2D: `tex` / `array` appear on demand for a view, at once for an uploaded image; readback returns the data
+        UtilsCuda::BindlessTexture2D<float>* t = dtrs[1]->getTexture();
+        if (t->tex != 0 || t->array != 0x0 || !t->normalizedCoords || t->size[0] != n_a || t->size[1] != n_t) return fail("texture view before use");
+        const unsigned long long handle = *t;
+        if (handle == 0 || t->tex != handle || t->array == 0x0) return fail("texture view after use");
+        UtilsCuda::MemoryBlock<float> back;
+        t->readback(back);
+        std::vector<float> host(n_a * n_t);
+        back.readback(host.data());
+        dtrs[1]->readback();
+        if (std::memcmp(host.data(), (const float*)dtrs[1]->data(), sizeof(float) * n_a * n_t) != 0) return fail("texture readback");
+        UtilsCuda::BindlessTexture2D<float> up(n_u, n_v, (const float*)images[0]);
+        if (up.tex == 0 || up.array == 0x0 || up.normalizedCoords) return fail("uploaded texture");
+        RadonIntermediate from_tex(up, n_a, n_t, RadonIntermediate::Derivative, RadonIntermediate::Identity);
+        from_tex.readback();
+        dtrs[0]->readback();
+        if (std::memcmp((const float*)from_tex.data(), (const float*)dtrs[0]->data(), sizeof(float) * n_a * n_t) != 0) return fail("dtr from a GPU-resident image");
+        // CPU sampling helpers of the reference (RadonIntermediate.h:85-108): texel mapping (n-1) s, clamped bilinear
+        NRRD::Image<float> ramp(9, 5);
+        for (int y = 0; y < 5; y++)
+            for (int x = 0; x < 9; x++) ramp.pixel(x, y) = (float)(x + 10 * y);
+        ramp.meta_info["Bin Size/Angle"] = "0.3490658503988659";
+        ramp.meta_info["Bin Size/Distance"] = "40.98";
+        ramp.meta_info["Original Image/Width"] = "160";
+        ramp.meta_info["Original Image/Height"] = "128";
+        ramp.meta_info["Filter"] = "Derivative";
+        RadonIntermediate small(ramp);
+        if (std::fabs(small.tex2D(0.5f, 0.25f) - (4.0f + 10.0f)) > 1e-5f || small.tex2D(0.f, 0.f) != 0.f || small.tex2D(1.f, 1.f) != 48.f) return fail("tex2D");
+        if (std::fabs(small.tex2D(0.3f, 0.6f) - (8 * 0.3f + 10 * 4 * 0.6f)) > 1e-4f) return fail("tex2D bilinear");
+        const float lines[4][3] = {{0.3f, 0.9f, 20.f}, {-0.7f, 0.2f, -55.f}, {0.1f, -1.3f, 3.f}, {-0.4f, -0.6f, 80.f}};
+        for (int q = 0; q < 4; q++) {
+            float l[3] = {lines[q][0], lines[q][1], lines[q][2]};
+            const float v = small.sample(l);
+            std::printf("l2s %.9g %.9g %.9g\n", l[0], l[1], v);
+        }
+    }
     // save / reload a dtr: identical data and properties
     dtrs[2]->readback();
     const std::string path = std::string(tmpdir) + "/facade_dtr2.nrrd";

@@ -235,6 +235,10 @@ def ref_cuda():
                                          C.POINTER(C.c_float)]
         L.ref_cuda_metric_create_any.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
         L.ref_cuda_metric_create_any.restype = C.c_void_p
+    if hasattr(L, "ref_cuda_metric_set_launcher"):
+        L.ref_cuda_metric_create_pitch2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_cuda_metric_create_pitch2d.restype = C.c_void_p
+        L.ref_cuda_metric_set_launcher.argtypes = [C.c_void_p, C.c_void_p]
     if hasattr(L, "ref_cuda_metric_get_k01"):
         L.ref_cuda_metric_get_k01.argtypes = [C.c_void_p, _f32p, C.c_int]
     if hasattr(L, "ref_cuda_metric_evaluate_corr"):
@@ -270,10 +274,18 @@ def ref_cuda_radon(images, n_alpha, n_t, filter=0, post=0):
 class RefCudaMetric:
     """The reference MetricRadonIntermediate's device path (its launcher + kernels)."""
 
-    def __init__(self, Ps, dtrs, n_u, n_v, is_derivative=True):
+    def __init__(self, Ps, dtrs, n_u, n_v, is_derivative=True, pitch2d=False):
+        """pitch2d (diagnostics): dtr textures over pitched linear memory instead of CUDA arrays."""
         self.L = ref_cuda()
         diag = np.sqrt(float(n_u) ** 2 + float(n_v) ** 2)
-        if hasattr(dtrs, "data_ptr"):  # contiguous float32 torch cuda tensor
+        if pitch2d:
+            import torch
+            keep = dtrs if hasattr(dtrs, "data_ptr") else torch.from_numpy(np.ascontiguousarray(dtrs, np.float32)).cuda()
+            m, n_t, n_alpha = keep.shape
+            torch.cuda.synchronize()
+            self.h = self.L.ref_cuda_metric_create_pitch2d(keep.data_ptr(), m, n_alpha, n_t, np.float32(np.pi / n_alpha), np.float32(diag / n_t),
+                                                           n_u, n_v, int(is_derivative))
+        elif hasattr(dtrs, "data_ptr"):  # contiguous float32 torch cuda tensor
             import torch
             assert dtrs.is_cuda and dtrs.is_contiguous() and dtrs.dtype == torch.float32
             m, n_t, n_alpha = dtrs.shape
@@ -306,6 +318,10 @@ class RefCudaMetric:
             mean = self.L.ref_cuda_metric_evaluate(self.h, idx4.ctypes.data_as(C.c_void_p), idx4.shape[0], radius,
                                                    dkappa, out.ctypes.data_as(C.c_void_p), C.byref(ms))
         return mean, out, ms.value
+
+    def set_launcher(self, address):
+        """Diagnostics: evaluate() through another function with the reference launcher's signature (None = the reference's)."""
+        self.L.ref_cuda_metric_set_launcher(self.h, address)
 
     def k01(self, n_pairs):
         """The K01 records (n_pairs, 16) the reference's own kernel computed in the last evaluate call."""

@@ -102,8 +102,10 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
             pairs[(int(t[1]), int(t[2]))] = float(t[3])
         elif t[0] in ("radius", "mean", "subset", "fixed"):
             vals[t[0]] = float(t[1])
-        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre", "signals"):
+        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre", "signals", "fdct", "fdctview"):
             vals[t[0]] = [float(x) for x in t[1:]]
+        elif t[0] == "l2s":
+            vals.setdefault("l2s", []).append([float(x) for x in t[1:]])
     # the same scene through the Python mirror
     import torch
     n, n_u, n_v, n_a, n_t = 6, 160, 128, 128, 128
@@ -112,7 +114,7 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
     Ps = api.make_circular_trajectory(n, 750.0, 1200.0, n_u, n_v, 200.0, 2.0)
     imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
     ctx.synth_projections(Ps, n_u, n_v, ell, imgs)
-    dtrs = ctx.radon_compute(imgs, n_a, n_t)
+    dtrs = ctx.radon_compute(imgs, n_a, n_t, interp=api.INTERP_HYBRID_STATIC)  # the facade's default engine
     ctx.set_projection_matrices(Ps)
     ctx.set_radon_intermediates(dtrs, n_u, n_v, True)
     cost = np.zeros((n, n), np.float32)
@@ -168,6 +170,18 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
         moved[i] = (Ps[i].reshape(4, 3).T @ T).T.reshape(12)
     ctx.set_projection_matrices(moved)
     assert abs(vals["reg33"][1] - ctx.evaluate_indices(cross)) <= 1e-7 * vals["reg33"][1]
+    # RadonIntermediate::sample / tex2D (CPU helpers of the reference): location = the reference's lineToSampleDtr (oracle, pinned
+    # by golden vectors), value = clamped bilinear lookup at ((n_alpha-1) a, (n_t-1) d) in the 9 x 5 ramp x + 10 y
+    lines = [(0.3, 0.9, 20.0), (-0.7, 0.2, -55.0), (0.1, -1.3, 3.0), (-0.4, -0.6, 80.0)]
+    assert len(vals["l2s"]) == 4
+    for line, (a, d, v) in zip(lines, vals["l2s"]):
+        loc, flipped = ol.line_to_sample(np.array(line, np.float32), np.float32(40.98) * 5)
+        assert abs(loc[0] - a) < 1e-6 and abs(loc[1] - d) < 1e-5
+        x, y = 8 * np.clip(a, 0, 1), 4 * np.clip(d, 0, 1)
+        assert abs(v - (x + 10 * y)) < 1e-3, (line, a, d, v)  # no sign flip in this CPU helper, as upstream
+    # FDCTMoCo: K trajectories expanded on the device = the host models' matrices evaluated one by one (checked in C++);
+    # here: the unperturbed candidate is the plain mean
+    assert abs(vals["fdct"][0] - all0) <= 1e-7 * all0 and vals["fdct"][1] > all0 and vals["fdct"][2] > all0
     # PreProccess facade vs the oracle restatement (defaults: zero 1, feather 16; no low-pass in this check)
     want = ol.preprocess(np.full((n_v, n_u), 5.0, np.float32), sigma=0.0, feather=(16, 16, 16, 16), P=Ps[0])
     assert abs(vals["pre"][0] - want[n_v // 2, 8]) <= 2e-6 * 5 and abs(vals["pre"][1] - want[30, 40]) <= 2e-6 * 5

@@ -84,4 +84,22 @@ for k in order[:2]:
         qp, qm = count + m, count - 1 - m
         print(f"      m={m} kappa={sig['kappas'][qp]:.6f}: +k s0={sig['signal0'][qp]:.6g} s1={sig['signal1'][qp]:.6g} line0=({sig['lines0'][qp][0]:.6g},{sig['lines0'][qp][1]:.6g}) line1=({sig['lines1'][qp][0]:.6g},{sig['lines1'][qp][1]:.6g})"
               f" | -k s0={sig['signal0'][qm]:.6g} s1={sig['signal1'][qm]:.6g} line0=({sig['lines0'][qm][0]:.6g},{sig['lines0'][qm][1]:.6g}) line1=({sig['lines1'][qm][0]:.6g},{sig['lines1'][qm][1]:.6g})")
+# ---- which side of the seam makes the difference?  (1) OUR kernel through the reference launcher's signature on the
+# reference's own CUDA-array textures and buffers; (2) the REFERENCE kernel on pitch2D (linear-memory) textures
+import ctypes as C
+from epipolarconsistency_b200 import _lib
+ours_launcher = C.cast(getattr(_lib.load(), "_Z19epipolarConsistencyiiiPciiffiPfS0_iPiS0_S0_ffbbS0_"), C.c_void_p).value
+ref.set_launcher(ours_launcher)
+_, xcost, _ = ref.evaluate(radius, dk)
+ref.set_launcher(None)
+ref2 = ol.RefCudaMetric(Ps, dtrs, n_u, n_v, pitch2d=True)
+_, pcost, _ = ref2.evaluate(radius, dk)
+ref2.close()
+x, p2 = pv(xcost), pv(pcost)
+print("ours (pitch2D textures) | ours on the reference's array textures | reference (array textures) | reference on pitch2D textures")
+for k in order[:8]:
+    print(f"  pair {k}: {g[k]:.9g} | {x[k]:.9g} | {r[k]:.9g} | {p2[k]:.9g}")
+print("max rel: ours-pitch2D vs ours-array %.3g; ref-array vs ref-pitch2D %.3g; ours-array vs ref-array %.3g; ours-pitch2D vs ref-pitch2D %.3g" % (
+    np.max(np.abs(g - x) / np.maximum(np.abs(g), 1e-9)), np.max(np.abs(r - p2) / np.maximum(np.abs(r), 1e-9)),
+    np.max(np.abs(x - r) / np.maximum(np.abs(r), 1e-9)), np.max(np.abs(g - p2) / np.maximum(np.abs(p2), 1e-9))))
 ref.close()
