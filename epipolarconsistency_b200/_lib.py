@@ -24,6 +24,8 @@ SIGNATURES = {
     "ecc_synchronize": (C.c_int, [c_ctx]),
     "ecc_radon_compute": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "ecc_radon_bin_sizes": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ecc_radon_calibrate_split": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "ecc_radon_set_split": (C.c_int, [c_ctx, C.c_int]),
     "ecc_radon_num_samples": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "ecc_set_radon_intermediates": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
     "ecc_set_radon_intermediate_pointers": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),

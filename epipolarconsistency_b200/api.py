@@ -144,6 +144,16 @@ class Context:
                                                interp, _ptr(out, _F32)))
         return out
 
+    def radon_calibrate_split(self, n_u, n_v, n_alpha, n_t):
+        """Window path's share of the samples (per mille) at which the two sampling pipes of THIS GPU balance for this geometry."""
+        v = C.c_int()
+        self._check(self.lib.ecc_radon_calibrate_split(self.h, n_u, n_v, n_alpha, n_t, C.byref(v)))
+        return v.value
+
+    def radon_set_split(self, permille):
+        """Pins the static split of INTERP_HYBRID_STATIC for this context (0 = built-in 580 / 605 per mille)."""
+        self._check(self.lib.ecc_radon_set_split(self.h, int(permille)))
+
     def radon_num_samples(self, n_u, n_v, n_alpha, n_t, filter=FILTER_DERIVATIVE):
         c = C.c_double()
         self._check(self.lib.ecc_radon_num_samples(self.h, n_u, n_v, n_alpha, n_t, filter, C.byref(c)))

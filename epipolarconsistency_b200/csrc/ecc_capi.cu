@@ -393,6 +393,22 @@ int ecc_preprocess(ecc_context* ctx, float* images, int n, int n_u, int n_v, con
     return ECC_OK;
 }
 
+int ecc_radon_calibrate_split(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int* window_share_permille)
+{
+    if (!ctx || !window_share_permille) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (n_u < 2 || n_v < 2 || n_alpha < 1 || n_t < 1) return fail(ctx, ECC_ERR_INVALID, "ecc_radon_calibrate_split: bad argument");
+    return radon_hybrid4_calibrate(ctx, n_u, n_v, n_alpha, n_t, 5, window_share_permille);
+}
+
+int ecc_radon_set_split(ecc_context* ctx, int window_share_permille)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    if (window_share_permille < 0 || window_share_permille > 1000) return fail(ctx, ECC_ERR_INVALID, "ecc_radon_set_split: 0 (built-in) .. 1000 per mille");
+    ctx->hybrid4.share_override = window_share_permille;
+    return ECC_OK;
+}
+
 int ecc_radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count)
 {
     if (!ctx || !count) return ECC_ERR_INVALID;

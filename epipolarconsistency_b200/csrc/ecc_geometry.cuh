@@ -127,7 +127,7 @@ __host__ __device__ inline float pair_angle(const float* C0, const float* C1)
 // kappa of sample m: (m + 1/2) dkappa, with the roundings of the reference's compiled kernel.  Its source reads
 // "dkappa*0.5f+dkappa*idx_y" (EpipolarConsistencyRadonIntermediate.cu:194,260); nvcc 12.9 turns that into
 //     FMUL t = dkappa * float(idx_y);   FFMA kappa = dkappa * 0.5 + t
-// (cuobjdump of oracle/_ref/ecc_ri.o, kernelEpipolarCosistency at 0x0390/0x03a0): the product with the sample index is
+// (cuobjdump of the sm_100 build of the reference's own .cu file, kernelEpipolarCosistency at 0x0390/0x03a0): the product with the sample index is
 // rounded on its own.  Round 1 had guessed the other fusion, fma(dkappa, m, dkappa/2), which is an ulp off for about a
 // third of the samples -- invisible in the sums, but enough to move a texture coordinate across a 1/256 weight step where
 // an intermediate is steep (found at BASELINE size: 2 of 1830 pairs off by 0.5 % in ONE sample each, tools/pair_outlier_probe.py).

@@ -56,6 +56,8 @@ struct Hybrid4Stage {
     int split_key[4] = {0, 0, 0, 0};  // n_u, n_v, n_alpha, n_t
     int split_items = -1;
     int split_cfg = -1;               // window configuration the split was computed for
+    int split_share = 0;              // share_override the split was computed for
+    int share_override = 0;           // > 0: window path's share of the samples in per mille (ecc_radon_set_split), 0: built-in
     int map_cfg = -1;                 // window configuration the tensor maps are encoded for
 };
 
@@ -296,6 +298,7 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
                          bool static_split = false);
 void free_hybrid4(ecc_context* ctx);
 int radon_hybrid4_reserve(ecc_context* ctx, int n_u, int n_v, int n_images);
+int radon_hybrid4_calibrate(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int repeats, int* permille);
 int radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter, double* count);
 
 // ---- multi-GPU team (ecc_team.cu) ----

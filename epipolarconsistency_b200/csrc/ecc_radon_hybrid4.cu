@@ -16,6 +16,7 @@
 //   queue:  two-ended at run time (ECC_INTERP_HYBRID), or a static split of every quad's items between the two paths,
 //           58-60 % of the samples to the window path (ECC_INTERP_HYBRID_STATIC: reproducible, batch-invariant).
 //   several GPUs: every finished bin is also stored into the other ranks' buffers (Mirrors, ecc_team.cu).
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -588,36 +589,52 @@ __global__ void item_samples_kernel(int n_u_i, int n_v_i, int n_alpha, int n_t, 
     atomicAdd(&per_item[(iy / kItemT) * groups_a + ix / kItemAngles], count);
 }
 
-// The window path's share of the samples when both pipes run side by side (B200, measured: window path 0.936, texture path
-// 0.677 projections per ms inside the combined kernel); development knob ECC_HYBRID4_SPLIT (per mille).
-int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int n_alpha, int n_t, int groups_a, int groups_t, int cfg,
-                       int* split)
+// Bilinear samples of every item of one projection (host copy).
+int item_sample_counts(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int groups_a, int groups_t, std::vector<float>& counts)
 {
-    if (H.split_items >= 0 && H.split_key[0] == n_u && H.split_key[1] == n_v && H.split_key[2] == n_alpha && H.split_key[3] == n_t &&
-        H.split_cfg == cfg) {
-        *split = H.split_items;
-        return ECC_OK;
-    }
     const int per_quad = groups_a * groups_t;
     float* counts_d = nullptr;
     ECC_CUDA(ctx, cudaMalloc(&counts_d, sizeof(float) * per_quad));
     ECC_CUDA(ctx, cudaMemsetAsync(counts_d, 0, sizeof(float) * per_quad, ctx->stream));
     item_samples_kernel<<<dim3((n_alpha + 127) / 128, n_t), 128, 0, ctx->stream>>>(n_u, n_v, n_alpha, n_t, groups_a, counts_d);
-    std::vector<float> counts(per_quad);
+    counts.assign(per_quad, 0.f);
     ECC_CUDA(ctx, cudaMemcpyAsync(counts.data(), counts_d, sizeof(float) * per_quad, cudaMemcpyDeviceToHost, ctx->stream));
     ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(counts_d);
+    return ECC_OK;
+}
+
+// The window path's share of the samples when both pipes run side by side.  Built-in: what the run-time queue settles at on
+// B200 at 1965 MHz (window path 0.936, texture path 0.677 projections per ms inside the combined kernel) -- 580 per mille
+// with the general window configuration, 605 with the fine one.  The balance is a property of the GPU (ratio of
+// shared-memory to texture throughput, clocks, SM count do not enter: both paths scale with them alike, but another
+// architecture or a power-capped part may sit elsewhere): ecc_radon_calibrate_split measures it on the GPU at hand,
+// ecc_radon_set_split pins it for a context (results then are reproducible for that number).  ECC_HYBRID4_SPLIT
+// (per mille) is the development knob.
+int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int n_alpha, int n_t, int groups_a, int groups_t, int cfg,
+                       int* split)
+{
+    if (H.split_items >= 0 && H.split_key[0] == n_u && H.split_key[1] == n_v && H.split_key[2] == n_alpha && H.split_key[3] == n_t &&
+        H.split_cfg == cfg && H.split_share == H.share_override) {
+        *split = H.split_items;
+        return ECC_OK;
+    }
+    const int per_quad = groups_a * groups_t;
+    std::vector<float> counts;
+    const int rc = item_sample_counts(ctx, n_u, n_v, n_alpha, n_t, groups_a, groups_t, counts);
+    if (rc) return rc;
     double total = 0;
     for (float c : counts) total += c;
-    // general window configuration 580, fine configuration (faster window path) 605 per mille
     static const int share_env = env_int("ECC_HYBRID4_SPLIT", 0);
-    const double share = (share_env > 0 ? share_env : (cfg == 1 ? 605 : 580)) / 1000.0;
+    const int permille = H.share_override > 0 ? H.share_override : (share_env > 0 ? share_env : (cfg == 1 ? 605 : 580));
+    const double share = permille / 1000.0;
     double run = 0;
     int m = 0;
     while (m < per_quad && run + counts[m] * 0.5 < share * total) run += counts[m++];
     H.split_items = m;
     H.split_key[0] = n_u; H.split_key[1] = n_v; H.split_key[2] = n_alpha; H.split_key[3] = n_t;
     H.split_cfg = cfg;
+    H.split_share = H.share_override;
     *split = m;
     return ECC_OK;
 }
@@ -648,7 +665,9 @@ void free_hybrid4(ecc_context* ctx)
     if (H.pad_n) cudaFree(H.pad_n);
     if (H.pad_t) cudaFree(H.pad_t);
     if (H.queue) cudaFree(H.queue);
+    const int keep = H.share_override;
     H = Hybrid4Stage();
+    H.share_override = keep;
 }
 
 template <typename W>
@@ -789,6 +808,46 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
                              : launch_window_config<Win4General>(ctx, H, P, cfg, threads, ctas, n_u, n_v);
     prof_end(ctx, slot);
     return rcl;
+}
+
+// Runs the RUN-TIME queue (which balances the two pipes by itself) on one quad of this geometry and reads off where the two
+// sides met: the share of the samples the window path took.  Median of `repeats` launches, per mille.
+int radon_hybrid4_calibrate(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int repeats, int* permille)
+{
+    Hybrid4Stage& H = ctx->hybrid4;
+    const size_t px = (size_t)n_u * n_v, bins = (size_t)n_alpha * n_t;
+    float *img_d = nullptr, *out_d = nullptr;
+    ECC_CUDA(ctx, cudaMalloc(&img_d, sizeof(float) * px * 4));
+    ECC_CUDA(ctx, cudaMalloc(&out_d, sizeof(float) * bins * 4));
+    ECC_CUDA(ctx, cudaMemsetAsync(img_d, 0, sizeof(float) * px * 4, ctx->stream));  // the work does not depend on the pixel values
+    const int groups_a = (n_alpha + kItemAngles - 1) / kItemAngles, groups_t = (n_t + kItemT - 1) / kItemT;
+    const int per_quad = groups_a * groups_t;
+    std::vector<float> counts;
+    int rc = item_sample_counts(ctx, n_u, n_v, n_alpha, n_t, groups_a, groups_t, counts);
+    double total = 0;
+    for (float c : counts) total += c;
+    std::vector<int> shares;
+    std::vector<unsigned> claim(per_quad);
+    for (int r = 0; r < (repeats > 0 ? repeats : 1) + 1 && rc == ECC_OK; r++) {
+        rc = radon_hybrid4_launch(ctx, img_d, 4, n_u, n_v, n_alpha, n_t, ECC_POST_IDENTITY, out_d, false);
+        if (rc) break;
+        if (cudaMemcpyAsync(claim.data(), H.queue + 2, sizeof(unsigned) * per_quad, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = fail(ctx, ECC_ERR_CUDA, "radon_hybrid4_calibrate: reading the queue back failed");
+            break;
+        }
+        if (r == 0) continue;  // warm-up launch (tensor maps, staging)
+        double window = 0;
+        for (int k = 0; k < per_quad; k++)
+            if (claim[k] == kClaimWindow) window += counts[k];
+        shares.push_back(total > 0 ? (int)(1000.0 * window / total + 0.5) : 0);
+    }
+    cudaFree(img_d);
+    cudaFree(out_d);
+    if (rc) return rc;
+    std::sort(shares.begin(), shares.end());
+    *permille = shares.empty() ? 0 : shares[shares.size() / 2];
+    return ECC_OK;
 }
 
 }  // namespace eccb200

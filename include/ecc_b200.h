@@ -95,6 +95,15 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
 void ecc_radon_bin_sizes(int n_u, int n_v, int n_alpha, int n_t, double* step_alpha,
                          double* step_t);
 
+/* ECC_INTERP_HYBRID_STATIC assigns a fixed share of every projection's samples to the shared-memory path and the rest to
+ * the texture unit.  The built-in share (580 / 605 per mille, by window configuration) is where the two pipes of a B200
+ * balance; ecc_radon_calibrate_split measures that balance on the GPU at hand for a geometry (a handful of short launches
+ * of the run-time work queue, which balances itself, on one quad of empty images; returns per mille), and
+ * ecc_radon_set_split pins a share for this context (0 restores the built-in).  Results are bit-reproducible and
+ * independent of batching and sharding for a GIVEN share; ranks of a team must use the same one. */
+int ecc_radon_calibrate_split(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int* window_share_permille);
+int ecc_radon_set_split(ecc_context* ctx, int window_share_permille);
+
 /* Work counter for benchmarks: bilinear image samples per projection for this geometry (exactly what the
  * kernel takes: clipped lines, step 0.66 px, two lines per bin for the derivative filter). */
 int ecc_radon_num_samples(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int filter,
