@@ -315,7 +315,7 @@ def test_all_pairs_texture_vs_reference_cuda(ctx, scene):
     got_v = pair_values(cost, n)
     ok, text = compare_with_racy_reference(got_v, runs, K_ours, K_ref, "45-pair scene")
     ref_v = runs.max(axis=0)
-    assert ok.mean() >= 0.95, text
+    assert ok.all() and rel_err(got_v, ref_v).max() < 2e-4, text  # measured 4.8e-5 (few samples per pair on this coarse scene)
     assert abs(mean - ref_v[ok].mean() * 1.0) / mean < 1e-2
     assert abs(got_v[ok].mean() - ref_v[ok].mean()) / ref_v[ok].mean() < SUM_TOL
     # pin the oracle's texture model against the reference CUDA path as well
@@ -974,9 +974,13 @@ def test_pairs_full_size_vs_reference_cuda_with_explained_outliers(ctx):
     ref.close()
     got_v = pair_values(cost, n)
     ok, text = compare_with_racy_reference(got_v, runs, K_ours, K_ref, "64 full-size views, dkappa 0.01 deg")
-    assert ok.mean() >= 0.995, text
+    assert ok.all(), text
     ref_v = runs.max(axis=0)
-    assert rel_err(got_v, ref_v).max() < 1e-2, text  # even a pair that lost updates in all eight runs lost few
+    # Measured: max 2.6e-6, the size of the reference's own run-to-run spread (1.9e-6: its atomicAdds land in any order).
+    # The pair kernel takes the roundings of the reference's COMPILED kernel (kappa grid, line coefficients, per-sample
+    # term; ecc_pairs.cu), so that every texture coordinate is the reference's bit for bit: before that, 2 of these 1830
+    # pairs were off by 0.5 % / 0.7 % in ONE sample each, where an intermediate is steep (tools/pair_outlier_probe.py).
+    assert rel_err(got_v, ref_v).max() < 2e-5, text
     assert abs(got_v[ok].mean() - ref_v[ok].mean()) / ref_v[ok].mean() < SUM_TOL
     assert abs(mean - ref_v.mean()) / mean < SUM_TOL
 
