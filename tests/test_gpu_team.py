@@ -2,7 +2,10 @@
 single-GPU results BIT FOR BIT (texture engine: deterministic), whichever way the blocks are mapped --
   * ranks as threads of one process, blocks connected by pointer (ecc_team_connect_pointers),
   * ranks as processes, blocks connected through CUDA IPC handles carried by torch.distributed (gloo) -- the bench's way.
-With one GPU in the box the ranks share it; the code path (peer stores, flag barriers, publish, fixed-order sum) is the same."""
+The ranks' flag barriers are kernels that wait on one another: every rank needs a GPU of its own (nothing guarantees that
+two such kernels are resident at the same time on ONE GPU -- B200_PROFILING.md; sharing a GPU can end in a context-switch
+time-out).  The multi-rank tests therefore run with `gpurun --gpus 2` (logs in profiles/) and skip on a one-GPU box, where
+the team of ONE and the CPU tests of the host logic (tests/test_distributed_cpu.py, gloo) remain."""
 import os
 import socket
 import subprocess
@@ -17,6 +20,39 @@ from team_scene import make_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def need_gpus(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"{world} ranks need {world} GPUs (flag barriers wait on one another); this box has {torch.cuda.device_count()}")
+
+
+def test_team_of_one_is_the_plain_path():
+    """world = 1: the team block, the alternating value buffers and the fixed-order sum without any peer -- same bits as the
+    plain calls, evaluation after evaluation."""
+    S = make_scene()
+    n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
+    want_dtrs, want_cost, want_mean = single_gpu(S, api.INTERP_HYBRID_STATIC)
+    c = api.Context()
+    try:
+        c.team_create(0, 1, n, n_a, n_t)
+        c.set_interpolation(api.INTERP_TEXTURE)
+        c.set_epipolar_plane_step(S["dkappa"])
+        c.team_radon_compute(S["imgs"], 0, n_u, n_v, interp=api.INTERP_HYBRID_STATIC)
+        c.team_set_radon_intermediates(n_u, n_v, True)
+        for step in range(3):
+            c.set_projection_matrices(S["Ps"])
+            cost = np.zeros((n, n), np.float32)
+            mean = c.team_evaluate(cost)
+            assert mean == want_mean and np.array_equal(cost, want_cost), step
+        assert np.array_equal(c.team_dtrs().cpu().numpy(), want_dtrs)
+        sets = loop_sets(S, 3)
+        c.set_projection_matrices(sets[2])
+        moved = c.team_evaluate(None)
+        assert moved > want_mean
+    finally:
+        c.close()
 
 
 def single_gpu(S, interp):
@@ -37,6 +73,7 @@ def single_gpu(S, interp):
 @pytest.mark.parametrize("world", [2, 3])
 def test_team_threads_bit_identical_to_single_gpu(world):
     import torch
+    need_gpus(world)
     from epipolarconsistency_b200.distributed import shard_bounds
     S = make_scene()
     n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
@@ -106,7 +143,8 @@ def test_team_back_to_back_evaluations_with_changing_matrices(tmp_path):
     still be summing those of evaluation k: the two alternating value buffers keep them apart (round-1 advisor finding).
     Every evaluation on every rank must be the single-GPU result bit for bit, also when the ranks drift apart (the workers
     sleep at different steps).  Ranks are processes, as in the bench (tests/team_worker.py, mode "loop")."""
-    world = 3
+    world = 2
+    need_gpus(world)
     S = make_scene()
     n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
     sets = loop_sets(S)
@@ -153,6 +191,7 @@ def _free_port():
 @pytest.mark.parametrize("engine", ["texture", "hybrid", "hybrid-static"])
 def test_team_processes_over_cuda_ipc(tmp_path, engine):
     world = 2
+    need_gpus(world)
     S = make_scene()
     port = str(_free_port())
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "team_worker.py"), str(r), str(world), port, str(tmp_path), engine],
