@@ -73,9 +73,10 @@ DATA = "synthetic: analytic 5-ellipsoid phantom, circular cone-beam trajectory, 
 MEASURED_PEAKS = os.path.join(ROOT, "MEASURED_PEAKS.json")
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 SM_COUNT = 148
-# dram__bytes_read.sum + dram__bytes_write.sum of one 128-projection launch of `python bench.py` under ncu --set full, by
-# Radon engine (profiles/INDEX.md names the capture each comes from); known for the C3 image size only
-RADON_TRAFFIC_128 = {"hybrid-static": 2.3295e9, "hybrid": 1.4524e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of `python bench.py` under ncu --set full, scaled to 128
+# projections, by Radon engine (hybrid-static: profiles/ncu_radon_hybrid4_r02.txt, a 112-projection launch: 1728.5 + 287.3 MB;
+# hybrid: profiles/ncu_radon_hybrid4_bench_r01b.txt); known for the C3 image size only
+RADON_TRAFFIC_128 = {"hybrid-static": 2.3038e9, "hybrid": 1.4524e9}
 
 
 def hbm_peak():
