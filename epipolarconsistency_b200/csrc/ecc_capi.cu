@@ -119,6 +119,8 @@ void destroy_dtr_textures(ecc_context* ctx)
 {
     for (auto t : ctx->dtr_tex_h) cudaDestroyTextureObject(t);
     ctx->dtr_tex_h.clear();
+    for (auto a : ctx->dtr_arrays) cudaFreeArray(a);
+    ctx->dtr_arrays.clear();
 }
 
 // Fills the launch record with everything that depends only on the context state.
@@ -429,6 +431,7 @@ static int install_dtrs(ecc_context* ctx, const std::vector<const float*>& ptrs,
         ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         destroy_dtr_textures(ctx);
         ctx->dtr_tex_h.resize(n_dtrs, 0);
+        static const int dev_arrays = getenv("ECC_DTR_ARRAYS") ? atoi(getenv("ECC_DTR_ARRAYS")) : 0;
         for (int k = 0; k < n_dtrs; k++) {
             cudaResourceDesc res = {};
             res.resType = cudaResourceTypePitch2D;
@@ -437,6 +440,17 @@ static int install_dtrs(ecc_context* ctx, const std::vector<const float*>& ptrs,
             res.res.pitch2D.width = n_alpha;
             res.res.pitch2D.height = n_t;
             res.res.pitch2D.pitchInBytes = sizeof(float) * pitch;
+            if (dev_arrays) {  // development: tiled CUDA arrays as the reference's (measured: same speed, same bits)
+                cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+                cudaArray_t arr = nullptr;
+                ECC_CUDA(ctx, cudaMallocArray(&arr, &desc, n_alpha, n_t));
+                ctx->dtr_arrays.push_back(arr);
+                ECC_CUDA(ctx, cudaMemcpy2DToArrayAsync(arr, 0, 0, ptrs[k], sizeof(float) * pitch, sizeof(float) * n_alpha, n_t,
+                                                       cudaMemcpyDeviceToDevice, ctx->stream));
+                res = cudaResourceDesc();
+                res.resType = cudaResourceTypeArray;
+                res.res.array.array = arr;
+            }
             cudaTextureDesc td = {};
             td.normalizedCoords = 1;  // as the reference's dtr textures (RadonIntermediate.cpp:192)
             td.filterMode = cudaFilterModeLinear;

@@ -59,6 +59,9 @@ struct Hybrid4Stage {
     int split_share = 0;              // share_override the split was computed for
     int share_override = 0;           // > 0: window path's share of the samples in per mille (ecc_radon_set_split), 0: built-in
     int map_cfg = -1;                 // window configuration the tensor maps are encoded for
+    // order of a quad's items for the static split: order[0 .. split_items) -> window path, the rest -> texture path
+    int* order_d = nullptr;
+    int order_len = 0;
 };
 
 // Peer mirrors of an output buffer (multi-GPU team, ecc_team.cu): a kernel that stores out[k] also stores the same
@@ -156,6 +159,7 @@ struct ecc_context {
     float* dtrs_owned = nullptr;    // non-null when the context owns the storage
     size_t dtrs_owned_bytes = 0;
     std::vector<cudaTextureObject_t> dtr_tex_h;
+    std::vector<cudaArray_t> dtr_arrays;   // development (ECC_DTR_ARRAYS=1): tiled copies of the dtrs instead of textures over the caller's memory
     cudaTextureObject_t* dtr_tex_d = nullptr;
     size_t dtr_tex_cap = 0;
 

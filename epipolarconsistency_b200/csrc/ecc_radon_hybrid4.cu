@@ -19,7 +19,9 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "ecc_radon_common.cuh"
 
@@ -71,8 +73,11 @@ struct Hybrid4Params {
     unsigned* counters;
     unsigned* claim;
     unsigned magic;
-    int split_items;  // < 0: two-ended run-time queue; >= 0: items [0, split_items) of every quad -> window warps, the rest
-                      // -> texture warps (reproducible results: the path of a bin is a function of the geometry alone)
+    unsigned long long* item_clock;  // development (ECC_ITEM_CLOCK=file): [2][items per quad] cycles spent per item, texture / window path
+    int ag_lo, ag_hi;  // development (ECC_ITEM_AG_LO / _HI): only the items of these angle groups are computed (timing per angle)
+    int split_items;  // < 0: two-ended run-time queue; >= 0: items order[0 .. split_items) of every quad -> window warps, the
+                      // rest -> texture warps (reproducible results: the path of a bin is a function of the geometry alone)
+    const int* order; // static split: a permutation of a quad's items (static_split_items)
     float* out;
     Mirrors mir;  // multi-GPU team: every bin is also stored into the other ranks' buffers (NVLink peer stores)
 };
@@ -337,19 +342,28 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
                 sub = __shfl_sync(0xffffffffu, sub, 0);
                 if (sub >= p.n_quads * tex_items * kSubTiles) break;
                 const int x = sub / kSubTiles;
-                item = (x / tex_items) * (p.groups_a * p.groups_t) + p.split_items + x % tex_items;
+                item = (x / tex_items) * (p.groups_a * p.groups_t) + __ldg(&p.order[p.split_items + x % tex_items]);
             } else {
                 if (lane == 0) sub = take_back(p.counters, p.claim, total_items);
                 sub = __shfl_sync(0xffffffffu, sub, 0);
                 if (sub < 0) break;
                 item = (int)total_items - 1 - sub / kSubTiles;
             }
+            {
+                const int ag_i = (item % (p.groups_a * p.groups_t)) % p.groups_a;
+                if (ag_i < p.ag_lo || ag_i > p.ag_hi) continue;
+            }
+            const long long clock0 = p.item_clock ? clock64() : 0;
             const Item4 B = item_bins4(item, sub % kSubTiles, lane, p);
             if (B.ix >= p.n_alpha || B.iy >= p.n_t) continue;
             const BinLine L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
             Sum4 r = {0.f, 0.f, 0.f, 0.f};
             if (L.valid) bin_texture4(p.texs[B.quad], L, r);
             store4(p, B, r, L.valid);
+            if (p.item_clock) {
+                __syncwarp();
+                if (lane == 0) atomicAdd(&p.item_clock[item % (p.groups_a * p.groups_t)], (unsigned long long)(clock64() - clock0));
+            }
         }
         return;
     }
@@ -366,7 +380,7 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
             if (p.split_items >= 0) {  // static split: items [0, split_items) of every quad, in order
                 const unsigned w = atomicAdd(&p.counters[0], 1u);
                 s_item = (p.split_items > 0 && w < (unsigned)(p.n_quads * p.split_items))
-                             ? (int)(w / p.split_items) * (p.groups_a * p.groups_t) + (int)(w % p.split_items) : -1;
+                             ? (int)(w / p.split_items) * (p.groups_a * p.groups_t) + __ldg(&p.order[w % p.split_items]) : -1;
             } else {
                 s_item = take_front(p.counters, p.claim, total_items);
             }
@@ -378,6 +392,11 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
         group_sync();
         const int item = s_item;
         if (item < 0) break;
+        const long long clock0 = p.item_clock ? clock64() : 0;
+        {
+            const int ag_i = (item % (p.groups_a * p.groups_t)) % p.groups_a;
+            if (ag_i < p.ag_lo || ag_i > p.ag_hi) { group_sync(); continue; }
+        }
         Item4 B = item_bins4(item, warp, lane, p);
         if (p.lane_map == 1) {  // warp = one angle, lanes = 32 t bins
             B.ix = (B.ix / kItemAngles) * kItemAngles + warp;
@@ -539,6 +558,8 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
             store4(p, B, result, L.valid);
         }
         group_sync();
+        if (p.item_clock && tid == 0)
+            atomicAdd(&p.item_clock[p.groups_a * p.groups_t + item % (p.groups_a * p.groups_t)], (unsigned long long)(clock64() - clock0));
     }
 }
 
@@ -628,9 +649,36 @@ int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int 
     static const int share_env = env_int("ECC_HYBRID4_SPLIT", 0);
     const int permille = H.share_override > 0 ? H.share_override : (share_env > 0 ? share_env : (cfg == 1 ? 605 : 580));
     const double share = permille / 1000.0;
-    double run = 0;
-    int m = 0;
-    while (m < per_quad && run + counts[m] * 0.5 < share * total) run += counts[m++];
+    std::vector<int> order(per_quad);
+    for (int k = 0; k < per_quad; k++) order[k] = k;
+    int m = -1;
+    static const char* order_file = getenv("ECC_HYBRID4_ORDER");  // development: [int split][int order[per_quad]] from a file
+    if (order_file) {
+        if (FILE* f = fopen(order_file, "rb")) {
+            int ms = 0;
+            std::vector<int> o(per_quad);
+            if (fread(&ms, sizeof(int), 1, f) == 1 && fread(o.data(), sizeof(int), per_quad, f) == (size_t)per_quad) {
+                order = o;
+                m = ms;
+            }
+            fclose(f);
+        }
+    }
+    if (m < 0) {
+        double run = 0;
+        m = 0;
+        while (m < per_quad && run + counts[order[m]] * 0.5 < share * total) run += counts[order[m++]];
+    }
+    if (H.order_len < per_quad) {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (H.order_d) cudaFree(H.order_d);
+        H.order_d = nullptr;
+        H.order_len = 0;
+        ECC_CUDA(ctx, cudaMalloc(&H.order_d, sizeof(int) * per_quad));
+        H.order_len = per_quad;
+    }
+    ECC_CUDA(ctx, cudaMemcpyAsync(H.order_d, order.data(), sizeof(int) * per_quad, cudaMemcpyHostToDevice, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `order` is a local
     H.split_items = m;
     H.split_key[0] = n_u; H.split_key[1] = n_v; H.split_key[2] = n_alpha; H.split_key[3] = n_t;
     H.split_cfg = cfg;
@@ -665,6 +713,7 @@ void free_hybrid4(ecc_context* ctx)
     if (H.pad_n) cudaFree(H.pad_n);
     if (H.pad_t) cudaFree(H.pad_t);
     if (H.queue) cudaFree(H.queue);
+    if (H.order_d) cudaFree(H.order_d);
     const int keep = H.share_override;
     H = Hybrid4Stage();
     H.share_override = keep;
@@ -791,11 +840,23 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     const double t_spacing = std::sqrt((double)n_u * n_u + (double)n_v * n_v) / n_t;
     const int cfg = cfg_env >= 0 ? cfg_env : (t_spacing <= 2.1 ? 1 : 0);
     P.split_items = -1;
+    P.order = nullptr;
     if (static_split) {
         const int rcs = static_split_items(ctx, H, n_u, n_v, n_alpha, n_t, P.groups_a, P.groups_t, cfg, &P.split_items);
         if (rcs) return rcs;
+        P.order = H.order_d;
     }
+    static const int ag_lo = env_int("ECC_ITEM_AG_LO", 0), ag_hi = env_int("ECC_ITEM_AG_HI", INT_MAX);
+    P.ag_lo = ag_lo;
+    P.ag_hi = ag_hi;
     P.mir = team_mirrors(ctx, out_d);
+    static const char* clock_file = getenv("ECC_ITEM_CLOCK");
+    P.item_clock = nullptr;
+    const size_t clock_words = 2 * (size_t)P.groups_a * P.groups_t;
+    if (clock_file) {
+        ECC_CUDA(ctx, cudaMalloc(&P.item_clock, sizeof(unsigned long long) * clock_words));
+        ECC_CUDA(ctx, cudaMemsetAsync(P.item_clock, 0, sizeof(unsigned long long) * clock_words, ctx->stream));
+    }
     static const int nt = env_int("ECC_HYBRID4_NT", 8);
     static const int ctas = env_int("ECC_HYBRID4_CTAS", 2);
     static const int mode = env_int("ECC_HYBRID_MODE", 0);
@@ -807,6 +868,18 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     const int rcl = cfg == 1 ? launch_window_config<Win4Fine>(ctx, H, P, cfg, threads, ctas, n_u, n_v)
                              : launch_window_config<Win4General>(ctx, H, P, cfg, threads, ctas, n_u, n_v);
     prof_end(ctx, slot);
+    if (clock_file) {  // development: the per-item cycle counts of this launch, overwritten by every launch
+        std::vector<unsigned long long> h(clock_words);
+        cudaMemcpyAsync(h.data(), P.item_clock, sizeof(unsigned long long) * clock_words, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(P.item_clock);
+        if (FILE* f = fopen(clock_file, "wb")) {
+            const int hdr[4] = {P.groups_a, P.groups_t, nq, 0};
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(h.data(), sizeof(unsigned long long), clock_words, f);
+            fclose(f);
+        }
+    }
     return rcl;
 }
 
