@@ -315,9 +315,10 @@ def run_pipeline(B):
     """c1 / c3: Radon intermediates of all projections -> matrices -> all pairs -> mean."""
     torch, api, ctx, pipe, args, W = B.torch, B.api, B.ctx, B.pipe, B.args, B.W
     n, n_u, n_v, n_a, n_t, world, rank = B.n, B.n_u, B.n_v, B.n_a, B.n_t, B.world, B.rank
-    bounds = B.shard_bounds(n, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
+    lo, hi, part = pipe.radon_shard(n, n_a, n_t, interp=B.radon_interp)  # the static-split engine shards in quads of projections
     images = B.synth(lo, hi)  # this rank's projections, resident
+    work = (hi - lo) if part is None else n / world           # projections' worth of Radon work on this rank
+    uploaded = n if part is None else sum(ctx.team_radon_shard(n, world, r)[1] for r in range(world))  # e2e: images over all ranks
     images_host = torch.empty((hi - lo, n_v, n_u), dtype=torch.float32, pin_memory=True)
     images_host.copy_(images)
     cost_dev = torch.zeros((n, n), dtype=torch.float32, device=B.dev)
@@ -357,7 +358,10 @@ def run_pipeline(B):
                               "hybrid-static": "as hybrid, with a fixed (geometry-only) assignment of bins to the two paths: bit-reproducible, independent of batching and sharding",
                               "texture": "texture unit (reference CUDA numerics, bit-identical Radon bins)",
                               "exact": "Radon with exact fp32 weights; metric through the texture unit"}[args.radon],
-            "sharding": f"projections block-sharded over {world} GPU(s), pairs partitioned by equal kappa samples",
+            "sharding": (f"projections block-sharded over {world} GPU(s)" if part is None else
+                         f"quads of four projections cut into {world} equal intervals, the quad on a boundary shared by its two ranks "
+                         f"(rank 0: projections {lo}..{hi - 1}, share {part[0]}/{part[2]}..{part[1]}/{part[2]} of its first / last quad)")
+                        + ", pairs partitioned by equal kappa samples",
             "exchange": ("none (1 GPU)" if world == 1 else
                          "peer stores: the Radon kernels write every bin into all ranks' buffers over NVLink, pair values published "
                          "the same way, flag barriers in peer memory; no collective on the data path" if pipe._team_key is not None else
@@ -365,21 +369,21 @@ def run_pipeline(B):
                          + (f" (team transport unavailable: {pipe.team_error})" if pipe.team_error else "")),
             "matrices": "every step gets a matrix set that differs from the previous step's by one ulp in one entry (no cached derivation / partition)",
             "l2": "inputs larger than L2 (%.2f GB images + %.2f GB dtrs per step)" % (n * n_u * n_v * 4 / 1e9, n * n_a * n_t * 4 / 1e9)}
-        line["stages"] = {"radon_intermediates_per_s": world * (hi - lo) / ((radon_ms / args.steps) * 1e-3) if radon_ms > 0 else None,
+        line["stages"] = {"radon_intermediates_per_s": world * work / ((radon_ms / args.steps) * 1e-3) if radon_ms > 0 else None,
                           "radon_kernel_ms_per_step_rank0": radon_ms / args.steps,
                           "pairs_per_s_metric_only_rank0": float(my_hi - my_lo) / ((pairs_ms / args.steps) * 1e-3) if pairs_ms > 0 else None,
                           "pair_kernel_ms_per_step_rank0": pairs_ms / args.steps,
                           "kernel_share_of_step": {k: v[0] / ms_total for k, v in prof.items()}, "mean_ecc": mean}
         line["e2e"] = {"value": n_pairs / (ms_step_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_step_e2e,
-                       "h2d_bytes_per_step": int(n) * n_u * n_v * 4 + n * 96, "d2h_bytes_per_step": n * n * 4 + 8 * world,
+                       "h2d_bytes_per_step": int(uploaded) * n_u * n_v * 4 + n * 96, "d2h_bytes_per_step": n * n * 4 + 8 * world,
                        "mean_ecc": mean_e2e}
         line["gpu_launches"] = int(sum(v[1] for v in prof.values()))
         line["clocks"] = clocks
-        line["roofline"] = B.radon_roofline(prof, clocks, hi - lo)
+        line["roofline"] = B.radon_roofline(prof, clocks, work)
         line["roofline_pairs"] = B.pairs_roofline(prof, float(counts[int(my_lo):int(my_hi)].sum()))
         if args.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(W, B.Ps, full_dtrs=pipe._full)
-            line["ref_cuda"] = ref_cuda_leg(B, images, pipe._full, radon_ms / args.steps / max(hi - lo, 1), pairs_ms / args.steps, ms_step)
+            line["ref_cuda"] = ref_cuda_leg(B, images, pipe._full, radon_ms / args.steps / max(work, 1), pairs_ms / args.steps, ms_step)
         print(json.dumps(line))
 
 
@@ -387,8 +391,9 @@ def run_radon(B):
     """c2: the Radon stage alone, sharded by projection; on several GPUs every rank ends with all intermediates."""
     torch, api, ctx, pipe, args, W = B.torch, B.api, B.ctx, B.pipe, B.args, B.W
     n, n_u, n_v, n_a, n_t, world, rank = B.n, B.n_u, B.n_v, B.n_a, B.n_t, B.world, B.rank
-    bounds = B.shard_bounds(n, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
+    lo, hi, part = pipe.radon_shard(n, n_a, n_t, interp=B.radon_interp)
+    work = (hi - lo) if part is None else n / world
+    uploaded = n if part is None else sum(ctx.team_radon_shard(n, world, r)[1] for r in range(world))
     images = B.synth(lo, hi)
     images_host = torch.empty((hi - lo, n_v, n_u), dtype=torch.float32, pin_memory=True)
     images_host.copy_(images)
@@ -414,17 +419,17 @@ def run_radon(B):
                                       + ("" if world == 1 else " (peer stores from inside the kernel)" if pipe._team_key is not None else " (NCCL all-gather)"),
                           "l2": "inputs larger than L2 (%.2f GB images, %.2f GB dtrs per step)" % (n * n_u * n_v * 4 / 1e9, n * n_a * n_t * 4 / 1e9)}
         line["stages"] = {"radon_kernel_ms_per_step_rank0": prof["radon"][0] / args.steps,
-                          "ms_per_projection_rank0": prof["radon"][0] / args.steps / max(hi - lo, 1),
+                          "ms_per_projection_rank0": prof["radon"][0] / args.steps / max(work, 1),
                           "kernel_share_of_step": {k: v[0] / ms_total for k, v in prof.items()},
                           "checksum": float(full[lo:hi].double().abs().sum().item())}
         line["e2e"] = {"value": n / (ms_step_e2e * 1e-3), "unit": "intermediates/s", "ms_per_step": ms_step_e2e,
-                       "h2d_bytes_per_step": int(n) * n_u * n_v * 4, "d2h_bytes_per_step": int(n) * n_a * n_t * 4}
+                       "h2d_bytes_per_step": int(uploaded) * n_u * n_v * 4, "d2h_bytes_per_step": int(uploaded) * n_a * n_t * 4}
         line["gpu_launches"] = int(sum(v[1] for v in prof.values()))
         line["clocks"] = clocks
-        line["roofline"] = B.radon_roofline(prof, clocks, hi - lo)
+        line["roofline"] = B.radon_roofline(prof, clocks, work)
         if args.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(W, B.Ps, full_dtrs=None, radon_only=True)
-            line["ref_cuda"] = ref_cuda_leg(B, images, None, prof["radon"][0] / args.steps / max(hi - lo, 1), None, ms_step)
+            line["ref_cuda"] = ref_cuda_leg(B, images, None, prof["radon"][0] / args.steps / max(work, 1), None, ms_step)
         print(json.dumps(line))
 
 

@@ -66,6 +66,8 @@ SIGNATURES = {
     "ecc_team_block": (C.c_int, [c_ctx, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "ecc_team_destroy": (C.c_int, [c_ctx]),
     "ecc_team_radon_compute": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ecc_team_radon_shard": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 5),
+    "ecc_team_radon_compute_part": (C.c_int, [c_ctx, c_vp] + [C.c_int] * 10),
     "ecc_team_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),
     "ecc_team_barrier": (C.c_int, [c_ctx]),
     "ecc_make_circular_trajectory": (None, [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, c_vp]),

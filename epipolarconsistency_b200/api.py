@@ -352,6 +352,18 @@ class Context:
         self._check(self.lib.ecc_team_radon_compute(self.h, _ptr(images, _F32) if n_local else None, int(first), n_local, n_u, n_v,
                                                     filter, post, interp))
 
+    def team_radon_shard(self, n_total, world, rank):
+        """Sharding in quads of projections for the static-split engine: (first, count, (lo_num, hi_num, den))."""
+        v = [C.c_int() for _ in range(5)]
+        self._check(self.lib.ecc_team_radon_shard(int(n_total), int(world), int(rank), *[C.byref(x) for x in v]))
+        return v[0].value, v[1].value, (v[2].value, v[3].value, v[4].value)
+
+    def team_radon_compute_part(self, images, first, part, n_u, n_v, filter=FILTER_DERIVATIVE, post=POST_IDENTITY, interp=INTERP_HYBRID_STATIC):
+        """images: projections [first, first + count) of team_radon_shard; part: its (lo_num, hi_num, den)."""
+        n_local = 0 if images is None else images.shape[0]
+        self._check(self.lib.ecc_team_radon_compute_part(self.h, _ptr(images, _F32) if n_local else None, int(first), n_local, int(part[0]),
+                                                         int(part[1]), int(part[2]), n_u, n_v, filter, post, interp))
+
     def team_set_radon_intermediates(self, n_u, n_v, is_derivative=True):
         """setRadonIntermediates with the team block's dtrs (borrowed, zero copy)."""
         _, d = self.team_block()

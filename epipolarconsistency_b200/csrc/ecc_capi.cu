@@ -282,7 +282,7 @@ int ecc_radon_compute(ecc_context* ctx, const float* images, int n_images, int n
 int eccb200::fill_pair_launch(ecc_context* ctx, PairLaunch& L) { return fill_launch(ctx, L); }
 
 int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_images, int n_u, int n_v, int n_alpha, int n_t,
-                                int filter, int post, int interp, float* dtrs_out, bool final_sync)
+                                int filter, int post, int interp, float* dtrs_out, bool final_sync, QuadPart part)
 {
     if (!images || !dtrs_out || n_images < 0 || n_u < 2 || n_v < 2 || n_alpha < 1 || n_t < 1)
         return fail(ctx, ECC_ERR_INVALID, "ecc_radon_compute: bad argument");
@@ -293,7 +293,7 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
     if (n_images == 0) return ECC_OK;
     const bool in_dev = is_device_pointer(images), out_dev = is_device_pointer(dtrs_out);
     const size_t img_elems = (size_t)n_u * n_v, dtr_elems = (size_t)n_alpha * n_t;
-    if (in_dev && out_dev) return radon_batch(ctx, images, n_images, n_u, n_v, n_alpha, n_t, filter, post, interp, dtrs_out);
+    if (in_dev && out_dev) return radon_batch(ctx, images, n_images, n_u, n_v, n_alpha, n_t, filter, post, interp, dtrs_out, part);
     // Host memory on either side: stream the batch through device staging in chunks.  Host images go through two
     // staging buffers on a copy stream of their own, so that the upload of chunk i+1 runs under the kernels of chunk i
     // (the first chunk is small: its upload is the only one that is exposed).
@@ -337,7 +337,7 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
             src = stage;
         }
         float* dst = out_dev ? dtrs_out + (size_t)first * dtr_elems : ctx->out_stage_d;
-        rc = radon_batch(ctx, src, n, n_u, n_v, n_alpha, n_t, filter, post, interp, dst);
+        rc = radon_batch(ctx, src, n, n_u, n_v, n_alpha, n_t, filter, post, interp, dst, part.sub(first == 0, first + n == n_images));
         if (rc) return rc;
         if (!in_dev) ECC_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
         if (!out_dev)

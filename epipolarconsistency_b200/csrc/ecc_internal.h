@@ -288,9 +288,26 @@ int batch_begin(ecc_context* ctx, const int* idx4, int n_pairs, PairLaunch& L, c
 int batch_reserve(ecc_context* ctx, int n_sets, bool want_matrices);
 int batch_finish(ecc_context* ctx, PairLaunch& L, int n_sets, float* out, double* means);
 
+// A call that computes only PART of its first and of its last quad of projections (static-split engine; a team shares the
+// quad that straddles two ranks' shards, ecc_team_radon_compute_part): of the first quad the share from lo_num / den on,
+// of the last quad the share up to hi_num / den, of both item lists (window path, texture path) alike.  Whole: {0, den, den}.
+struct QuadPart {
+    int lo_num = 0, hi_num = 1, den = 1;
+    bool whole() const { return lo_num == 0 && hi_num == den; }
+    // the part that applies to a sub-range of the call's images: its first / last quad is the call's first / last or not
+    QuadPart sub(bool has_first, bool has_last) const
+    {
+        QuadPart q;
+        q.den = den;
+        q.lo_num = has_first ? lo_num : 0;
+        q.hi_num = has_last ? hi_num : den;
+        return q;
+    }
+};
+
 // ---- launchers (ecc_radon.cu) ----
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
-                int n_alpha, int n_t, int filter, int post, int interp, float* out_d);
+                int n_alpha, int n_t, int filter, int post, int interp, float* out_d, QuadPart part = QuadPart());
 void free_image_pool(ecc_context* ctx);
 int ramp_filter(ecc_context* ctx, float* dtrs_d, int n, int n_alpha, int n_t);
 // ---- launchers (ecc_radon_hybrid.cu) ----
@@ -299,7 +316,7 @@ int radon_hybrid_launch(ecc_context* ctx, const cudaTextureObject_t* texs_d, con
 void free_hybrid(ecc_context* ctx);
 // ---- launchers (ecc_radon_hybrid4.cu) ----
 int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d,
-                         bool static_split = false);
+                         bool static_split = false, QuadPart part = QuadPart());
 void free_hybrid4(ecc_context* ctx);
 int radon_hybrid4_reserve(ecc_context* ctx, int n_u, int n_v, int n_images);
 int radon_hybrid4_calibrate(ecc_context* ctx, int n_u, int n_v, int n_alpha, int n_t, int repeats, int* permille);
@@ -313,7 +330,7 @@ int team_publish(ecc_context* ctx, const void* ptr, size_t bytes);
 int team_barrier(ecc_context* ctx);
 void team_free(ecc_context* ctx);
 int radon_compute_impl(ecc_context* ctx, const float* images, int n_images, int n_u, int n_v, int n_alpha, int n_t, int filter,
-                       int post, int interp, float* dtrs_out, bool sync_device_path);
+                       int post, int interp, float* dtrs_out, bool sync_device_path, QuadPart part = QuadPart());
 
 // ---- launchers (ecc_preprocess.cu) ----
 int preprocess_batch(ecc_context* ctx, float* images_d, int n, int n_u, int n_v, const ecc_preprocess_params* pp, const double* Ps_h);

@@ -329,7 +329,7 @@ void free_image_pool(ecc_context* ctx)
 // images_d / out_d are device pointers.  The batch is processed in chunks of at most kPool images:
 // copy the chunk into the array pool (device-to-device, async), one kernel launch per chunk.
 int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, int n_v,
-                int n_alpha, int n_t, int filter, int post, int interp, float* out_d)
+                int n_alpha, int n_t, int filter, int post, int interp, float* out_d, QuadPart part)
 {
     constexpr int kPool = 64;  // projections per launch (texture engines: one CUDA array per projection)
     // the quad kernel is persistent: every launch ends with a tail (CTAs run dry one by one) and starts with its image
@@ -337,6 +337,8 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
     constexpr int kPoolQuad = 128;
     const int pool = n_images < kPool ? n_images : kPool;
     const bool deriv = (filter == ECC_FILTER_DERIVATIVE);  // ramp: plain line integrals first (RadonIntermediate.cu:160-168)
+    if (!part.whole() && !(interp == ECC_INTERP_HYBRID_STATIC && deriv))
+        return fail(ctx, ECC_ERR_INVALID, "parts of a quad of projections: only the static-split engine (ECC_INTERP_HYBRID_STATIC, derivative filter) shares a quad");
     // development knob: ECC_HYBRID_QUADS=0 keeps the one-image-per-item hybrid kernel for everything
     static const int use_quads = getenv("ECC_HYBRID_QUADS") ? atoi(getenv("ECC_HYBRID_QUADS")) : 1;
     if (interp == ECC_INTERP_HYBRID_STATIC && deriv) {
@@ -345,7 +347,7 @@ int radon_batch(ecc_context* ctx, const float* images_d, int n_images, int n_u, 
         for (int first = 0; first < n_images; first += kPoolQuad) {
             const int n = (n_images - first < kPoolQuad) ? n_images - first : kPoolQuad;
             const int rc4 = radon_hybrid4_launch(ctx, images_d + (size_t)first * n_u * n_v, n, n_u, n_v, n_alpha, n_t, post,
-                                                 out_d + (size_t)first * n_t * n_alpha, true);
+                                                 out_d + (size_t)first * n_t * n_alpha, true, part.sub(first == 0, first + n == n_images));
             if (rc4) return rc4;
         }
         return ECC_OK;

@@ -78,6 +78,10 @@ struct Hybrid4Params {
     int split_items;  // < 0: two-ended run-time queue; >= 0: items order[0 .. split_items) of every quad -> window warps, the
                       // rest -> texture warps (reproducible results: the path of a bin is a function of the geometry alone)
     const int* order; // static split: a permutation of a quad's items (static_split_items)
+    // static split: the launch's share of the two item lists (QuadPart: a team shares the quad that straddles two ranks'
+    // shards) -- window entries [w_begin, w_end) of n_quads * split_items, texture sub-tiles [x_begin, x_end) of
+    // n_quads * (items per quad - split_items) * kSubTiles
+    unsigned w_begin, w_end, x_begin, x_end;
     float* out;
     Mirrors mir;  // multi-GPU team: every bin is also stored into the other ranks' buffers (NVLink peer stores)
 };
@@ -338,9 +342,9 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
             int sub = 0, item;
             if (p.split_items >= 0) {  // static split: sub-tiles of the items [split_items, per_quad) of every quad, in order
                 const int tex_items = p.groups_a * p.groups_t - p.split_items;
-                if (lane == 0) sub = (int)atomicAdd(&p.counters[1], 1u);
+                if (lane == 0) sub = (int)(atomicAdd(&p.counters[1], 1u) + p.x_begin);
                 sub = __shfl_sync(0xffffffffu, sub, 0);
-                if (sub >= p.n_quads * tex_items * kSubTiles) break;
+                if ((unsigned)sub >= p.x_end) break;
                 const int x = sub / kSubTiles;
                 item = (x / tex_items) * (p.groups_a * p.groups_t) + __ldg(&p.order[p.split_items + x % tex_items]);
             } else {
@@ -378,8 +382,8 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
     for (;;) {
         if (tid == 0) {
             if (p.split_items >= 0) {  // static split: items [0, split_items) of every quad, in order
-                const unsigned w = atomicAdd(&p.counters[0], 1u);
-                s_item = (p.split_items > 0 && w < (unsigned)(p.n_quads * p.split_items))
+                const unsigned w = atomicAdd(&p.counters[0], 1u) + p.w_begin;
+                s_item = (p.split_items > 0 && w < p.w_end)
                              ? (int)(w / p.split_items) * (p.groups_a * p.groups_t) + __ldg(&p.order[w % p.split_items]) : -1;
             } else {
                 s_item = take_front(p.counters, p.claim, total_items);
@@ -792,8 +796,11 @@ int radon_hybrid4_reserve(ecc_context* ctx, int n_u, int n_v, int n) { return en
 
 // n images (device, dense) -> their Radon intermediates; works on ceil(n/4) quads.
 int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u, int n_v, int n_alpha, int n_t, int post, float* out_d,
-                         bool static_split)
+                         bool static_split, QuadPart part)
 {
+    if (!part.whole() && !static_split) return fail(ctx, ECC_ERR_INVALID, "parts of a quad need the static split");
+    if (part.den < 1 || part.lo_num < 0 || part.lo_num >= part.den || part.hi_num < 1 || part.hi_num > part.den)
+        return fail(ctx, ECC_ERR_INVALID, "radon_hybrid4_launch: bad part of a quad");
     Hybrid4Stage& H = ctx->hybrid4;
     const int nq = (n + 3) / 4;
     {
@@ -841,10 +848,19 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     const int cfg = cfg_env >= 0 ? cfg_env : (t_spacing <= 2.1 ? 1 : 0);
     P.split_items = -1;
     P.order = nullptr;
+    P.w_begin = P.w_end = P.x_begin = P.x_end = 0;
     if (static_split) {
         const int rcs = static_split_items(ctx, H, n_u, n_v, n_alpha, n_t, P.groups_a, P.groups_t, cfg, &P.split_items);
         if (rcs) return rcs;
         P.order = H.order_d;
+        // the launch's share of the item lists: same floor() on both sides of a cut, so two ranks that share a quad
+        // (one with hi = k / den, the other with lo = k / den) take complementary entries
+        const long long split = P.split_items, subs = (long long)(P.groups_a * P.groups_t - P.split_items) * kSubTiles;
+        if (nq == 1 && part.lo_num >= part.hi_num) return fail(ctx, ECC_ERR_INVALID, "radon_hybrid4_launch: empty part of a quad");
+        P.w_begin = (unsigned)(split * part.lo_num / part.den);
+        P.w_end = (unsigned)((long long)(nq - 1) * split + split * part.hi_num / part.den);
+        P.x_begin = (unsigned)(subs * part.lo_num / part.den);
+        P.x_end = (unsigned)((long long)(nq - 1) * subs + subs * part.hi_num / part.den);
     }
     static const int ag_lo = env_int("ECC_ITEM_AG_LO", 0), ag_hi = env_int("ECC_ITEM_AG_HI", INT_MAX);
     P.ag_lo = ag_lo;

@@ -279,26 +279,55 @@ int ecc_team_barrier(ecc_context* ctx)
     return team_barrier(ctx);
 }
 
-int ecc_team_radon_compute(ecc_context* ctx, const float* images, int first, int n_local, int n_u, int n_v, int filter,
-                           int post_process, int interp)
+int ecc_team_radon_shard(int n_total, int world, int rank, int* first, int* count, int* lo_num, int* hi_num, int* den)
+{
+    if (n_total < 0 || world < 1 || rank < 0 || rank >= world || !first || !count || !lo_num || !hi_num || !den) return ECC_ERR_INVALID;
+    // Q quads of four projections, cut into `world` equal intervals of Q / world quads each (a rational number of quads):
+    // rank r takes [r Q / world, (r + 1) Q / world).  The quad an interval boundary falls into is shared by the two ranks.
+    const long long Q = (n_total + 3) / 4, a = (long long)rank * Q, b = (long long)(rank + 1) * Q;
+    const long long first_quad = a / world, end_quad = (b + world - 1) / world;  // quads [first_quad, end_quad) are touched
+    *den = world;
+    *lo_num = (int)(a % world);
+    *hi_num = (b % world) ? (int)(b % world) : world;
+    *first = (int)(4 * first_quad);
+    const long long last = 4 * end_quad < n_total ? 4 * end_quad : n_total;
+    *count = (int)(last - 4 * first_quad > 0 ? last - 4 * first_quad : 0);
+    if (*count == 0) { *first = 0; *lo_num = 0; *hi_num = world; }
+    return ECC_OK;
+}
+
+int ecc_team_radon_compute_part(ecc_context* ctx, const float* images, int first, int n_local, int lo_num, int hi_num, int den, int n_u,
+                                int n_v, int filter, int post_process, int interp)
 {
     if (!ctx) return ECC_ERR_INVALID;
     DeviceGuard g(ctx);
     Team& T = ctx->team;
     if (!T.connected) return fail(ctx, ECC_ERR_STATE, "team not connected");
     if (first < 0 || n_local < 0 || first + n_local > T.n_total) return fail(ctx, ECC_ERR_INVALID, "ecc_team_radon_compute: projection range outside the team's data set");
+    QuadPart part;
+    part.lo_num = lo_num;
+    part.hi_num = hi_num;
+    part.den = den;
+    if (den < 1 || lo_num < 0 || lo_num >= den || hi_num < 1 || hi_num > den) return fail(ctx, ECC_ERR_INVALID, "ecc_team_radon_compute_part: bad part");
+    if (!part.whole() && first % 4 != 0) return fail(ctx, ECC_ERR_INVALID, "ecc_team_radon_compute_part: a shared quad starts at a multiple of four projections");
     int rc = ECC_OK;
     if (n_local > 0) {
         if (!images) return fail(ctx, ECC_ERR_INVALID, "ecc_team_radon_compute: null images");
         T.mirror_radon = true;
         rc = radon_compute_impl(ctx, images, n_local, n_u, n_v, T.n_alpha, T.n_t, filter, post_process, interp,
-                                T.dtrs() + (size_t)first * T.n_t * T.n_alpha, false);
+                                T.dtrs() + (size_t)first * T.n_t * T.n_alpha, false, part);
         T.mirror_radon = false;
         if (rc) return rc;
     }
     if ((rc = team_barrier(ctx))) return rc;
     if (n_local > 0 && !is_device_pointer(images)) ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's host buffer is free again
     return ECC_OK;
+}
+
+int ecc_team_radon_compute(ecc_context* ctx, const float* images, int first, int n_local, int n_u, int n_v, int filter,
+                           int post_process, int interp)
+{
+    return ecc_team_radon_compute_part(ctx, images, first, n_local, 0, 1, 1, n_u, n_v, filter, post_process, interp);
 }
 
 int ecc_team_evaluate(ecc_context* ctx, float* cost_image, double* mean)

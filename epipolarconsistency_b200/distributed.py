@@ -83,17 +83,31 @@ class ShardedPipeline:
         return True
 
     # -- stage 1 + exchange -------------------------------------------------------------------------------
+    def radon_shard(self, n_total, n_alpha, n_t, interp=None, filter=0):
+        """(lo, hi, part): the projections [lo, hi) this rank supplies to radon_allgather.  Contiguous blocks of n / world
+        projections -- except with the team transport and the static-split engine (interp 3, derivative filter), which
+        works on quads of projections: there the quads are cut into `world` equal intervals and the quad a boundary falls
+        into is shared by the two neighbours (`part`, include/ecc_b200.h ecc_team_radon_shard): no rank pads a quad."""
+        if self.world > 1 and interp == 3 and filter == 0 and hasattr(self.c, "team_radon_shard") and self._ensure_team(n_total, n_alpha, n_t):
+            first, count, part = self.c.team_radon_shard(n_total, self.world, self.rank)
+            return first, first + count, part
+        bounds = shard_bounds(n_total, self.world)
+        return bounds[self.rank], bounds[self.rank + 1], None
+
     def radon_allgather(self, local_images, n_total, n_alpha, n_t, **radon_kwargs):
-        """local_images: this rank's block of projections (torch tensor on self.device, or pinned host tensor /
+        """local_images: this rank's projections [lo, hi) of radon_shard (torch tensor on self.device, or pinned host tensor /
         numpy array for the end-to-end path).  Returns the full (n_total, n_t, n_alpha) dtr tensor."""
         import torch
-        bounds = shard_bounds(n_total, self.world)
-        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        lo, hi, part = self.radon_shard(n_total, n_alpha, n_t, radon_kwargs.get("interp"), radon_kwargs.get("filter", 0))
         assert local_images.shape[0] == hi - lo, (local_images.shape, lo, hi)
         if self.world > 1 and self._ensure_team(n_total, n_alpha, n_t):
             n_v, n_u = local_images.shape[1], local_images.shape[2]
-            self.c.team_radon_compute(local_images if hi > lo else None, lo, n_u, n_v, **radon_kwargs)
+            if part is not None:
+                self.c.team_radon_compute_part(local_images if hi > lo else None, lo, part, n_u, n_v, **radon_kwargs)
+            else:
+                self.c.team_radon_compute(local_images if hi > lo else None, lo, n_u, n_v, **radon_kwargs)
             return self._full
+        bounds = shard_bounds(n_total, self.world)
         if self._full is None or tuple(self._full.shape) != (n_total, n_t, n_alpha):
             self._full = torch.empty((n_total, n_t, n_alpha), dtype=torch.float32, device=self.device)
         full = self._full

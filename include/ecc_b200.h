@@ -308,6 +308,16 @@ int ecc_team_destroy(ecc_context* ctx);
  * the intermediates of ALL ranks.  Asynchronous for device images. */
 int ecc_team_radon_compute(ecc_context* ctx, const float* images, int first, int n_local, int n_u, int n_v, int filter,
                            int post_process, int interp);
+/* Sharding in QUADS of projections for the static-split engine (ECC_INTERP_HYBRID_STATIC works on four interleaved
+ * projections at a time; a shard that is not a whole number of quads pads its last one -- 496 projections on 8 GPUs are 15.5
+ * quads per rank, 3 % of the step).  ecc_team_radon_shard cuts the ceil(n_total / 4) quads into `world` equal intervals; the
+ * quad an interval boundary falls into is computed by BOTH neighbours, each taking its share (lo_num / den .. hi_num / den)
+ * of the quad's bins -- which bins follows from the geometry alone, every bin is computed by exactly one rank, with the
+ * arithmetic a single GPU would use, and stored into all ranks' blocks.  A pure function (no context): rank r supplies
+ * projections [first, first + count) -- up to three more than n_total / world -- to ecc_team_radon_compute_part. */
+int ecc_team_radon_shard(int n_total, int world, int rank, int* first, int* count, int* lo_num, int* hi_num, int* den);
+int ecc_team_radon_compute_part(ecc_context* ctx, const float* images, int first, int n_local, int lo_num, int hi_num, int den, int n_u,
+                                int n_v, int filter, int post_process, int interp);
 /* All pairs, cut into world ranges of equal kappa-sample count (ecc_partition_pairs); this rank scores range [rank].
  * cost_image [h|d], nullable: as ecc_evaluate, complete on every rank.  mean: over all pairs, the same on every rank. */
 int ecc_team_evaluate(ecc_context* ctx, float* cost_image, double* mean);

@@ -28,13 +28,12 @@ def main():
         S = make_scene()
         n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
         ctx = api.Context(dev_index)
-        bounds = shard_bounds(n, world)
-        lo, hi = bounds[rank], bounds[rank + 1]
-        local = torch.from_numpy(S["imgs"][lo:hi]).cuda()
         pipe = ShardedPipeline(ctx, rank, world, device=torch.device("cuda", dev_index), transport="team")
+        interp = {"texture": api.INTERP_TEXTURE, "hybrid": api.INTERP_HYBRID, "hybrid-static": api.INTERP_HYBRID_STATIC}[engine]
+        lo, hi, _ = pipe.radon_shard(n, n_a, n_t, interp)  # the static-split engine shards in quads of projections
+        local = torch.from_numpy(S["imgs"][lo:hi]).cuda()
         ctx.set_interpolation(api.INTERP_TEXTURE)
         ctx.set_epipolar_plane_step(S["dkappa"])
-        interp = {"texture": api.INTERP_TEXTURE, "hybrid": api.INTERP_HYBRID, "hybrid-static": api.INTERP_HYBRID_STATIC}[engine]
         if mode == "loop":
             # optimiser loop: intermediates once, then evaluation after evaluation with other matrices and NO Radon barrier in
             # between; the ranks drift apart on purpose

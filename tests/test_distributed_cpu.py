@@ -84,21 +84,56 @@ class StubTeam(StubCompute):
         total = self.n * (self.n - 1) // 2
         return self.evaluate_range(0, total, cost_image) / total
 
+    # sharding in quads of projections (static-split engine): the library's own shard function (host only, no GPU needed)
+    def team_radon_shard(self, n_total, world, rank):
+        import ctypes as C
+        from epipolarconsistency_b200 import _lib
+        v = [C.c_int() for _ in range(5)]
+        assert _lib.load().ecc_team_radon_shard(n_total, world, rank, *[C.byref(x) for x in v]) == 0
+        return v[0].value, v[1].value, (v[2].value, v[3].value, v[4].value)
+
+    def team_radon_compute_part(self, images, first, part, n_u, n_v, **kw):
+        """Emulation: a rank "computes" the bins of its whole quads and, of a shared quad, the bins of its share of the
+        flattened bin list; the peer stores are an all-gather of (value, written) and every bin must be written ONCE."""
+        n_total, n_t, n_alpha = self._full.shape
+        lo_num, hi_num, den = part
+        val = torch.zeros((n_total, n_t * n_alpha))
+        hit = torch.zeros((n_total, n_t * n_alpha))
+        count = 0 if images is None else images.shape[0]
+        bins = n_t * n_alpha
+        for k in range(count):
+            quad = k // 4
+            b0 = bins * lo_num // den if quad == 0 else 0
+            b1 = bins * hi_num // den if quad == (count + 3) // 4 - 1 else bins
+            val[first + k, b0:b1] = images[k].mean()
+            hit[first + k, b0:b1] = 1
+        vals = [torch.zeros_like(val) for _ in range(self.world)]
+        hits = [torch.zeros_like(hit) for _ in range(self.world)]
+        dist.all_gather(vals, val)
+        dist.all_gather(hits, hit)
+        assert torch.equal(sum(hits), torch.ones_like(hit)), "a bin was computed twice or not at all"
+        self._full.copy_(sum(vals).reshape(n_total, n_t, n_alpha))
+
 
 def _worker(rank, world, port, n_total, results, mode="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        bounds = shard_bounds(n_total, world)
-        lo, hi = bounds[rank], bounds[rank + 1]
-        local = torch.stack([torch.full((6, 8), float(k)) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 6, 8))
         if mode in ("nccl", "batch"):
             compute, transport = StubCompute(n_total, world), "nccl"
         else:
             compute, transport = StubTeam(n_total, world, rank, fail_create=(mode == "team-fails" and rank == 1)), "team"
         pipe = ShardedPipeline(compute, rank, world, device="cpu", transport=transport)
-        full = pipe.radon_allgather(local, n_total, 5, 4)
+        kw = {"interp": 3} if mode == "team-quads" else {}  # the static-split engine: sharded in quads of projections
+        lo, hi, part = pipe.radon_shard(n_total, 5, 4, **kw)
+        if mode == "team-quads":
+            assert part is not None and lo % 4 == 0
+        else:
+            bounds = shard_bounds(n_total, world)
+            assert (lo, hi, part) == (bounds[rank], bounds[rank + 1], None)
+        local = torch.stack([torch.full((6, 8), float(k)) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 6, 8))
+        full = pipe.radon_allgather(local, n_total, 5, 4, **kw)
         cost = torch.zeros((n_total, n_total))
         mean = pipe.evaluate_all_pairs(n_total, cost)
         extra = None
@@ -139,7 +174,7 @@ def _check(n_total, mode="nccl"):
     want_mean = np.mean([1000.0 * i + j for i, j in pairs])
     for rank in (0, 1):
         dtr_vals, mean, cost, extra = res[rank]
-        if mode == "team":  # both ranks connected with the handles in rank order
+        if mode in ("team", "team-quads"):  # both ranks connected with the handles in rank order
             assert extra[0] == "team" and extra[1] is None
             assert extra[2] == [b"handle-of-rank-0", b"handle-of-rank-1"]
         if mode == "team-fails":  # one rank could not create its block: BOTH fall back to the collectives and say why
@@ -161,6 +196,12 @@ def test_world2_ragged_shards():
 
 def test_world2_team_transport():
     _check(5, mode="team")
+
+
+def test_world2_team_shards_in_quads_for_the_static_split_engine():
+    """11 projections = 3 quads over 2 ranks: 1.5 quads each, the middle quad shared; every bin written exactly once."""
+    _check(11, mode="team-quads")
+    _check(8, mode="team-quads")  # 2 quads: nothing shared
 
 
 def test_world2_team_falls_back_together():

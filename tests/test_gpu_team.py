@@ -55,6 +55,38 @@ def test_team_of_one_is_the_plain_path():
         c.close()
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_quad_shards_of_a_team_compose_to_the_single_gpu_result(world):
+    """Sharding in quads of projections (ecc_team_radon_shard / ecc_team_radon_compute_part): the shards of `world` ranks,
+    computed one after the other by a team of one into the same block, give the single-GPU intermediates bit for bit -- every
+    bin of a shared quad is computed by exactly one of the two ranks that share it, with the same arithmetic."""
+    S = make_scene()
+    n, n_u, n_v, n_a, n_t = S["n"], S["n_u"], S["n_v"], S["n_a"], S["n_t"]
+    want_dtrs, _, _ = single_gpu(S, api.INTERP_HYBRID_STATIC)
+    c = api.Context()
+    try:
+        c.team_create(0, 1, n, n_a, n_t)
+        c.team_dtrs().fill_(float("nan"))
+        covered = np.zeros(n, np.int32)
+        shared = 0
+        for r in range(world):
+            first, count, part = c.team_radon_shard(n, world, r)
+            assert first % 4 == 0 and 0 <= first and first + count <= n
+            covered[first:first + count] += 1
+            shared += part[0] != 0
+            if count:
+                c.team_radon_compute_part(S["imgs"][first:first + count], first, part, n_u, n_v, interp=api.INTERP_HYBRID_STATIC)
+        assert covered.min() >= 1
+        assert (shared > 0) == (((n + 3) // 4) % world != 0)  # 11 projections are 3 quads: shared among 2 and among 8 ranks
+        assert np.array_equal(c.team_dtrs().cpu().numpy(), want_dtrs)
+        # engines without a static split refuse a part of a quad instead of computing something else
+        first, count, part = c.team_radon_shard(n, 2, 0)
+        with pytest.raises(api.EccError):
+            c.team_radon_compute_part(S["imgs"][first:first + count], first, part, n_u, n_v, interp=api.INTERP_TEXTURE)
+    finally:
+        c.close()
+
+
 def single_gpu(S, interp):
     c = api.Context()
     try:

@@ -131,3 +131,35 @@ def test_library_models_match_numpy_and_are_exact_where_the_reference_branches()
     got, want = api.model_camera_similarity_2d3d(Ps[1], x), api.camera_similarity_2d3d(Ps[1], x)
     assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
     assert np.array_equal(api.model_camera_similarity_2d3d(Ps[1], [0] * 11), Ps[1])
+
+
+def test_team_radon_shard_tiles_the_quads():
+    """ecc_team_radon_shard (host only): the ranks' intervals tile the ceil(n / 4) quads exactly -- rank r ends where rank r + 1
+    begins, in the same quad at the same fraction -- and every rank is asked for whole quads of projections."""
+    import ctypes as C
+    lib = _lib.load()
+
+    def shard(n, world, rank):
+        v = [C.c_int() for _ in range(5)]
+        assert lib.ecc_team_radon_shard(n, world, rank, *[C.byref(x) for x in v]) == 0
+        return [x.value for x in v]
+
+    for n in (0, 1, 3, 4, 5, 11, 62, 248, 496, 497, 1000):
+        for world in (1, 2, 3, 4, 7, 8, 16):
+            Q = (n + 3) // 4
+            pos = 0  # in units of 1 / world quads
+            for r in range(world):
+                first, count, lo, hi, den = shard(n, world, r)
+                assert den == world and 0 <= lo < den and 1 <= hi <= den
+                if count == 0:
+                    assert Q == 0
+                    continue
+                assert first % 4 == 0 and first + count <= n
+                assert (first // 4) * den + lo == pos, (n, world, r)      # begins where the previous rank ended
+                last_quad = (first + count + 3) // 4 - 1
+                pos = last_quad * den + hi
+                assert pos == (r + 1) * Q, (n, world, r)                   # equal shares of Q quads
+                assert count == min(n, 4 * (last_quad + 1)) - first
+            assert pos == world * Q or Q == 0
+    assert shard(496, 8, 0) == [0, 64, 0, 4, 8] and shard(496, 8, 1) == [60, 64, 4, 8, 8]
+    assert lib.ecc_team_radon_shard(8, 0, 0, None, None, None, None, None) != 0
