@@ -8,6 +8,6 @@ interface; `distributed` shards the path over the GPUs of one node with torch.di
 from ._lib import LIB_PATH, EccLibraryMissing, load  # noqa: F401
 from .api import (  # noqa: F401
     FILTER_DERIVATIVE, FILTER_NONE, FILTER_RAMP, INTERP_EXACT, INTERP_TEXTURE, POST_IDENTITY, POST_LOG, POST_SQRT,
-    Context, EccError, MetricRadonIntermediate, RadonIntermediate, compute_radon_intermediates,
+    Context, EccError, MetricDirect, MetricRadonIntermediate, RadonIntermediate, compute_radon_intermediates,
     make_circular_trajectory,
 )

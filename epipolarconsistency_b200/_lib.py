@@ -58,6 +58,15 @@ SIGNATURES = {
     "ecc_model_camera_similarity_2d3d": (None, [c_vp, c_vp, c_vp]),
     "ecc_evaluate_batch_params": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "ecc_model_expand": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "ecc_direct_set_images": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int]),
+    "ecc_direct_set_fan_beam": (C.c_int, [c_ctx, C.c_int]),
+    "ecc_direct_set_reference_clip": (C.c_int, [c_ctx, C.c_int]),
+    "ecc_direct_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),
+    "ecc_direct_evaluate_pair": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, C.POINTER(C.c_int),
+                                          C.POINTER(C.c_double)]),
+    "ecc_direct_pair_geometry": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(C.c_int),
+                                          C.POINTER(C.c_double)]),
+    "ecc_direct_line_integrals": (C.c_int, [c_ctx, C.c_int, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
     "ecc_pair_sample_counts": (C.c_int, [c_ctx, c_vp]),
     "ecc_partition_pairs": (C.c_int, [c_ctx, C.c_int, c_vp]),
     "ecc_team_create": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),

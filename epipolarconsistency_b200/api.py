@@ -288,6 +288,67 @@ class Context:
         out["weight"], out["value"] = w.value, v.value
         return out
 
+    # -- direct metric (include/ecc_b200.h "Direct metric"): no Radon intermediates
+    def direct_set_images(self, images, n_u=None, n_v=None):
+        """MetricDirect::setProjectionImages: images [n, n_v, n_u] float32, host or device."""
+        n = images.shape[0]
+        n_v = images.shape[1] if n_v is None else n_v
+        n_u = images.shape[2] if n_u is None else n_u
+        self._check(self.lib.ecc_direct_set_images(self.h, _ptr(images, _F32), int(n), int(n_u), int(n_v)))
+
+    def direct_set_fan_beam(self, fbcc=True):
+        self._check(self.lib.ecc_direct_set_fan_beam(self.h, int(bool(fbcc))))
+
+    def direct_set_reference_clip(self, on=True):
+        self._check(self.lib.ecc_direct_set_reference_clip(self.h, int(bool(on))))
+
+    def direct_evaluate(self, cost_image=None):
+        """MetricDirect::evaluate: the SUM over all pairs; cost_image [n, n] float32 gets entry [j, i] = pair (i < j)."""
+        total = C.c_double()
+        self._check(self.lib.ecc_direct_evaluate(self.h, _ptr(cost_image, _F32), C.byref(total)))
+        return total.value
+
+    def direct_evaluate_pair(self, i, j, kappas=None):
+        """computeForImagePair: dict(value, kappas, samples0, samples1); kappas given = the caller's plane angles."""
+        n, v = C.c_int(), C.c_double()
+        if kappas is not None:
+            k = np.ascontiguousarray(kappas, np.float32).copy()
+            m = k.shape[0]
+            s0, s1 = np.zeros(m, np.float32), np.zeros(m, np.float32)
+            self._check(self.lib.ecc_direct_evaluate_pair(self.h, int(i), int(j), m, m, _ptr(k, _F32), _ptr(s0, _F32), _ptr(s1, _F32),
+                                                          C.byref(n), C.byref(v)))
+            return dict(value=v.value, kappas=k, samples0=s0, samples1=s1)
+        self._check(self.lib.ecc_direct_evaluate_pair(self.h, int(i), int(j), 0, 0, None, None, None, C.byref(n), None))
+        m = n.value
+        k, s0, s1 = np.zeros(m, np.float32), np.zeros(m, np.float32), np.zeros(m, np.float32)
+        self._check(self.lib.ecc_direct_evaluate_pair(self.h, int(i), int(j), 0, m, _ptr(k, _F32), _ptr(s0, _F32), _ptr(s1, _F32),
+                                                      C.byref(n), C.byref(v)))
+        return dict(value=v.value, kappas=k, samples0=s0, samples1=s1)
+
+    def direct_pair_geometry(self, i, j):
+        """What computeForImagePair prepares for its kernel: dict(kappas, lines0, lines1, fbcc0, fbcc1, dkappa)."""
+        n, dk = C.c_int(), C.c_double()
+        self._check(self.lib.ecc_direct_pair_geometry(self.h, int(i), int(j), 0, None, None, None, None, None, C.byref(n), C.byref(dk)))
+        m = n.value
+        out = dict(kappas=np.zeros(m, np.float32), lines0=np.zeros((m, 3), np.float32), lines1=np.zeros((m, 3), np.float32),
+                   fbcc0=np.zeros((m, 8), np.float32), fbcc1=np.zeros((m, 8), np.float32))
+        self._check(self.lib.ecc_direct_pair_geometry(self.h, int(i), int(j), m, _ptr(out["kappas"], _F32), _ptr(out["lines0"], _F32),
+                                                      _ptr(out["lines1"], _F32), _ptr(out["fbcc0"], _F32), _ptr(out["fbcc1"], _F32),
+                                                      C.byref(n), C.byref(dk)))
+        out["dkappa"] = dk.value
+        return out
+
+    def direct_line_integrals(self, image, lines, fbcc=None):
+        """cuda_computeLineIntegrals: lines [m, >= 3] float32, fbcc [m, >= 6] float32 or None -> [m] float32 (host)."""
+        lines = np.ascontiguousarray(lines, np.float32)
+        m = lines.shape[0]
+        out = np.zeros(m, np.float32)
+        if fbcc is not None:
+            fbcc = np.ascontiguousarray(fbcc, np.float32)
+        self._check(self.lib.ecc_direct_line_integrals(self.h, int(image), _ptr(lines, _F32), m, lines.shape[1], _ptr(fbcc, _F32),
+                                                       0 if fbcc is None else fbcc.shape[1], _ptr(out, _F32)))
+        return out
+
     def pair_maps(self, idx4=None, n_views=None):
         """The reference's K01 records (16 floats per pair) as the pair kernels compute them; all pairs when idx4 is None."""
         n_pairs = n_views * (n_views - 1) // 2 if idx4 is None else idx4.shape[0]
@@ -675,3 +736,57 @@ class MetricRadonIntermediate:
         """New capability: score K projection-matrix sets in one launch (means per set)."""
         idx = None if indices is None else np.ascontiguousarray(indices, np.int32).reshape(-1, 4)
         return self.ctx.evaluate_batch(np.ascontiguousarray(Ps_sets, np.float64), idx, out)
+
+
+class MetricDirect:
+    """Mirror of EpipolarConsistency::MetricDirect (EpipolarConsistencyDirect.h:27-60, .cpp:214-270): epipolar consistency
+    straight from the projection images.  evaluate() returns the SUM over the pairs, as the reference's does."""
+
+    def __init__(self, Ps=None, Is=None, ctx=None):
+        self.ctx = ctx or Context()
+        self.Ps = np.zeros((0, 12))
+        self.n_images = 0
+        if Ps is not None:
+            self.setProjectionMatrices(Ps)
+        if Is is not None:
+            self.setProjectionImages(Is)
+
+    def setObjectRadius(self, radius_mm=0.0):
+        self.ctx.set_object_radius(radius_mm)
+        return self
+
+    def getObjectRadius(self):
+        return self.ctx.get_object_radius()
+
+    def setEpipolarPlaneStep(self, dkappa_rad=0.0):
+        self.ctx.set_epipolar_plane_step(dkappa_rad)
+        return self
+
+    def setProjectionMatrices(self, Ps):
+        self.Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12).copy()
+        self.ctx.set_projection_matrices(self.Ps)
+        return self
+
+    def getProjectionMatrices(self):
+        return self.Ps
+
+    def setProjectionImages(self, Is):
+        """Is: [n, n_v, n_u] float32 array / tensor (host or device)."""
+        self.ctx.direct_set_images(Is)
+        self.n_images = Is.shape[0]
+        return self
+
+    def getNumberOfProjetions(self):  # [sic]
+        return self.n_images
+
+    def setFanBeamConsistency(self, fbcc=True):
+        self.ctx.direct_set_fan_beam(fbcc)
+        return self
+
+    def evaluate(self, out=None):
+        return self.ctx.direct_evaluate(out)
+
+    def evaluateForImagePair(self, i, j, kappas=None):
+        """Returns (value, redundant_samples0, redundant_samples1, kappas)."""
+        r = self.ctx.direct_evaluate_pair(i, j, kappas)
+        return r["value"], r["samples0"], r["samples1"], r["kappas"]

@@ -227,6 +227,7 @@ void ecc_destroy(ecc_context* ctx)
     free_hybrid4(ctx);
     team_free(ctx);
     track_free(ctx);
+    free_direct(ctx);
     if (ctx->ramp_g_d) cudaFree(ctx->ramp_g_d);
     if (ctx->pre_work_d) cudaFree(ctx->pre_work_d);
     if (ctx->pre_small_d) cudaFree(ctx->pre_small_d);

@@ -125,6 +125,33 @@ struct BatchBuffers {
     size_t base_cap = 0;
 };
 
+// The direct metric (ecc_direct.cu): the projection images resident as textures, geometry records and scratch.
+struct DirectState {
+    int n_u = 0, n_v = 0, n_images = 0;
+    int fbcc = 0;            // MetricDirect::setFanBeamConsistency
+    int reference_clip = 0;  // clip lines against n_u x n_u as the reference's launcher does (EpipolarConsistencyDirect.cu:135)
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> tex_h;
+    cudaTextureObject_t* tex_d = nullptr;
+    void* views_d = nullptr;   // DirectView per view
+    size_t views_bytes = 0;
+    double* Ps_d = nullptr;
+    size_t Ps_bytes = 0;
+    void* pairs_d = nullptr;   // DirectPair per pair
+    size_t pairs_bytes = 0;
+    int* ij_d = nullptr;
+    size_t ij_bytes = 0;
+    int* offsets_d = nullptr;  // [n_pairs + 1] first CTA of every pair, then [n_pairs] CTAs per pair
+    size_t offsets_bytes = 0;
+    double* vals_d = nullptr;  // [n_pairs] pair values, then the total
+    size_t vals_bytes = 0;
+    double* partials_d = nullptr;
+    size_t partials_bytes = 0;
+    float* scratch_d = nullptr;
+    size_t scratch_bytes = 0;
+    std::vector<int> all_pairs_h;
+};
+
 }  // namespace eccb200
 
 struct ecc_context {
@@ -201,6 +228,7 @@ struct ecc_context {
     eccb200::Team team;
     eccb200::TrackGraph track;
     eccb200::BatchBuffers batch;
+    eccb200::DirectState direct;
 
     // ---- profiling ----
     bool profiling = false;
@@ -335,6 +363,9 @@ int radon_compute_impl(ecc_context* ctx, const float* images, int n_images, int 
 // ---- launchers (ecc_preprocess.cu) ----
 int preprocess_batch(ecc_context* ctx, float* images_d, int n, int n_u, int n_v, const ecc_preprocess_params* pp, const double* Ps_h);
 void camera_intrinsics_host(const double* P, double* fu, double* u0, double* v0);
+
+// ---- direct metric (ecc_direct.cu) ----
+void free_direct(ecc_context* ctx);
 
 // ---- launchers (ecc_synth.cu) ----
 int synth_projections(ecc_context* ctx, const double* Ps_h, int n, int n_u, int n_v,

@@ -279,6 +279,46 @@ int ecc_pair_sample_counts(ecc_context* ctx, int* counts);
  * bounds: n_parts+1 entries, bounds[0]=0, bounds[n_parts]=n(n-1)/2. */
 int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds);
 
+/* ---- Direct metric: epipolar consistency straight from the projection images (no Radon intermediates) -----------------
+ * EpipolarConsistency::MetricDirect and computeForImagePair (LibEpipolarConsistency/EpipolarConsistencyDirect.h:17-60,
+ * .cpp:64-270; kernel_computeLineIntegrals / cuda_computeLineIntegrals, EpipolarConsistencyDirect.cu:31-142; the fan-beam
+ * variant's weighting, RectifiedFBCC.h).  The reference derives the epipolar lines of ONE pair on the host, uploads them and
+ * launches one thread per line, once per image; here all pairs of the data set are one launch (geometry in fp64 on the
+ * device, one CTA per 32 epipolar planes of a pair, fixed-order sums).  Uses the context's projection matrices
+ * (ecc_set_projection_matrices), object radius (0: estimated from the FIRST matrix, Metric::getObjectRadius) and epipolar
+ * plane step (0: per pair, half the kappa range over the image diagonal, EpipolarConsistencyDirect.cpp:91-96). */
+
+/* MetricDirect::setProjectionImages: n pre-processed projections [h|d] of n_v rows x n_u floats, copied into CUDA arrays
+ * behind pixel-coordinate, linear-filter, clamp textures (BindlessTexture2D<float>'s defaults). */
+int ecc_direct_set_images(ecc_context* ctx, const float* images, int n, int n_u, int n_v);
+/* MetricDirect::setFanBeamConsistency: the rectified fan-beam consistency (weighted integrals) instead of the derivative. */
+int ecc_direct_set_fan_beam(ecc_context* ctx, int fbcc);
+/* The reference's launcher hands the kernel n_u for BOTH image sizes (EpipolarConsistencyDirect.cu:135), i.e. it clips
+ * every line against an n_u x n_u box.  Off (default): lines are clipped against the image.  On: as the reference. */
+int ecc_direct_set_reference_clip(ecc_context* ctx, int on);
+/* MetricDirect::evaluate (EpipolarConsistencyDirect.cpp:236-247): all pairs i < j.  cost_image [h|d], nullable: n*n floats,
+ * entry i + j*n receives the pair's value, other entries keep the caller's.  sum: the SUM over the pairs (the direct
+ * metric returns the sum, not the mean). */
+int ecc_direct_evaluate(ecc_context* ctx, float* cost_image, double* sum);
+/* MetricDirect::evaluateForImagePair / computeForImagePair (.cpp:64-212, 249-258): one pair and its redundant signals.
+ * kappas / samples0 / samples1: host arrays of `capacity` floats, each nullable.  n_given > 0: the first n_given entries of
+ * kappas are the caller's epipolar plane angles (the reference's "unless provided"), else they receive the angles used.
+ * n_lines: how many planes the pair has (also when capacity is smaller).  value = sum_q (s0[q] - s1[q])^2 * dkappa. */
+int ecc_direct_evaluate_pair(ecc_context* ctx, int i, int j, int n_given, int capacity, float* kappas, float* samples0,
+                             float* samples1, int* n_lines, double* value);
+/* The host-side geometry of one pair as the reference's computeForImagePair prepares it for its kernel, from the same
+ * code the device kernel runs: kappas (capacity floats), the corresponding epipolar lines of both views in Hessian normal
+ * form (3 floats per plane) and the FBCC_weighting_info records (RectifiedFBCC.h:82-87: 8 floats per plane and view). Every
+ * array is host memory and nullable.  No GPU needed beyond the context. */
+int ecc_direct_pair_geometry(ecc_context* ctx, int i, int j, int capacity, float* kappas, float* lines0, float* lines1,
+                             float* fbcc0, float* fbcc1, int* n_lines, double* dkappa);
+/* The launcher-level seam, cuda_computeLineIntegrals (EpipolarConsistencyDirect.cu:122-142): integrals of image `image`
+ * (index into the set images) along n_lines given lines.  lines [h|d]: line_stride floats per line, the first three =
+ * (l0, l1, l2) in Hessian normal form; fbcc [h|d], nullable: fbcc_stride floats per line, the first six = the
+ * FBCC_weighting_info record; out [h|d]: n_lines floats. */
+int ecc_direct_line_integrals(ecc_context* ctx, int image, const float* lines, int n_lines, int line_stride,
+                              const float* fbcc, int fbcc_stride, float* out);
+
 /* ---- Multi-GPU team: the GPUs of one node on one data set, one process (or thread) and one context per GPU ----------
  * The reference is single-GPU.  A team shards the path with NO collective on the data path: every
  * rank owns one device block [flags | pair values | the Radon intermediates of all n_total projections] that is mapped

@@ -618,3 +618,368 @@ void oracle_project_ellipsoids(const double* P, int n_u, int n_v, const double* 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Direct metric (no Radon intermediates).  Restates LibEpipolarConsistency/EpipolarConsistencyDirect.cpp
+// (host geometry, Eigen there, plain arrays here), EpipolarConsistencyDirect.cu:31-119 (the line kernel) and
+// RectifiedFBCC.h (fan-beam weighting).  PARITY UNPINNED for the host geometry: the reference takes the
+// pseudo-inverse and the camera centre from Eigen's JacobiSVD and Eigen is not available here; both are
+// restated by closed forms that give the same quantities to fp64 rounding.  The line kernel IS pinned: the
+// reference's own EpipolarConsistencyDirect.cu is compiled into oracle/_ref/libecc_ref_cuda.so and the GPU
+// tests feed it the same lines.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct DView {
+    double pinvT[12];  // (P^+)^T, 3x4 col-major
+    double C[4];
+    const double* P;
+};
+
+// ProjectionMatrix.cpp:21-24 (pseudoInverse) and :70-76 (getCameraCenter).
+void dview(const double* P, DView& V)
+{
+    V.P = P;
+    double G[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int k = 0; k < 4; k++) s += P[r + 3 * k] * P[c + 3 * k];
+            G[r + 3 * c] = s;
+        }
+    const double det = det3(G[0], G[3], G[6], G[1], G[4], G[7], G[2], G[5], G[8]);
+    double Gi[9];
+    Gi[0] = (G[4] * G[8] - G[7] * G[5]) / det;
+    Gi[3] = -(G[3] * G[8] - G[6] * G[5]) / det;
+    Gi[6] = (G[3] * G[7] - G[6] * G[4]) / det;
+    Gi[1] = -(G[1] * G[8] - G[7] * G[2]) / det;
+    Gi[4] = (G[0] * G[8] - G[6] * G[2]) / det;
+    Gi[7] = -(G[0] * G[7] - G[6] * G[1]) / det;
+    Gi[2] = (G[1] * G[5] - G[4] * G[2]) / det;
+    Gi[5] = -(G[0] * G[5] - G[3] * G[2]) / det;
+    Gi[8] = (G[0] * G[4] - G[3] * G[1]) / det;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += Gi[r + 3 * k] * P[k + 3 * c];
+            V.pinvT[r + 3 * c] = s;
+        }
+    double m[4], nrm = 0;
+    for (int k = 0; k < 4; k++) {
+        int c[3], q = 0;
+        for (int j = 0; j < 4; j++)
+            if (j != k) c[q++] = j;
+        m[k] = det3(P[0 + 3 * c[0]], P[0 + 3 * c[1]], P[0 + 3 * c[2]], P[1 + 3 * c[0]], P[1 + 3 * c[1]], P[1 + 3 * c[2]],
+                    P[2 + 3 * c[0]], P[2 + 3 * c[1]], P[2 + 3 * c[2]]);
+        if (k & 1) m[k] = -m[k];
+        nrm += m[k] * m[k];
+    }
+    nrm = sqrt(nrm);
+    for (int k = 0; k < 4; k++) V.C[k] = m[k] / nrm;
+    if (V.C[3] < -1e-12 || V.C[3] > 1e-12) {
+        const double w = V.C[3];
+        for (int k = 0; k < 4; k++) V.C[k] /= w;
+    }
+}
+
+// ProjectiveGeometry.hxx:188-237.
+void pl_join_points(const double* A, const double* B, double* L)
+{
+    L[0] = A[0] * B[1] - A[1] * B[0]; L[1] = A[0] * B[2] - A[2] * B[0]; L[2] = A[0] * B[3] - A[3] * B[0];
+    L[3] = A[1] * B[2] - A[2] * B[1]; L[4] = A[1] * B[3] - A[3] * B[1]; L[5] = A[2] * B[3] - A[3] * B[2];
+}
+void pl_meet_planes(const double* A, const double* B, double* L)
+{
+    L[0] = A[2] * B[3] - A[3] * B[2]; L[1] = A[3] * B[1] - A[1] * B[3]; L[2] = A[1] * B[2] - A[2] * B[1];
+    L[3] = A[0] * B[3] - A[3] * B[0]; L[4] = A[2] * B[0] - A[0] * B[2]; L[5] = A[0] * B[1] - A[1] * B[0];
+}
+void pl_join_line_point(const double* L, const double* X, double* E)
+{
+    E[0] = X[1] * L[5] - X[2] * L[4] + X[3] * L[3];
+    E[1] = -X[0] * L[5] + X[2] * L[2] - X[3] * L[1];
+    E[2] = X[0] * L[4] - X[1] * L[2] + X[3] * L[0];
+    E[3] = -X[0] * L[3] + X[1] * L[1] - X[2] * L[0];
+}
+void pl_meet_line_plane(const double* L, const double* P, double* X)
+{
+    X[0] = -P[1] * L[0] - P[2] * L[1] - P[3] * L[2];
+    X[1] = P[0] * L[0] - P[2] * L[3] - P[3] * L[4];
+    X[2] = P[0] * L[1] + P[1] * L[3] - P[3] * L[5];
+    X[3] = P[0] * L[2] + P[1] * L[4] + P[2] * L[5];
+}
+
+struct DPair {
+    double E0[4], E90[4], lo, hi, dkappa, dir[3], E[4], H0[9], H1[9];
+    int n_lines;
+};
+
+// EpipolarConsistencyDirect.cpp:26-40 (pencil), :84-105 + EpipolarConsistency.cpp:49-60 (range, step, count), :128-145
+// (virtual detector and rectifying homographies).
+void dpair(const DView& V0, const DView& V1, double radius, double dkappa, int n_u, int n_v, DPair& R)
+{
+    double B[6];
+    pl_join_points(V0.C, V1.C, B);
+    const double origin[4] = {0, 0, 0, 1};
+    pl_join_line_point(B, origin, R.E0);
+    pl_join_line_point(B, R.E0, R.E90);
+    const double n0 = norm3(R.E0), n90 = norm3(R.E90);
+    for (int k = 0; k < 4; k++) { R.E0[k] /= n0; R.E90[k] /= n90; }
+    const double d[3] = {-B[2], -B[4], -B[5]}, m[3] = {B[3], -B[1], B[0]};  // ProjectiveGeometry.hxx:242-251
+    const double dist = norm3(m) / norm3(d);
+    if (dist <= radius) { R.lo = -0.5 * kPiD; R.hi = 0.5 * kPiD; }
+    else { const double kmax = fabs(asin(radius / dist)); R.lo = -kmax; R.hi = kmax; }
+    if (dkappa <= 0) dkappa = 0.5 * (R.hi - R.lo) / sqrt((double)(n_u * n_u + n_v * n_v));
+    R.dkappa = dkappa;
+    R.n_lines = (int)((R.hi - R.lo) / dkappa);
+    for (int k = 0; k < 3; k++) R.dir[k] = d[k];
+    double U[3], W[3];
+    const double nd = norm3(d), nm = norm3(m);
+    for (int k = 0; k < 3; k++) { U[k] = d[k] / nd; W[k] = m[k] / nm; }
+    cross3(U, W, R.E);
+    R.E[3] = 0;
+    for (int view = 0; view < 2; view++) {
+        const DView& V = view ? V1 : V0;
+        const double* C = V.C;
+        const double* E = R.E;
+        double T[4][4] = {  // ProjectiveGeometry.hxx:333-343, T[row][col]
+            {C[1] * E[1] + C[2] * E[2] + C[3] * E[3], -C[0] * E[1], -C[0] * E[2], -C[0] * E[3]},
+            {-C[1] * E[0], C[0] * E[0] + C[2] * E[2] + C[3] * E[3], -C[1] * E[2], -C[1] * E[3]},
+            {-C[2] * E[0], -C[2] * E[1], C[0] * E[0] + C[3] * E[3] + C[1] * E[1], -C[2] * E[3]},
+            {-C[3] * E[0], -C[3] * E[1], -C[3] * E[2], C[0] * E[0] + C[1] * E[1] + C[2] * E[2]}};
+        const double PE[3][4] = {{U[0], U[1], U[2], 0}, {W[0], W[1], W[2], 0}, {0, 0, 0, 1.0}};
+        double PT[3][4];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) {
+                double s = 0;
+                for (int k = 0; k < 4; k++) s += PE[r][k] * T[k][c];
+                PT[r][c] = s;
+            }
+        double* H = view ? R.H1 : R.H0;  // H(r,c) at H[r + 3c]; P^+(k,c) = pinvT(c,k)
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                double s = 0;
+                for (int k = 0; k < 4; k++) s += PT[r][k] * V.pinvT[c + 3 * k];
+                H[r + 3 * c] = s;
+            }
+    }
+}
+
+// EpipolarConsistencyDirect.cpp:47-59.
+void dlines(const DView& V0, const DView& V1, const DPair& R, double kappa, float* l0, float* l1)
+{
+    double Ek[4];
+    for (int k = 0; k < 4; k++) Ek[k] = cos(kappa) * R.E0[k] + sin(kappa) * R.E90[k];
+    for (int view = 0; view < 2; view++) {
+        const double* A = view ? V1.pinvT : V0.pinvT;
+        double l[3];
+        for (int r = 0; r < 3; r++) {
+            l[r] = 0;
+            for (int c = 0; c < 4; c++) l[r] += A[r + 3 * c] * Ek[c];
+        }
+        const double n = sqrt(l[0] * l[0] + l[1] * l[1]);
+        for (int r = 0; r < 3; r++) (view ? l1 : l0)[r] = (float)(l[r] / n);
+    }
+}
+
+// RectifiedFBCC.h:66-69 in fp32 as the host evaluates it.
+float phi_transform(const float* f, float t) { return (f[0] * t + f[1]) / (f[2] * t + f[3]); }
+
+// EpipolarConsistencyDirect.cpp:147-186 + RectifiedFBCC.h:41-50: 8 floats per view (a, b, c, d, t_prime_ak, d_l_kappa_C_sq, 0, 0).
+void dfbcc(const DView& V0, const DView& V1, const DPair& R, const float* l0f, const float* l1f, float* f0, float* f1)
+{
+    const double l0[3] = {l0f[0], l0f[1], l0f[2]}, l1[3] = {l1f[0], l1f[1], l1f[2]};
+    double Ek[4];
+    for (int c = 0; c < 4; c++) Ek[c] = V0.P[3 * c] * l0[0] + V0.P[1 + 3 * c] * l0[1] + V0.P[2 + 3 * c] * l0[2];
+    for (int view = 0; view < 2; view++) {
+        const DView& V = view ? V1 : V0;
+        const double* l = view ? l1 : l0;
+        const double* H = view ? R.H1 : R.H0;
+        float* f = view ? f1 : f0;
+        const double EB[4] = {R.dir[0], R.dir[1], R.dir[2], -dot3(R.dir, V.C)};
+        double L[6], Ak[4];
+        pl_meet_planes(EB, Ek, L);
+        pl_meet_line_plane(L, R.E, Ak);
+        if (Ak[3] > 1e-12 || Ak[3] < -1e-12) { const double w = Ak[3]; for (int k = 0; k < 4; k++) Ak[k] /= w; }
+        else { Ak[3] = 0; const double n = norm3(Ak); for (int k = 0; k < 4; k++) Ak[k] /= n; }
+        double dd = 0;
+        for (int k = 0; k < 4; k++) dd += (Ak[k] - V.C[k]) * (Ak[k] - V.C[k]);
+        const float d_px = (float)sqrt(dd);
+        double ak[3];
+        for (int r = 0; r < 3; r++) ak[r] = V.P[r] * Ak[0] + V.P[r + 3] * Ak[1] + V.P[r + 6] * Ak[2] + V.P[r + 9] * Ak[3];
+        if (ak[2] > 1e-11 || ak[2] < -1e-11) { const double w = ak[2]; for (int k = 0; k < 3; k++) ak[k] /= w; }
+        else { ak[2] = 0; const double n = sqrt(ak[0] * ak[0] + ak[1] * ak[1]); for (int k = 0; k < 3; k++) ak[k] /= n; }
+        f[0] = (float)(H[0] * l[1] - H[1] * l[0]);
+        f[1] = (float)(H[6] - H[0] * l[0] * l[2]);
+        f[2] = (float)(H[2] * l[1] - H[5] * l[0]);
+        f[3] = (float)(H[8] - H[2] * l[0] * l[2] - H[5] * l[1] * l[2]);
+        if (f[0] * f[3] - f[1] * f[2] < 0) { f[0] *= -1; f[1] *= -1; }
+        f[4] = phi_transform(f, (float)(l[1] * ak[0] / ak[2] - l[0] * ak[1] / ak[2]));
+        f[5] = d_px * d_px;
+        f[6] = f[7] = 0;
+    }
+}
+
+// One line integral.  EpipolarConsistencyDirect.cu:44-118; fmaf() where the reference's sm_100 build fuses.  shape 1: the
+// loop as that build executes it (blocks of four samples under one test, then two, then one), shape 0: the source loop.
+float dline_integral(const float* img, int n_ui, int n_vi, int n_v_clip, const float* l, const float* fbcc, int interp, int shape)
+{
+    float o0 = -l[2] * l[0], o1 = -l[2] * l[1];
+    const float d0 = l[1], d1 = -l[0];
+    float ts[4] = {(1.0f - o0) / d0, ((float)(n_ui - 1) - o0) / d0, (1.0f - o1) / d1, ((float)(n_v_clip - 1) - o1) / d1};
+    if ((double)(d0 * d0) < 1e-12) { ts[1] = 1e10f; ts[0] = -1e10f; }
+    if ((double)(d1 * d1) < 1e-12) { ts[3] = 1e10f; ts[2] = -1e10f; }
+    sort_four(ts);
+    const float t_min = ts[1], t_max = ts[2];
+    const float pu = fmaf(t_min, d0, o0), pv = fmaf(t_min, d1, o1);
+    if (!(pu <= (float)n_ui && pv <= (float)n_v_clip && pu >= 0 && pv >= 0)) return 0.0f;
+    const float step = 0.4f;
+    o0 += 0.5f;
+    o1 += 0.5f;
+    if (fbcc) {
+        const float a = fbcc[0], b = fbcc[1], c = fbcc[2], d = fbcc[3], t_ak = fbcc[4], dsq = fbcc[5];
+        const float det = fmaf(a, d, -(b * c)), cc = c * c, dd = d * d, cd2 = d * (c + c);
+        float sum = 0;
+        for (float t = t_min; t <= t_max; t += step) {
+            const float u_prime = fmaf(a, t, b) / fmaf(c, t, d) - t_ak;
+            const float den = dd + fmaf(cd2, t, (cc * t) * t);
+            const float w = (det / den) / sqrtf(fmaf(u_prime, u_prime, dsq));
+            sum = fmaf(bilinear(img, n_ui, n_vi, fmaf(d0, t, o0), fmaf(d1, t, o1), interp) * step, w, sum);
+        }
+        return sum;
+    }
+    float sump = 0, summ = 0;
+    auto sample = [&](float t) {
+        const float u = fmaf(d0, t, o0), v = fmaf(d1, t, o1);
+        sump = fmaf(bilinear(img, n_ui, n_vi, fmaf(l[0], 0.5f, u), fmaf(l[1], 0.5f, v), interp), step, sump);
+        summ = fmaf(bilinear(img, n_ui, n_vi, fmaf(l[0], -0.5f, u), fmaf(l[1], -0.5f, v), interp), step, summ);
+    };
+    float t = t_min;
+    if (!shape) {
+        for (; t <= t_max; t += step) sample(t);
+        return sump - summ;
+    }
+    if (t > t_max) return 0.0f;
+    bool none_yet = true;
+    if (!(t + 1.2f > t_max)) {
+        const float r3 = t_max - 1.2f;
+        do {
+            const float t1 = t + step, t2 = t1 + step, t3 = t2 + step;
+            sample(t); sample(t1); sample(t2); sample(t3);
+            t = t3 + step;
+        } while (!(t > r3));
+        none_yet = false;
+    }
+    const float t1 = t + step;
+    if (!(t1 > t_max)) { sample(t); sample(t1); t = t1 + step; none_yet = false; }
+    if (t <= t_max || none_yet) sample(t);
+    return sump - summ;
+}
+
+}  // namespace
+
+extern "C" {
+
+// The weight one sample of a fan-beam line integral carries (EpipolarConsistencyDirect.cu:86-93, RectifiedFBCC.h:66-79), with
+// the roundings of dline_integral.  rec: a, b, c, d, t_prime_ak, d_l_kappa_C_sq.
+float oracle_direct_fbcc_weight(const float* rec, float t)
+{
+    const float a = rec[0], b = rec[1], c = rec[2], d = rec[3];
+    const float det = fmaf(a, d, -(b * c)), cc = c * c, dd = d * d, cd2 = d * (c + c);
+    const float u_prime = fmaf(a, t, b) / fmaf(c, t, d) - rec[4];
+    const float den = dd + fmaf(cd2, t, (cc * t) * t);
+    return (det / den) / sqrtf(fmaf(u_prime, u_prime, rec[5]));
+}
+
+// cuda_computeLineIntegrals, EpipolarConsistencyDirect.cu:122-142 (n_v_clip: the height the clipping uses; the reference
+// passes n_u).  lines: stride floats per line; fbcc nullable: fbcc_stride floats per line.
+void oracle_direct_line_integrals(const float* img, int n_u, int n_v, int n_v_clip, const float* lines, int n_lines, int stride,
+                                  const float* fbcc, int fbcc_stride, int interp, int shape, float* out)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int k = 0; k < n_lines; k++)
+        out[k] = dline_integral(img, n_u, n_v, n_v_clip, lines + (size_t)k * stride, fbcc ? fbcc + (size_t)k * fbcc_stride : nullptr, interp, shape);
+}
+
+// Geometry of one pair (computeForImagePair up to its kernel launches, EpipolarConsistencyDirect.cpp:64-186).  All output
+// arrays nullable, `capacity` planes each: kappas, lines (3 floats), fbcc records (8 floats).  Returns the number of planes.
+int oracle_direct_pair_geometry(const double* P0, const double* P1, double radius, double dkappa, int n_u, int n_v, int capacity,
+                                float* kappas, float* lines0, float* lines1, float* fbcc0, float* fbcc1, double* dkappa_out)
+{
+    DView V0, V1;
+    dview(P0, V0);
+    dview(P1, V1);
+    if (radius <= 0) radius = std::max(oracle_object_radius(P0, n_u, n_v), oracle_object_radius(P1, n_u, n_v));  // :80-82
+    DPair R;
+    dpair(V0, V1, radius, dkappa, n_u, n_v, R);
+    if (dkappa_out) *dkappa_out = R.dkappa;
+    for (int q = 0; q < R.n_lines && q < capacity; q++) {
+        const float kf = (float)(R.lo + R.dkappa * q);  // :104
+        float l0[3], l1[3], f0[8], f1[8];
+        dlines(V0, V1, R, (double)kf, l0, l1);
+        if (kappas) kappas[q] = kf;
+        if (lines0) memcpy(lines0 + 3 * (size_t)q, l0, sizeof(l0));
+        if (lines1) memcpy(lines1 + 3 * (size_t)q, l1, sizeof(l1));
+        if (fbcc0 || fbcc1) {
+            dfbcc(V0, V1, R, l0, l1, f0, f1);
+            if (fbcc0) memcpy(fbcc0 + 8 * (size_t)q, f0, sizeof(f0));
+            if (fbcc1) memcpy(fbcc1 + 8 * (size_t)q, f1, sizeof(f1));
+        }
+    }
+    return R.n_lines;
+}
+
+// computeForImagePair, EpipolarConsistencyDirect.cpp:64-212: the pair's metric and (nullable, `capacity` entries) its
+// redundant signals.  n_given > 0: the first n_given kappas are the caller's.  reference_clip: clip against n_u x n_u.
+double oracle_direct_pair(const double* P0, const double* P1, const float* img0, const float* img1, int n_u, int n_v, double radius,
+                          double dkappa, int fbcc, int interp, int shape, int reference_clip, int n_given, int capacity, float* kappas,
+                          float* s0, float* s1, int* n_lines_out)
+{
+    DView V0, V1;
+    dview(P0, V0);
+    dview(P1, V1);
+    if (radius <= 0) radius = std::max(oracle_object_radius(P0, n_u, n_v), oracle_object_radius(P1, n_u, n_v));
+    DPair R;
+    dpair(V0, V1, radius, dkappa, n_u, n_v, R);
+    const int n_lines = n_given > 0 ? n_given : R.n_lines;
+    if (n_lines_out) *n_lines_out = n_lines;
+    const int clip = reference_clip ? n_u : n_v;
+    std::vector<double> terms(n_lines > 0 ? n_lines : 0);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int q = 0; q < n_lines; q++) {
+        const float kf = n_given > 0 ? kappas[q] : (float)(R.lo + R.dkappa * q);
+        float l0[3], l1[3], f0[8], f1[8];
+        dlines(V0, V1, R, (double)kf, l0, l1);
+        if (fbcc) dfbcc(V0, V1, R, l0, l1, f0, f1);
+        const float v0 = dline_integral(img0, n_u, n_v, clip, l0, fbcc ? f0 : nullptr, interp, shape);
+        const float v1 = dline_integral(img1, n_u, n_v, clip, l1, fbcc ? f1 : nullptr, interp, shape);
+        terms[q] = (double)((v0 - v1) * (v0 - v1)) * R.dkappa;  // :207-210
+        if (q < capacity) {
+            if (kappas && n_given == 0) kappas[q] = kf;
+            if (s0) s0[q] = v0;
+            if (s1) s1[q] = v1;
+        }
+    }
+    double metric = 0;
+    for (int q = 0; q < n_lines; q++) metric += terms[q];
+    return metric;
+}
+
+// MetricDirect::evaluate, EpipolarConsistencyDirect.cpp:236-247: all pairs i < j, cost image entry i + j n (nullable), returns
+// the SUM.  radius <= 0: Metric::getObjectRadius, i.e. estimated from the first matrix (EpipolarConsistency.cpp:76-84).
+double oracle_direct_evaluate(const double* Ps, int n, const float* images, int n_u, int n_v, double radius, double dkappa, int fbcc,
+                              int interp, int shape, int reference_clip, float* cost_image)
+{
+    if (radius <= 0 && n > 0) radius = oracle_object_radius(Ps, n_u, n_v);
+    const size_t px = (size_t)n_u * n_v;
+    double cost = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            const double ecc = oracle_direct_pair(Ps + 12 * (size_t)i, Ps + 12 * (size_t)j, images + px * i, images + px * j, n_u, n_v, radius,
+                                                  dkappa, fbcc, interp, shape, reference_clip, 0, 0, nullptr, nullptr, nullptr, nullptr);
+            cost += ecc;
+            if (cost_image) cost_image[i + (size_t)j * n] = (float)ecc;
+        }
+    return cost;
+}
+
+}  // extern "C"

@@ -95,6 +95,22 @@ void oracle_circular_trajectory(int n_proj, double sid, double sdd, int n_u, int
 void oracle_project_ellipsoids(const double* P, int n_u, int n_v, const double* ellipsoids,
                                int n_ell, int cos_weight, int zero_border, float* img);
 
+/* --- direct metric (no Radon intermediates) ------------------------------------------------
+ * Restates LibEpipolarConsistency/EpipolarConsistencyDirect.cpp:22-270, EpipolarConsistencyDirect.cu:31-142 and
+ * RectifiedFBCC.h.  PARITY UNPINNED for the fp64 host geometry (the reference uses Eigen's JacobiSVD, which is not
+ * available here); the line kernel is pinned by the reference's own .cu in oracle/_ref/libecc_ref_cuda.so.
+ * shape: 0 = the source loop, 1 = the loop as the reference's sm_100 build executes it (blocks of 4 / 2 / 1 samples). */
+void oracle_direct_line_integrals(const float* img, int n_u, int n_v, int n_v_clip, const float* lines, int n_lines, int stride,
+                                  const float* fbcc, int fbcc_stride, int interp, int shape, float* out);
+float oracle_direct_fbcc_weight(const float* rec, float t);
+int oracle_direct_pair_geometry(const double* P0, const double* P1, double radius, double dkappa, int n_u, int n_v, int capacity,
+                                float* kappas, float* lines0, float* lines1, float* fbcc0, float* fbcc1, double* dkappa_out);
+double oracle_direct_pair(const double* P0, const double* P1, const float* img0, const float* img1, int n_u, int n_v, double radius,
+                          double dkappa, int fbcc, int interp, int shape, int reference_clip, int n_given, int capacity, float* kappas,
+                          float* s0, float* s1, int* n_lines_out);
+double oracle_direct_evaluate(const double* Ps, int n, const float* images, int n_u, int n_v, double radius, double dkappa, int fbcc,
+                              int interp, int shape, int reference_clip, float* cost_image);
+
 int oracle_max_threads(void);
 int oracle_set_threads(int n);  /* OpenMP threads for the oracle's loops; returns the resulting maximum */
 

@@ -1,5 +1,5 @@
 // ref_cuda_harness.cu -- drives the REFERENCE's own CUDA launchers (compiled unchanged from
-// /root/reference/code/LibEpipolarConsistency/{RadonIntermediate,EpipolarConsistencyRadonIntermediate}.cu
+// /root/reference/code/LibEpipolarConsistency/{RadonIntermediate,EpipolarConsistencyRadonIntermediate,EpipolarConsistencyDirect}.cu
 // by oracle/Makefile) so that tests and bench.py can run "the reference CUDA path" on the GPU box.
 // Ours: this harness only.  It re-creates, without Eigen/GetSet, the ~100 lines of host logic that sit
 // between the reference's class API and its two launchers:
@@ -26,6 +26,10 @@ void epipolarConsistency(int n_x, int n_y, int num_dtrs, char* dtrs_d, int n_alp
                          float step_t, int num_Ps, float* Cs_d, float* PinvTs_d, int num_pairs, int* indices_d,
                          float* K01s_d, float* out_d, float object_radius_mm, float dkappa, bool isDerivative,
                          bool use_corr, float* out_corr_d);
+
+// EpipolarConsistencyDirect.cu:122-142 (C++ linkage, defined in the reference's .cu)
+void cuda_computeLineIntegrals(short n_lines, float* lines_d, short line_stride, float* fbcc_d, short fbcc_stride, cudaTextureObject_t I,
+                               short n_u, short n_v, float* integrals_out_d);
 
 namespace {
 
@@ -130,6 +134,45 @@ int ref_cuda_radon_any(const void* images, int n_images, int n_u, int n_v, int n
                        void* dtrs, float* ms)
 {
     return ref_cuda_radon((const float*)images, n_images, n_u, n_v, n_alpha, n_t, filter, post, (float*)dtrs, ms);
+}
+
+// The direct metric's line kernel (the reference's kernel_computeLineIntegrals through its own launcher) on one image.
+// All pointers host or device (cudaMemcpyDefault); n_lines < 32768 (the launcher's `short`).  fbcc nullable.  ms (nullable):
+// GPU time of the launcher call.
+int ref_cuda_direct_line_integrals(const float* image, int n_u, int n_v, const float* lines, int n_lines, int line_stride,
+                                   const float* fbcc, int fbcc_stride, float* out, float* ms)
+{
+    if (n_lines <= 0 || n_lines > 32767) return -2;
+    const size_t img = (size_t)n_u * n_v;
+    float *img_d = nullptr, *lines_d = nullptr, *fbcc_d = nullptr, *out_d = nullptr;
+    CK(cudaMalloc(&img_d, sizeof(float) * img));
+    CK(cudaMemcpy(img_d, image, sizeof(float) * img, cudaMemcpyDefault));
+    ArrayTex t;
+    if (make_array_texture(img_d, n_u, n_v, false, t)) return -1;  // BindlessTexture2D<float>(w, h, buffer): pixel coordinates
+    CK(cudaMalloc(&lines_d, sizeof(float) * n_lines * line_stride));
+    CK(cudaMemcpy(lines_d, lines, sizeof(float) * n_lines * line_stride, cudaMemcpyDefault));
+    if (fbcc) {
+        CK(cudaMalloc(&fbcc_d, sizeof(float) * n_lines * fbcc_stride));
+        CK(cudaMemcpy(fbcc_d, fbcc, sizeof(float) * n_lines * fbcc_stride, cudaMemcpyDefault));
+    }
+    CK(cudaMalloc(&out_d, sizeof(float) * n_lines));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    cuda_computeLineIntegrals((short)n_lines, lines_d, (short)line_stride, fbcc_d, (short)fbcc_stride, t.tex, (short)n_u, (short)n_v, out_d);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    if (ms) CK(cudaEventElapsedTime(ms, e0, e1));
+    CK(cudaMemcpy(out, out_d, sizeof(float) * n_lines, cudaMemcpyDefault));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    free_array_texture(t);
+    cudaFree(img_d);
+    cudaFree(lines_d);
+    if (fbcc_d) cudaFree(fbcc_d);
+    cudaFree(out_d);
+    return 0;
 }
 
 // Metric object: dtrs become array textures exactly like RadonIntermediate::getTexture() (normalised).

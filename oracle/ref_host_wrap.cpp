@@ -120,3 +120,24 @@ void ref_border(float* data, int w, int h, const int* zero, const int* feather)
 }
 
 }  // extern "C"
+
+// ---- fan-beam weighting of the direct metric: the reference's own LinePerspectivity (RectifiedFBCC.h, the parts that do not
+// need Eigen) and the per-sample weight exactly as kernel_computeLineIntegrals forms it (EpipolarConsistencyDirect.cu:86-93).
+#include <LibEpipolarConsistency/RectifiedFBCC.h>
+
+extern "C" {
+
+float ref_fbcc_transform(const float* abcd, float t) { return LinePerspectivity((float*)abcd).transform(t); }
+float ref_fbcc_inverse(const float* abcd, float t) { return LinePerspectivity((float*)abcd).inverse(t); }
+float ref_fbcc_derivative(const float* abcd, float t) { return LinePerspectivity((float*)abcd).derivative(t); }
+float ref_fbcc_weight(const float* rec8, float t)
+{
+    FBCC_weighting_info fbcc = *((FBCC_weighting_info*)rec8);
+    float u_prime = fbcc.phi.transform(t) - fbcc.t_prime_ak;
+    float fbcc_weight = fbcc.phi.derivative(t) / sqrtf(u_prime * u_prime + fbcc.d_l_kappa_C_sq);
+    return fbcc_weight;
+}
+int ref_fbcc_record_floats() { return (int)(sizeof(FBCC_weighting_info) / sizeof(float)); }
+
+}  // extern "C"
+

@@ -57,6 +57,19 @@ def oracle():
     L.oracle_circular_trajectory.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                              C.c_double, C.c_double, _f64p]
     L.oracle_project_ellipsoids.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_int, _f32p]
+    L.oracle_direct_line_integrals.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_int, _f32p]
+    L.oracle_direct_pair_geometry.argtypes = [_f64p, _f64p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    L.oracle_direct_pair_geometry.restype = C.c_int
+    L.oracle_direct_pair.argtypes = [_f64p, _f64p, _f32p, _f32p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    L.oracle_direct_pair.restype = C.c_double
+    L.oracle_direct_evaluate.argtypes = [_f64p, C.c_int, _f32p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p]
+    L.oracle_direct_evaluate.restype = C.c_double
+    L.oracle_direct_fbcc_weight.argtypes = [_f32p, C.c_float]
+    L.oracle_direct_fbcc_weight.restype = C.c_float
     L.oracle_max_threads.restype = C.c_int
     L.oracle_set_threads.argtypes = [C.c_int]
     L.oracle_set_threads.restype = C.c_int
@@ -168,6 +181,65 @@ def ecc(Ps, dtrs, n_u, n_v, is_derivative=True, object_radius_mm=0.0, dkappa=0.0
     return mean, out, ks
 
 
+# ---- direct metric (EpipolarConsistencyDirect.{cpp,cu}, RectifiedFBCC.h) ----------------------------------------------------
+def direct_line_integrals(img, lines, fbcc=None, interp=INTERP_TEX8, shape=1, n_v_clip=None):
+    """kernel_computeLineIntegrals on the CPU.  lines [m, >= 3], fbcc [m, >= 6] or None.  shape 1: the loop as the reference's
+    sm_100 build executes it.  n_v_clip: height the clipping uses (the reference's launcher passes n_u)."""
+    img = np.ascontiguousarray(img, np.float32)
+    lines = np.ascontiguousarray(lines, np.float32)
+    n_v, n_u = img.shape
+    out = np.zeros(lines.shape[0], np.float32)
+    if fbcc is not None:
+        fbcc = np.ascontiguousarray(fbcc, np.float32)
+    oracle().oracle_direct_line_integrals(img, n_u, n_v, n_v if n_v_clip is None else n_v_clip, lines, lines.shape[0], lines.shape[1],
+                                          None if fbcc is None else fbcc.ctypes.data, 0 if fbcc is None else fbcc.shape[1], interp,
+                                          shape, out)
+    return out
+
+
+def direct_pair_geometry(P0, P1, n_u, n_v, radius=0.0, dkappa=0.0):
+    """What computeForImagePair prepares for its kernel: dict(kappas, lines0, lines1, fbcc0, fbcc1, dkappa)."""
+    P0 = np.ascontiguousarray(P0, np.float64).reshape(12)
+    P1 = np.ascontiguousarray(P1, np.float64).reshape(12)
+    dk = C.c_double()
+    m = oracle().oracle_direct_pair_geometry(P0, P1, radius, dkappa, n_u, n_v, 0, None, None, None, None, None, C.byref(dk))
+    out = dict(kappas=np.zeros(m, np.float32), lines0=np.zeros((m, 3), np.float32), lines1=np.zeros((m, 3), np.float32),
+               fbcc0=np.zeros((m, 8), np.float32), fbcc1=np.zeros((m, 8), np.float32))
+    oracle().oracle_direct_pair_geometry(P0, P1, radius, dkappa, n_u, n_v, m, out["kappas"].ctypes.data, out["lines0"].ctypes.data,
+                                         out["lines1"].ctypes.data, out["fbcc0"].ctypes.data, out["fbcc1"].ctypes.data, C.byref(dk))
+    out["dkappa"] = dk.value
+    return out
+
+
+def direct_pair(P0, P1, img0, img1, radius=0.0, dkappa=0.0, fbcc=False, interp=INTERP_TEX8, shape=1, reference_clip=False, kappas=None):
+    """computeForImagePair on the CPU: dict(value, kappas, samples0, samples1)."""
+    P0 = np.ascontiguousarray(P0, np.float64).reshape(12)
+    P1 = np.ascontiguousarray(P1, np.float64).reshape(12)
+    img0 = np.ascontiguousarray(img0, np.float32)
+    img1 = np.ascontiguousarray(img1, np.float32)
+    n_v, n_u = img0.shape
+    n = C.c_int()
+    args = (P0, P1, img0, img1, n_u, n_v, radius, dkappa, int(fbcc), interp, shape, int(reference_clip))
+    if kappas is not None:
+        k = np.ascontiguousarray(kappas, np.float32).copy()
+        m = k.shape[0]
+    else:
+        m = oracle().oracle_direct_pair_geometry(P0, P1, radius, dkappa, n_u, n_v, 0, None, None, None, None, None, None)
+        k = np.zeros(m, np.float32)
+    s0, s1 = np.zeros(m, np.float32), np.zeros(m, np.float32)
+    v = oracle().oracle_direct_pair(*args, m if kappas is not None else 0, m, k.ctypes.data, s0.ctypes.data, s1.ctypes.data, C.byref(n))
+    return dict(value=v, kappas=k, samples0=s0, samples1=s1)
+
+
+def direct_evaluate(Ps, images, radius=0.0, dkappa=0.0, fbcc=False, interp=INTERP_TEX8, shape=1, reference_clip=False, cost_image=None):
+    """MetricDirect::evaluate on the CPU: the SUM over all pairs (radius 0: from the first matrix)."""
+    Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 12)
+    images = np.ascontiguousarray(images, np.float32)
+    n, n_v, n_u = images.shape
+    return oracle().oracle_direct_evaluate(Ps, n, images, n_u, n_v, radius, dkappa, int(fbcc), interp, shape, int(reference_clip),
+                                           None if cost_image is None else cost_image.ctypes.data)
+
+
 def circular_trajectory(n, sid, sdd, n_u, n_v, max_angle_deg, pixel_spacing):
     Ps = np.zeros((n, 12), np.float64)
     oracle().oracle_circular_trajectory(n, sid, sdd, n_u, n_v, max_angle_deg, pixel_spacing, Ps)
@@ -204,6 +276,11 @@ def ref_host():
                                   C.c_float, C.c_float, _f32p, _f32p]
     L.ref_line_to_sample.argtypes = [_f32p, C.c_float]
     L.ref_line_to_sample.restype = C.c_int
+    if hasattr(L, "ref_fbcc_weight"):
+        for name in ("ref_fbcc_transform", "ref_fbcc_inverse", "ref_fbcc_derivative", "ref_fbcc_weight"):
+            getattr(L, name).argtypes = [_f32p, C.c_float]
+            getattr(L, name).restype = C.c_float
+        L.ref_fbcc_record_floats.restype = C.c_int
     _ref_host = L
     return L
 
@@ -239,6 +316,9 @@ def ref_cuda():
         L.ref_cuda_metric_create_pitch2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
         L.ref_cuda_metric_create_pitch2d.restype = C.c_void_p
         L.ref_cuda_metric_set_launcher.argtypes = [C.c_void_p, C.c_void_p]
+    if hasattr(L, "ref_cuda_direct_line_integrals"):
+        L.ref_cuda_direct_line_integrals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                     C.c_void_p, C.POINTER(C.c_float)]
     if hasattr(L, "ref_cuda_metric_get_k01"):
         L.ref_cuda_metric_get_k01.argtypes = [C.c_void_p, _f32p, C.c_int]
     if hasattr(L, "ref_cuda_metric_evaluate_corr"):
@@ -246,6 +326,25 @@ def ref_cuda():
         L.ref_cuda_metric_evaluate_corr.restype = C.c_double
     _ref_cuda = L
     return L
+
+
+def ref_cuda_direct_line_integrals(img, lines, fbcc=None):
+    """The reference's kernel_computeLineIntegrals through its own launcher (which clips against n_u x n_u).  Returns
+    (integrals, gpu_ms)."""
+    L = ref_cuda()
+    img = np.ascontiguousarray(img, np.float32)
+    lines = np.ascontiguousarray(lines, np.float32)
+    n_v, n_u = img.shape
+    out = np.zeros(lines.shape[0], np.float32)
+    if fbcc is not None:
+        fbcc = np.ascontiguousarray(fbcc, np.float32)
+    ms = C.c_float()
+    rc = L.ref_cuda_direct_line_integrals(img.ctypes.data, n_u, n_v, lines.ctypes.data, lines.shape[0], lines.shape[1],
+                                          None if fbcc is None else fbcc.ctypes.data, 0 if fbcc is None else fbcc.shape[1],
+                                          out.ctypes.data, C.byref(ms))
+    if rc:
+        raise RuntimeError(f"ref_cuda_direct_line_integrals failed ({rc})")
+    return out, ms.value
 
 
 def ref_cuda_radon(images, n_alpha, n_t, filter=0, post=0):

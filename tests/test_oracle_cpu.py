@@ -304,3 +304,141 @@ def test_preprocess_golden_matches_live_reference_build():
     work = g["lowpass_in"].copy()
     R.ref_lowpass2d(work, work.shape[1], work.shape[0], 1.84, 5)
     assert np.array_equal(work, g["lowpass_out_0"])
+
+
+# ---- direct metric (row N4: MetricDirect / FBCC) ---------------------------------------------------------------------------
+FBCC_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_fbcc_vectors.npz")
+DIRECT_ELL = np.array([[0, 0, 0, 60, 40, 50, 1.0], [20, -10, 5, 20, 25, 15, 0.5], [-25, 15, -10, 15, 10, 20, -0.4]])
+
+
+def _centre(P):
+    """Camera centre by numpy's SVD (what the reference does with Eigen's: Geometry::getCameraCenter)."""
+    c = np.linalg.svd(P.reshape(4, 3).T)[2][-1]
+    return c / c[3]
+
+
+def test_direct_fbcc_weight_pinned_by_reference_header():
+    """tests/golden/ref_fbcc_vectors.npz: the reference's own LinePerspectivity and the per-sample fan-beam weight of its
+    kernel (host build of RectifiedFBCC.h).  The oracle follows the roundings of the reference's GPU build (fused where nvcc
+    fuses), the golden values are the host build's: they agree to fp32 rounding."""
+    g = np.load(FBCC_GOLDEN)
+    O = ol.oracle()
+    worst, checked = 0.0, 0
+    for rec, ts, out in zip(g["recs"], g["ts"], g["out"]):
+        rec = np.ascontiguousarray(rec)
+        for t, (tr, inv, der, w) in zip(ts, out):
+            a, b, c, d = (np.float32(v) for v in rec[:4])
+            t = np.float32(t)
+            assert (a * t + b) / (c * t + d) == tr  # transform, plain fp32
+            if abs(c * t + d) < 0.05 * (abs(c * t) + abs(d)):
+                continue  # a position next to the pole of the perspectivity: every fp32 evaluation is noise there
+            got = O.oracle_direct_fbcc_weight(rec, float(t))
+            worst = max(worst, abs(got - w) / abs(w))
+            checked += 1
+    assert checked > 2500 and worst < 2e-5, (checked, worst)  # up to 20 x conditioning x a few fp32 roundings
+
+
+def test_direct_fbcc_golden_matches_live_reference_build():
+    R = ol.ref_host()
+    if R is None or not hasattr(R, "ref_fbcc_weight"):
+        import pytest
+        pytest.skip("oracle/_ref/libecc_ref_host.so (with the fan-beam entry points) not built")
+    g = np.load(FBCC_GOLDEN)
+    rec = np.ascontiguousarray(g["recs"][7])
+    for t, row in zip(g["ts"][7], g["out"][7]):
+        assert R.ref_fbcc_weight(rec, float(t)) == row[3] and R.ref_fbcc_derivative(rec, float(t)) == row[2]
+
+
+def test_direct_geometry_projective_properties():
+    """The host geometry of the direct metric is restated without Eigen (parity unpinned); these properties hold for ANY
+    correct implementation: every epipolar line passes through the epipole, the two lines of a plane are projections of
+    that plane (points of it project onto both), kappa = 0 is the plane through the origin, and the planes span the object."""
+    n_u, n_v = 320, 256
+    Ps = ol.circular_trajectory(12, 750.0, 1200.0, n_u, n_v, 200.0, 1.2)
+    for (i, j) in [(0, 4), (3, 10), (6, 7)]:
+        P0, P1 = Ps[i].reshape(4, 3).T, Ps[j].reshape(4, 3).T
+        C0, C1 = _centre(Ps[i]), _centre(Ps[j])
+        g = ol.direct_pair_geometry(Ps[i], Ps[j], n_u, n_v)
+        m = len(g["kappas"])
+        assert m == len(g["lines0"]) and abs(m - 2 * np.hypot(n_u, n_v)) <= 1  # as many planes as twice the diagonal
+        assert np.allclose(np.hypot(g["lines0"][:, 0], g["lines0"][:, 1]), 1, atol=1e-6)
+        e0, e1 = P0 @ C1, P1 @ C0
+        e0, e1 = e0 / e0[2], e1 / e1[2]
+        scale0, scale1 = np.abs(e0).max(), np.abs(e1).max()
+        assert np.abs(g["lines0"].astype(np.float64) @ e0).max() < 1e-5 * scale0
+        assert np.abs(g["lines1"].astype(np.float64) @ e1).max() < 1e-5 * scale1
+        # a third point of the plane: back-project a point of line 0, project it into view 1
+        for q in (0, m // 3, m // 2, m - 1):
+            l0, l1 = g["lines0"][q].astype(np.float64), g["lines1"][q].astype(np.float64)
+            x0 = np.array([-l0[2] * l0[0] + 40 * l0[1], -l0[2] * l0[1] - 40 * l0[0], 1.0])  # on l0
+            X = np.linalg.pinv(P0) @ x0 + 0.3 * C0
+            x1 = P1 @ X
+            assert abs(l1 @ (x1 / x1[2])) < 2e-3  # fp32 line coefficients, epipole ~1e3 px away
+        # kappa = 0: the plane contains the origin -> its lines pass through the origin's projections
+        q0 = int(np.argmin(np.abs(g["kappas"])))
+        o0 = P0 @ np.array([0, 0, 0, 1.0])
+        assert abs(g["lines0"][q0].astype(np.float64) @ (o0 / o0[2])) < 1.5 * g["dkappa"] * 1200 / 1.2
+        # symmetric range, first angle = -kappa_max, step as computeForImagePair derives it
+        assert g["kappas"][0] == np.float32(-0.5 * g["dkappa"] * 2 * np.hypot(n_u, n_v)) or abs(g["kappas"][0] + g["kappas"][-1]) < 2 * g["dkappa"]
+        # fan-beam records: the perspectivity is orientation preserving (a d - b c >= 0 after the sign fix), distances positive
+        f = g["fbcc0"].astype(np.float64)
+        assert (f[:, 0] * f[:, 3] - f[:, 1] * f[:, 2] >= 0).all() and (f[:, 5] > 0).all()
+        # squared source-to-line distance in pixels: between (source-detector distance)^2 and that plus the image diagonal^2
+        assert (f[:, 5] > (0.5 * 750) ** 2).all()
+
+
+def test_direct_line_integral_invariants():
+    n_u, n_v = 96, 80
+    rng = np.random.default_rng(5)
+    ang = rng.uniform(-np.pi, np.pi, 200)
+    pts = np.stack([rng.uniform(10, n_u - 10, 200), rng.uniform(10, n_v - 10, 200)], 1)
+    lines = np.stack([np.cos(ang), np.sin(ang), -(np.cos(ang) * pts[:, 0] + np.sin(ang) * pts[:, 1])], 1).astype(np.float32)
+    const = np.full((n_v, n_u), 3.0, np.float32)
+    for interp in (ol.INTERP_EXACT, ol.INTERP_TEX8):
+        # the derivative of a constant image vanishes (both parallel lines see the same samples)
+        d = ol.direct_line_integrals(const, lines, interp=interp)
+        assert np.abs(d).max() < 1e-3
+        # a ramp along u: the derivative across the line is length * l0 (1 px between the two lines)
+        ramp = np.tile(np.arange(n_u, dtype=np.float32), (n_v, 1))
+        d = ol.direct_line_integrals(ramp, lines, interp=interp, shape=0)
+        o = -lines[:, 2:3] * lines[:, :2]
+        dvec = np.stack([lines[:, 1], -lines[:, 0]], 1)
+        with np.errstate(divide="ignore"):
+            ts = np.stack([(1 - o[:, 0]) / dvec[:, 0], (n_u - 1 - o[:, 0]) / dvec[:, 0], (1 - o[:, 1]) / dvec[:, 1], (n_v - 1 - o[:, 1]) / dvec[:, 1]], 1)
+        ts.sort(axis=1)
+        n_samples = np.floor((ts[:, 2] - ts[:, 1]) / 0.4) + 1
+        # (up to one clamped sample at either end: the outer line may leave the last pixel centre by half a pixel)
+        assert np.abs(d - lines[:, 0] * n_samples * 0.4).max() < 0.5
+    # source loop and executed shape differ by at most the last sample; a line outside the image gives zero
+    img = rng.standard_normal((n_v, n_u)).astype(np.float32)
+    a = ol.direct_line_integrals(img, lines, shape=0)
+    b = ol.direct_line_integrals(img, lines, shape=1)
+    assert (a != b).mean() < 0.05
+    outside = np.array([[1.0, 0.0, 50.0], [0.0, 1.0, -500.0]], np.float32)
+    assert (ol.direct_line_integrals(img, outside) == 0).all()
+    # the reference's launcher clips against n_u x n_u: on a wide image only lines through the bottom rows can change
+    wide = rng.standard_normal((40, 96)).astype(np.float32)
+    l2 = np.array([[0.0, 1.0, -20.0], [1.0, 0.0, -48.0]], np.float32)  # horizontal at v = 20, vertical at u = 48
+    r_img = ol.direct_line_integrals(wide, l2, n_v_clip=40)
+    r_ref = ol.direct_line_integrals(wide, l2, n_v_clip=96)
+    assert r_img[0] == r_ref[0] and r_img[1] != r_ref[1]
+
+
+def test_direct_pair_consistency_on_the_cpu():
+    """Small scene on the CPU: true matrices score lower than a shifted detector; the pair value is the sum its signals give."""
+    n_u, n_v = 96, 80
+    Ps = ol.circular_trajectory(6, 750.0, 1200.0, n_u, n_v, 200.0, 3.0)
+    imgs = [ol.project_ellipsoids(P, n_u, n_v, DIRECT_ELL) for P in Ps]
+    for fbcc in (False, True):
+        r = ol.direct_pair(Ps[0], Ps[2], imgs[0], imgs[2], fbcc=fbcc)
+        d = r["samples0"] - r["samples1"]
+        dk = ol.direct_pair_geometry(Ps[0], Ps[2], n_u, n_v)["dkappa"]
+        assert r["value"] == np.sum((d * d).astype(np.float64) * dk) or abs(r["value"] - np.sum((d * d).astype(np.float64)) * dk) < 1e-12 * r["value"]
+        H = np.array([[1, 0, 2.0], [0, 1, 2.0], [0, 0, 1]])
+        Pm = (H @ Ps[2].reshape(4, 3).T).T.reshape(12)
+        moved = ol.direct_pair(Ps[0], Pm, imgs[0], imgs[2], fbcc=fbcc)
+        assert moved["value"] > 1.5 * r["value"], (fbcc, r["value"], moved["value"])
+    total = ol.direct_evaluate(Ps[:3], np.stack(imgs[:3]))
+    radius = ol.object_radius(Ps[0], n_u, n_v)
+    pairs = [ol.direct_pair(Ps[i], Ps[j], imgs[i], imgs[j], radius=radius)["value"] for i in range(3) for j in range(i + 1, 3)]
+    assert total == sum(pairs)
