@@ -59,6 +59,7 @@ SIGNATURES = {
     "ecc_evaluate_batch_params": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "ecc_model_expand": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "ecc_direct_set_images": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int]),
+    "ecc_direct_set_image_pointers": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int]),
     "ecc_direct_set_fan_beam": (C.c_int, [c_ctx, C.c_int]),
     "ecc_direct_set_reference_clip": (C.c_int, [c_ctx, C.c_int]),
     "ecc_direct_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),

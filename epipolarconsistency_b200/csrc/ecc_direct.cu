@@ -218,7 +218,10 @@ struct DirectLaunch {
     float *sig0, *sig1, *kappas_out;  // single pair: the redundant signals (nullable)
 };
 
-__global__ void __launch_bounds__(2 * kLinesPerCta)
+#ifndef ECC_DIRECT_MINBLOCKS
+#define ECC_DIRECT_MINBLOCKS 16
+#endif
+__global__ void __launch_bounds__(2 * kLinesPerCta, ECC_DIRECT_MINBLOCKS)
 direct_lines_kernel(const __grid_constant__ DirectLaunch p)
 {
     __shared__ float v_s[2][kLinesPerCta];
@@ -439,6 +442,24 @@ int ecc_direct_set_images(ecc_context* ctx, const float* images, int n, int n_u,
     D.n_images = n;
     // Metric::n_u / n_v (MetricDirect::setProjectionImages, EpipolarConsistencyDirect.cpp:226-234): the size getObjectRadius
     // estimates the radius for, unless Radon intermediates have set it
+    if (ctx->n_dtrs == 0) { ctx->n_u = n_u; ctx->n_v = n_v; }
+    return ECC_OK;
+}
+
+int ecc_direct_set_image_pointers(ecc_context* ctx, const float* const* images, int n, int n_u, int n_v)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (n < 0 || (n > 0 && !images) || n_u < 2 || n_v < 2) return fail(ctx, ECC_ERR_INVALID, "ecc_direct_set_image_pointers: bad argument");
+    for (int k = 0; k < n; k++)
+        if (!images[k]) return fail(ctx, ECC_ERR_INVALID, "ecc_direct_set_image_pointers: null image");
+    int rc = ensure_direct_images(ctx, n_u, n_v, n);
+    if (rc) return rc;
+    DirectState& D = ctx->direct;
+    for (int k = 0; k < n; k++)
+        ECC_CUDA(ctx, cudaMemcpy2DToArrayAsync(D.arrays[k], 0, 0, images[k], sizeof(float) * n_u, sizeof(float) * n_u, n_v, cudaMemcpyDefault, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    D.n_images = n;
     if (ctx->n_dtrs == 0) { ctx->n_u = n_u; ctx->n_v = n_v; }
     return ECC_OK;
 }

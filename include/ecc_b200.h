@@ -291,6 +291,9 @@ int ecc_partition_pairs(ecc_context* ctx, int n_parts, long long* bounds);
 /* MetricDirect::setProjectionImages: n pre-processed projections [h|d] of n_v rows x n_u floats, copied into CUDA arrays
  * behind pixel-coordinate, linear-filter, clamp textures (BindlessTexture2D<float>'s defaults). */
 int ecc_direct_set_images(ecc_context* ctx, const float* images, int n, int n_u, int n_v);
+/* The same for images that live in separate allocations (the reference keeps a std::vector<BindlessTexture2D<float>*>,
+ * EpipolarConsistencyDirect.h:31): images = host array of n pointers, each [h|d]. */
+int ecc_direct_set_image_pointers(ecc_context* ctx, const float* const* images, int n, int n_u, int n_v);
 /* MetricDirect::setFanBeamConsistency: the rectified fan-beam consistency (weighted integrals) instead of the derivative. */
 int ecc_direct_set_fan_beam(ecc_context* ctx, int fbcc);
 /* The reference's launcher hands the kernel n_u for BOTH image sizes (EpipolarConsistencyDirect.cu:135), i.e. it clips

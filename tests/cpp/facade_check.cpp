@@ -5,6 +5,7 @@
 #define ECC_FACADE_THROW
 #include <EpipolarConsistency/EpipolarConsistencyRadonIntermediate.h>
 #include <EpipolarConsistency/Adaptors.h>
+#include <EpipolarConsistency/EpipolarConsistencyDirect.h>
 #include <EpipolarConsistency/Projtable.h>
 
 #include <cmath>
@@ -338,6 +339,34 @@ static int run_gpu(const char* tmpdir)
         if (std::fabs(q[n_u * (n_v / 2) + n_u / 2] - 5.f) > 1e-5f) return fail("PreProccess centre");
         if (!(q[n_u * (n_v / 2) + 8] > 0.f && q[n_u * (n_v / 2) + 8] < 5.f)) return fail("PreProccess feather");
         std::printf("pre %.9g %.9g\n", q[n_u * (n_v / 2) + 8], q[n_u * 30 + 40]);
+    }
+    {   // MetricDirect / computeForImagePair (EpipolarConsistencyDirect.h): the metric straight from the images
+        std::vector<UtilsCuda::BindlessTexture2D<float>*> Is(n);
+        for (int i = 0; i < n; i++) Is[i] = new UtilsCuda::BindlessTexture2D<float>(n_u, n_v, (const float*)images[i]);
+        MetricDirect direct(Ps, Is);
+        if (direct.getNumberOfProjetions() != n) return fail("MetricDirect::getNumberOfProjetions");
+        std::vector<float> cost((size_t)n * n, -1.f);
+        const double total = direct.evaluate(cost.data());
+        std::vector<float> s0, s1, kap;
+        const double v13 = direct.evaluateForImagePair(1, 3, &s0, &s1, &kap);
+        if (kap.empty() || s0.size() != 3 * kap.size() || s1.size() != 3 * kap.size()) return fail("MetricDirect sample vector sizes");
+        if (cost[1 + 3 * n] != (float)v13 || cost[3 + 1 * n] != -1.f || cost[0] != -1.f) return fail("MetricDirect cost image layout");
+        double ssd = 0;
+        for (size_t q = 0; q < kap.size(); q++) ssd += (double)((s0[q] - s1[q]) * (s0[q] - s1[q]));
+        // the caller's kappas: the same planes give the same signals
+        std::vector<float> t0, t1, given(kap.begin() + 5, kap.begin() + 40);
+        direct.evaluateForImagePair(1, 3, &t0, &t1, &given);
+        if (given.size() != 35 || std::memcmp(t0.data(), s0.data() + 5, sizeof(float) * 35) != 0) return fail("MetricDirect with given kappas");
+        // the free function on the same two views with the metric's radius and step: the same value
+        const double dk = (double)(kap[1] - kap[0]);
+        const double free_v = computeForImagePair(Ps[1], Ps[3], *Is[1], *Is[3], 0.0, direct.getObjectRadius());
+        direct.setFanBeamConsistency(true);
+        const double fb = direct.evaluateForImagePair(1, 3);
+        const double free_fb = computeForImagePair(Ps[1], Ps[3], *Is[1], *Is[3], 0.0, direct.getObjectRadius(), true);
+        std::printf("direct %.12g %.12g %d %.12g %.9g %.12g %.12g %.12g %.12g\n", total, v13, (int)kap.size(), ssd, dk, free_v, fb, free_fb,
+                    direct.getObjectRadius());
+        if (free_v != v13 || free_fb != fb) return fail("computeForImagePair vs MetricDirect::evaluateForImagePair");
+        for (auto t : Is) delete t;
     }
     for (auto d : dtrs) delete d;
     std::printf("OK gpu\n");

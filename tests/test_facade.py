@@ -102,7 +102,7 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
             pairs[(int(t[1]), int(t[2]))] = float(t[3])
         elif t[0] in ("radius", "mean", "subset", "fixed"):
             vals[t[0]] = float(t[1])
-        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre", "signals", "fdct", "fdctview"):
+        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre", "signals", "fdct", "fdctview", "direct"):
             vals[t[0]] = [float(x) for x in t[1:]]
         elif t[0] == "l2s":
             vals.setdefault("l2s", []).append([float(x) for x in t[1:]])
@@ -189,3 +189,18 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
     ctx.set_object_radius(50.0)
     ctx.set_epipolar_plane_step(0.002)
     assert abs(vals["fixed"] - ctx.evaluate(None)) <= 1e-7 * vals["fixed"]
+    # MetricDirect / computeForImagePair through the facade = the Python mirror of the same ABI on the same images
+    total, v13, n_lines, ssd, dk, free_v, fb, free_fb, radius = vals["direct"]
+    ctx.set_object_radius(0.0)
+    ctx.set_epipolar_plane_step(0.0)
+    ctx.direct_set_images(imgs)
+    ctx.direct_set_fan_beam(False)
+    same = lambda a, b: abs(a - b) <= 2e-11 * abs(b)  # the facade check prints 12 digits
+    assert same(total, ctx.direct_evaluate(None))
+    r13 = ctx.direct_evaluate_pair(1, 3)
+    assert same(v13, r13["value"]) and int(n_lines) == len(r13["kappas"]) and free_v == v13
+    assert abs(ssd * ctx.direct_pair_geometry(1, 3)["dkappa"] - v13) <= 1e-9 * v13
+    assert abs(radius - ol.object_radius(Ps[0], n_u, n_v)) <= 1e-9 * radius
+    ctx.direct_set_fan_beam(True)
+    assert same(fb, ctx.direct_evaluate_pair(1, 3)["value"]) and free_fb == fb
+    ctx.direct_set_fan_beam(False)
