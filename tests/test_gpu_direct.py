@@ -252,3 +252,30 @@ def test_metric_direct_class_and_errors(ctx, scene):
     ctx.direct_set_images(scene["imgs"][:1])
     ctx.set_projection_matrices(scene["Ps"][:1])
     assert ctx.direct_evaluate(None) == 0.0
+
+
+def test_ragged_and_degenerate_sizes(ctx):
+    """Tiny odd-sized images, plane counts that are no multiple of the 32 planes of a CTA, a single plane, no plane at all."""
+    n_u, n_v = 37, 23
+    Ps, imgs = make_scene(3, n_u, n_v, 9.0, arc=90)
+    for fbcc in (False, True):
+        for dkappa, expect in ((0.0, None), (0.05, None), (0.2, None), (10.0, 0)):
+            setup(ctx, Ps, imgs, fbcc=fbcc, dkappa=dkappa)
+            radius = ol.object_radius(Ps[0], n_u, n_v)
+            cost = np.zeros((3, 3), np.float32)
+            total = ctx.direct_evaluate(cost)
+            want_cost = np.zeros((3, 3), np.float32)
+            want = ol.direct_evaluate(Ps, imgs, dkappa=dkappa, fbcc=fbcc, cost_image=want_cost)
+            for (i, j) in ((0, 1), (0, 2), (1, 2)):
+                got = ctx.direct_evaluate_pair(i, j)
+                ref = ol.direct_pair(Ps[i], Ps[j], imgs[i], imgs[j], radius=radius, dkappa=dkappa, fbcc=fbcc)
+                assert len(got["kappas"]) == len(ref["kappas"])
+                if expect is not None:
+                    assert len(got["kappas"]) == expect and got["value"] == 0.0
+                if len(ref["kappas"]):
+                    scale = max(np.abs(ref["samples0"]).max(), 1e-6)
+                    assert np.abs(got["samples0"] - ref["samples0"]).max() <= 5e-3 * scale
+            if want > 0:
+                assert abs(total - want) <= 2e-2 * want
+            else:
+                assert total == 0.0 and not cost.any()
