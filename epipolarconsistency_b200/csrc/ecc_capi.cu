@@ -11,6 +11,7 @@
 // a value, errors are returned instead of exit().
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "ecc_geometry.cuh"
@@ -298,11 +299,14 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
     // Host memory on either side: stream the batch through device staging in chunks.  Host images go through two
     // staging buffers on a copy stream of their own, so that the upload of chunk i+1 runs under the kernels of chunk i
     // (the first chunk is small: its upload is the only one that is exposed).
-    // Chunk schedule for host images: 8, 16, 32, 64, 128, 128, ... -- the first upload is the only exposed one, every later
-    // upload (at most twice the images of the chunk computing above it) hides as long as the link delivers 16 GB/s, and the
-    // persistent kernel gets few, large launches (1.2 GB of staging at the C3 image size).
+    // Chunk schedule for host images: 4, 8, 16, 32, 64, 128, 128, ... -- the first upload (one quad of projections) is the
+    // only exposed one, every later upload (at most twice the images of the chunk computing above it) hides as long as the
+    // link delivers 17 GB/s, and the persistent kernel gets few, large launches (1.2 GB of staging at the C3 image size).
+    // ECC_FIRST_CHUNK: development knob (a multiple of four: chunks are whole quads of projections).
     const int chunk = n_images < 128 ? n_images : 128;
-    const int first_chunk = (!in_dev && n_images > 8) ? 8 : chunk;
+    static const int first_env = getenv("ECC_FIRST_CHUNK") ? atoi(getenv("ECC_FIRST_CHUNK")) : 4;
+    const int first_want = first_env >= 4 ? first_env / 4 * 4 : 4;
+    const int first_chunk = (!in_dev && n_images > first_want) ? first_want : chunk;
     int rc;
     if (!in_dev && (rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * img_elems * chunk * 2))) return rc;
     if (!out_dev && (rc = ensure_bytes(ctx, (void**)&ctx->out_stage_d, &ctx->out_stage_bytes, sizeof(float) * dtr_elems * chunk))) return rc;
@@ -325,7 +329,7 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
     int k = 0, want = first_chunk;
     for (int first = 0; first < n_images; k++) {
         int n = (n_images - first < want) ? n_images - first : want;
-        if (n_images - first - n > 0 && n_images - first - n < 8 && n_images - first <= chunk) n = n_images - first;  // no tiny last launch
+        if (n_images - first - n > 0 && n_images - first - n < 8 && n_images - first <= chunk && n >= 8) n = n_images - first;  // no tiny last launch
         want = (2 * want < chunk) ? 2 * want : chunk;
         const float* src = images + (size_t)first * img_elems;
         const int b = k & 1;
