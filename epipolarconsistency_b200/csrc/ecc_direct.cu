@@ -15,6 +15,8 @@
 // order.  No atomics: results are reproducible.  The line integral is the reference's EXECUTED kernel operation by operation
 // (sample positions, fused and unfused roundings, the compiler's four-sample blocks of its loop).
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -423,6 +425,29 @@ void free_direct(ecc_context* ctx)
 }  // namespace eccb200
 
 using namespace eccb200;
+
+// ---- the reference's launcher symbol with ITS OWN signature (C++ linkage) -------------------------------------------------
+// EpipolarConsistencyDirect.cpp:10-16 declares it `extern`, EpipolarConsistencyDirect.cu:122-142 defines it: linking the
+// reference's unmodified EpipolarConsistencyDirect.cpp against libecc_b200.so instead of its own .cu resolves the symbol here
+// (INTEGRATION.md option B).  Same arguments, same buffer written, legacy default stream, returns when the work has finished.
+// The reference's definition hands its kernel n_u for both image sizes (:135), i.e. clips against n_u x n_u: so does this
+// symbol -- it exists to give the reference's bits (checked: bit-identical integrals) -- unless ECC_COMPAT_DIRECT_CLIP=image.
+void cuda_computeLineIntegrals(short n_lines, float* lines_d, short line_stride, float* fbcc_d, short fbcc_stride, cudaTextureObject_t I,
+                               short n_u, short n_v, float* integrals_out_d)
+{
+    if (n_lines <= 0) return;
+    static const bool clip_image = [] {
+        const char* v = getenv("ECC_COMPAT_DIRECT_CLIP");
+        return v && v[0] == 'i';
+    }();
+    direct_given_lines_kernel<<<(n_lines + 31) / 32, 32, 0, cudaStreamLegacy>>>(n_lines, lines_d, line_stride, fbcc_d, fbcc_stride, I, n_u,
+                                                                             clip_image ? n_v : n_u, integrals_out_d);
+    const cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(cudaStreamLegacy);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {  // the reference's convention: print and exit (UtilsCuda.hxx:14-28)
+        std::fprintf(stderr, "libecc_b200 (cuda_computeLineIntegrals): %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        std::exit(1);
+    }
+}
 
 extern "C" {
 

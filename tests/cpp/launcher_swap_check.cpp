@@ -1,4 +1,4 @@
-// launcher_swap_check.cpp -- INTEGRATION.md option B, compiled: the reference's two launcher symbols, declared exactly as the
+// launcher_swap_check.cpp -- INTEGRATION.md option B, compiled: the reference's launcher symbols (two of the Radon-intermediate path, one of the direct metric), declared exactly as the
 // reference's own .cpp files declare them (EpipolarConsistencyRadonIntermediate.cpp:16-37, RadonIntermediate.cpp:12) and
 // called the way those files call them (cudaArray textures from BindlessTexture2D, handle table + Cs + PinvTs in device
 // memory, K01s / out / out_corr scratch), resolved by libecc_b200.so.  Results are compared with the C ABI's own entry
@@ -18,6 +18,14 @@ extern void computeDerivLineIntegrals(cudaTextureObject_t in, int n_x, int n_y, 
 void epipolarConsistency(int n_x, int n_y, int num_dtrs, char* dtrs_d, int n_alpha, int n_t, float step_alpha, float step_t, int num_Ps,
                          float* Cs_d, float* PinvTs_d, int num_pairs, int* indices_d, float* K01s_d, float* out_d, float object_radius_mm,
                          float dkappa, bool isDerivative, bool use_corr, float* out_corr_d);
+
+// EpipolarConsistencyDirect.cpp:10-16, verbatim
+extern void cuda_computeLineIntegrals(
+	short n_lines,                               // Number of lines
+	float* lines_d, short line_stride,           // Lines in Hessian normal form and number of float values to next line
+	float *fbcc_d, short fbcc_stride,            // Optional: FBCC_weighting_info for rectification and source-distance-weighting.
+	cudaTextureObject_t I, short n_u, short n_v, // The image and its size
+	float *integrals_out_d);                     // Output memory: the integrals (size is n_lines)
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
@@ -218,12 +226,53 @@ int main()
             EXPECT(std::fabs((1.0f - cc) - corr_abi[i + (size_t)j * n]) <= 2e-6f, "1 - cc of pair %d: %g vs %g", k, 1.0f - cc, corr_abi[i + (size_t)j * n]);
         }
 
+    {   // ---- computeForImagePair's device part as the reference runs it (EpipolarConsistencyDirect.cpp:108-125,188-198): lines
+        // interleaved l0 l1 (stride 6), FBCC records interleaved (stride 16), one launcher call per image -----------------------
+        ECC(ecc_direct_set_images(ctx, images_d, n, n_u, n_v));
+        ECC(ecc_direct_set_reference_clip(ctx, 1));  // the reference's launcher clips against n_u x n_u (EpipolarConsistencyDirect.cu:135)
+        ECC(ecc_set_object_radius(ctx, 0.0));
+        ECC(ecc_set_epipolar_plane_step(ctx, 0.0));
+        int n_lines = 0;
+        ECC(ecc_direct_pair_geometry(ctx, 1, 4, 0, 0x0, 0x0, 0x0, 0x0, 0x0, &n_lines, 0x0));
+        std::vector<float> l0(3 * n_lines), l1(3 * n_lines), f0(8 * n_lines), f1(8 * n_lines), l01(6 * n_lines), f01(16 * n_lines);
+        ECC(ecc_direct_pair_geometry(ctx, 1, 4, n_lines, 0x0, l0.data(), l1.data(), f0.data(), f1.data(), &n_lines, 0x0));
+        for (int q = 0; q < n_lines; q++) {
+            std::memcpy(&l01[6 * q], &l0[3 * q], 12);
+            std::memcpy(&l01[6 * q + 3], &l1[3 * q], 12);
+            std::memcpy(&f01[16 * q], &f0[8 * q], 32);
+            std::memcpy(&f01[16 * q + 8], &f1[8 * q], 32);
+        }
+        float *l01_d = nullptr, *f01_d = nullptr, *v_d = nullptr;
+        CK(cudaMalloc(&l01_d, sizeof(float) * l01.size()));
+        CK(cudaMalloc(&f01_d, sizeof(float) * f01.size()));
+        CK(cudaMalloc(&v_d, sizeof(float) * n_lines));
+        CK(cudaMemcpy(l01_d, l01.data(), sizeof(float) * l01.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(f01_d, f01.data(), sizeof(float) * f01.size(), cudaMemcpyHostToDevice));
+        ArrayTexture I1(n_u, n_v, images_d + img * 1, false), I4(n_u, n_v, images_d + img * 4, false);
+        std::vector<float> got(n_lines), want(n_lines);
+        for (int fb = 0; fb < 2; fb++)
+            for (int view = 0; view < 2; view++) {
+                cuda_computeLineIntegrals((short)n_lines, l01_d + 3 * view, 6, fb ? f01_d + 8 * view : 0x0, fb ? 16 : 0, view ? I4.tex : I1.tex,
+                                          (short)n_u, (short)n_v, v_d);
+                CK(cudaMemcpy(got.data(), v_d, sizeof(float) * n_lines, cudaMemcpyDeviceToHost));
+                ECC(ecc_direct_line_integrals(ctx, view ? 4 : 1, view ? l1.data() : l0.data(), n_lines, 3, fb ? (view ? f1.data() : f0.data()) : 0x0, 8,
+                                              want.data()));
+                double energy = 0;
+                for (int q = 0; q < n_lines; q++) energy += (double)want[q] * want[q];
+                EXPECT(n_lines > 100 && energy > 0 && std::memcmp(got.data(), want.data(), sizeof(float) * n_lines) == 0,
+                       "cuda_computeLineIntegrals (fbcc %d, view %d) != ecc_direct_line_integrals", fb, view);
+            }
+        cudaFree(l01_d);
+        cudaFree(f01_d);
+        cudaFree(v_d);
+    }
+
     for (auto* t : tex) delete t;
     ecc_destroy(ctx);
     if (failures) {
         std::printf("%d check(s) failed\n", failures);
         return 1;
     }
-    std::printf("OK launcher swap: computeDerivLineIntegrals and epipolarConsistency resolved by libecc_b200.so, results identical to the C ABI\n");
+    std::printf("OK launcher swap: computeDerivLineIntegrals, epipolarConsistency and cuda_computeLineIntegrals resolved by libecc_b200.so, results identical to the C ABI\n");
     return 0;
 }

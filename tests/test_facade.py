@@ -27,6 +27,9 @@ def test_launcher_symbols_have_the_reference_signatures():
     assert " T _Z19epipolarConsistencyiiiPciiffiPfS0_iPiS0_S0_ffbbS0_" in syms
     # _Z25computeDerivLineIntegralsyiiiiiiPf : (cudaTextureObject_t = unsigned long long,int,int,int,int,int,int,float*)
     assert " T _Z25computeDerivLineIntegralsyiiiiiiPf" in syms
+    # _Z25cuda_computeLineIntegralssPfsS_syssS_ : (short,float*,short,float*,short,cudaTextureObject_t,short,short,float*) --
+    # EpipolarConsistencyDirect.cpp:10-16, the direct metric's launcher
+    assert " T _Z25cuda_computeLineIntegralssPfsS_syssS_" in syms
     build("launcher_swap_check")  # the reference's declarations, verbatim, link against the library
 
 
