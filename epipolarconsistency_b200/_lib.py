@@ -57,6 +57,10 @@ SIGNATURES = {
     "ecc_model_transform": (None, [c_vp, c_vp, c_vp, c_vp]),
     "ecc_model_camera_similarity_2d3d": (None, [c_vp, c_vp, c_vp]),
     "ecc_evaluate_batch_params": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "ecc_evaluate_batch_transforms": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
+    "ecc_transform_expand": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
+    "ecc_model_calibration_correction": (None, [c_vp, c_vp, c_vp, c_vp]),
+    "ecc_model_normalize": (None, [c_vp]),
     "ecc_model_expand": (C.c_int, [c_ctx, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "ecc_direct_set_images": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int]),
     "ecc_direct_set_image_pointers": (C.c_int, [c_ctx, c_vp, C.c_int, C.c_int, C.c_int]),

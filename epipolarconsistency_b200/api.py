@@ -272,6 +272,37 @@ class Context:
         self._check(self.lib.ecc_model_expand(self.h, _ptr(base_Ps, _F64), _ptr(params, _F64), K, m, _ptr(view_to_param, _I32), _ptr(out, _F64)))
         return out
 
+    def evaluate_batch_transforms(self, base_Ps, transforms, view_to_transform=None, normalize=False, idx4=None, out=None):
+        """Batched mode fed with explicit homographies: transforms (K, m, 25) = H (3x3) then T (4x4), column-major; P' = H P T
+        (normalised when asked) on the device.  view_to_transform None: m == n, or m == 1 = one correction for the whole
+        trajectory (ModelFDCTCalibrationCorrection).  Returns the K means."""
+        transforms = np.ascontiguousarray(transforms, np.float64)
+        K, m = transforms.shape[0], transforms.shape[1]
+        if base_Ps is not None:
+            base_Ps = np.ascontiguousarray(base_Ps, np.float64).reshape(-1, 12)
+        if view_to_transform is not None:
+            view_to_transform = np.ascontiguousarray(view_to_transform, np.int32)
+        n_pairs = 0 if idx4 is None else idx4.shape[0]
+        means = np.zeros(K, np.float64)
+        self._check(self.lib.ecc_evaluate_batch_transforms(self.h, _ptr(base_Ps, _F64), _ptr(transforms, _F64), K, m,
+                                                           _ptr(view_to_transform, _I32), int(bool(normalize)), _ptr(idx4, _I32), n_pairs,
+                                                           _ptr(out, _F32), _ptr(means, _F64)))
+        return means
+
+    def transform_expand(self, base_Ps, transforms, view_to_transform=None, normalize=False, n_views=None):
+        """The matrices (K, n, 12) the device builds from transforms (K, m, 25): see evaluate_batch_transforms."""
+        transforms = np.ascontiguousarray(transforms, np.float64)
+        K, m = transforms.shape[0], transforms.shape[1]
+        if base_Ps is not None:
+            base_Ps = np.ascontiguousarray(base_Ps, np.float64).reshape(-1, 12)
+            n_views = base_Ps.shape[0]
+        if view_to_transform is not None:
+            view_to_transform = np.ascontiguousarray(view_to_transform, np.int32)
+        out = np.zeros((K, n_views, 12), np.float64)
+        self._check(self.lib.ecc_transform_expand(self.h, _ptr(base_Ps, _F64), _ptr(transforms, _F64), K, m, _ptr(view_to_transform, _I32),
+                                                  int(bool(normalize)), _ptr(out, _F64)))
+        return out
+
     def pair_signals(self, i, j, dtr_i=None, dtr_j=None):
         """evaluateForImagePair (EpipolarConsistencyRadonIntermediate.cpp:324-393): the redundant signals of one pair in
         ascending kappa.  Returns dict(kappas, signal0, signal1, lines0, lines1, weight, value)."""
@@ -537,6 +568,25 @@ def model_camera_similarity_2d3d(P, x):
     x = np.ascontiguousarray(x, np.float64).reshape(11)
     out = np.zeros(12, np.float64)
     _lib.load().ecc_model_camera_similarity_2d3d(_ptr(P), _ptr(x), _ptr(out))
+    return out
+
+
+def model_calibration_correction(geom4, x7):
+    """ModelFDCTCalibrationCorrection::getTransforms as the library computes it: geom4 = mean principal point u, v, source-
+    isocentre and source-detector distance; x7 = translation u, v, yaw, pitch, roll, delta SID, delta SDD.
+    Returns 25 doubles: H (3x3) then T (4x4), column-major -- one instance of evaluate_batch_transforms."""
+    g = np.ascontiguousarray(geom4, np.float64).reshape(4)
+    x = np.ascontiguousarray(x7, np.float64).reshape(7)
+    out = np.zeros(25, np.float64)
+    H, T = out[:9], out[9:]
+    _lib.load().ecc_model_calibration_correction(_ptr(g), _ptr(x), H.ctypes.data, T.ctypes.data)
+    return out
+
+
+def model_normalize(P):
+    """Geometry::normalizeProjectionMatrix with the library's bits; returns a new 12-vector."""
+    out = np.ascontiguousarray(P, np.float64).reshape(12).copy()
+    _lib.load().ecc_model_normalize(_ptr(out))
     return out
 
 

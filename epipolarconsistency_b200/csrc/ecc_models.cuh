@@ -138,4 +138,62 @@ __host__ __device__ inline void model_camera_similarity_2d3d(const double* P, co
     model_transform(H, P, T, out);
 }
 
+// C = A * B, 3x3 column-major, separately rounded operations.
+__host__ __device__ inline void mat3_mul(const double* A, const double* B, double* C)
+{
+    double R[9];
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) {
+            double acc = 0.0;
+            for (int k = 0; k < 3; k++) acc = R2::add(acc, R2::mul(A[r + 3 * k], B[k + 3 * c]));
+            R[r + 3 * c] = acc;
+        }
+    for (int i = 0; i < 9; i++) C[i] = R[i];
+}
+
+// ModelFDCTCalibrationCorrection::getTransforms (Models/ModelFDCTCalibrationCorrection.hxx:150-203): ONE correction for the
+// whole trajectory.  geom = mean principal point u, v, mean source-isocentre and source-detector distance (the model's
+// pp_u, pp_v, sid, sdd); x = translation u, v, yaw, pitch, roll, delta SID, delta SDD.
+//   H = H_shift * Hpp * H_roll * H_scale * Hppinv   (detector shift incl. tan(yaw|pitch) sdd; roll and SDD scale about the
+//   principal point), T = diag(s, s, s, 1) with s = (sid + x5) / sid.   H 3x3, T 4x4, column-major.
+__host__ __device__ inline void model_calibration_correction(const double* geom, const double* x, double* H, double* T)
+{
+    const double pp_u = geom[0], pp_v = geom[1], sid = geom[2], sdd = geom[3];
+    const double sid_scale = R2::div(R2::add(sid, x[5]), sid), sdd_scale = R2::div(R2::add(sdd, x[6]), sdd);
+    double H_roll[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, H_shift[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, H_scale[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double Hpp[9] = {1, 0, 0, 0, 1, 0, pp_u, pp_v, 1.0}, Hppinv[9] = {1, 0, 0, 0, 1, 0, -pp_u, -pp_v, 1.0};
+    if (x[4] != 0) {
+        double s, c;
+        det_sincos(x[4], &s, &c);
+        H_roll[0] = c; H_roll[3] = -s;
+        H_roll[1] = s; H_roll[4] = c;
+    }
+    double sy, cy, sp, cp;
+    det_sincos(x[2], &sy, &cy);
+    det_sincos(x[3], &sp, &cp);
+    H_shift[6] = R2::add(R2::add(0.0, x[0]), R2::mul(R2::div(sy, cy), sdd));
+    H_shift[7] = R2::add(R2::add(0.0, x[1]), R2::mul(R2::div(sp, cp), sdd));
+    H_scale[0] = sdd_scale;  // block<2,2>(0,0) *= sdd_scale on the identity
+    H_scale[4] = sdd_scale;
+    mat3_mul(H_shift, Hpp, H);
+    mat3_mul(H, H_roll, H);
+    mat3_mul(H, H_scale, H);
+    mat3_mul(H, Hppinv, H);
+    for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    T[0] = sid_scale;
+    T[5] = sid_scale;
+    T[10] = sid_scale;
+}
+
+// Geometry::normalizeProjectionMatrix (LibProjectiveGeometry/ProjectionMatrix.cpp:12-18): P times -sign(det M) / |m3|... as
+// the reference writes it: norm_m3 negated when det M < 0, then P * (1 / norm_m3).
+__host__ __device__ inline void model_normalize(double* P)
+{
+    double norm_m3 = R2::root(R2::add(R2::add(R2::mul(P[2], P[2]), R2::mul(P[5], P[5])), R2::mul(P[8], P[8])));
+    const double det = det3d(P[0], P[3], P[6], P[1], P[4], P[7], P[2], P[5], P[8]);
+    if (det < 0) norm_m3 = -norm_m3;
+    const double f = R2::div(1.0, norm_m3);
+    for (int i = 0; i < 12; i++) P[i] = R2::mul(P[i], f);
+}
+
 }  // namespace eccb200

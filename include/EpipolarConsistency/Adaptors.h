@@ -18,8 +18,11 @@
 #define ECC_FACADE_ADAPTORS_H
 
 #include <cmath>
+#include <cstring>
 #include <set>
 #include <stdexcept>
+#include <utility>
+#include <string>
 #include <vector>
 
 #include "EpipolarConsistencyRadonIntermediate.h"
@@ -137,6 +140,130 @@ public:
         ModelCameraSimilarity2D3D tmp(P);
         tmp.current_values = x;
         return tmp.getInstance();
+    }
+};
+
+/// ONE geometric correction for a whole FDCT trajectory (Models/ModelFDCTCalibrationCorrection.hxx:15-206): detector shift
+/// u, v; yaw, pitch (detector shifts of tan(angle) sdd); roll and source-detector distance (rotation / scale about the mean
+/// principal point); source-isocentre distance (3D scale).  P' = H * H_init * P * T, normalised.  `param`, `active`,
+/// getTransforms() and transform() as in the reference (its Model<7> base keeps the parameter vector in `param`).
+struct ModelFDCTCalibrationCorrection {
+    double pp_u, pp_v, spacing, sid, sdd;
+    double param[7];
+    bool active[7];
+    std::vector<std::string> names;
+
+    static int size() { return 7; }
+    static std::vector<std::string> ParameterNames()
+    {
+        const char* n[7] = {"Translation u", "Translation v", "Yaw", "Pitch", "Roll", "Source Isocenter Distance", "Source Detector Distance"};
+        return std::vector<std::string>(n, n + 7);
+    }
+    enum ParameterSet { Identity, DetectorShifts, DetectorRigid2D, DetectorRotations, SDDandSID, All };
+
+    ModelFDCTCalibrationCorrection(int _nu, int _nv, double _spacing, double _sid, double _sdd, ParameterSet set = Identity)
+        : pp_u(0.5 * _nu), pp_v(0.5 * _nv), spacing(_spacing), sid(_sid), sdd(_sdd), names(ParameterNames())
+    {
+        for (int i = 0; i < 7; i++) param[i] = 0;
+        setActiveParameters(set);
+    }
+    /// Mean principal point, source-isocentre and source-detector distance from the trajectory (computeMeanPPandSIDandSDD,
+    /// :53-76; the focal lengths are |m1 x m3| and |m2 x m3| of the normalised matrix -- K(0,0), K(1,1) of the reference's RQ
+    /// decomposition for a skew-free detector).
+    ModelFDCTCalibrationCorrection(double _spacing, const std::vector<ProjectionMatrix>& Ps, ParameterSet set = Identity)
+        : pp_u(0), pp_v(0), spacing(_spacing), sid(0), sdd(0), names(ParameterNames())
+    {
+        for (int i = 0; i < 7; i++) param[i] = 0;
+        setActiveParameters(set);
+        computeMeanPPandSIDandSDD(Ps);
+    }
+    void computeMeanPPandSIDandSDD(const std::vector<ProjectionMatrix>& Ps)
+    {
+        double sum_sid = 0, sum_sdd = 0, sum_u = 0, sum_v = 0;
+        const int n = (int)Ps.size();
+        if (!n) return;
+        std::vector<double> flat(12 * (size_t)n);
+        std::vector<float> A(12 * (size_t)n), C(4 * (size_t)n);
+        for (int i = 0; i < n; i++) std::memcpy(&flat[12 * (size_t)i], Ps[i].data(), sizeof(double) * 12);
+        ecc_derive_views_host(flat.data(), n, A.data(), C.data());
+        for (int i = 0; i < n; i++) {
+            double P[12];
+            std::memcpy(P, &flat[12 * (size_t)i], sizeof(P));
+            ecc_model_normalize(P);
+            const double m1[3] = {P[0], P[3], P[6]}, m2[3] = {P[1], P[4], P[7]}, m3[3] = {P[2], P[5], P[8]};
+            const double c1[3] = {m1[1] * m3[2] - m1[2] * m3[1], m1[2] * m3[0] - m1[0] * m3[2], m1[0] * m3[1] - m1[1] * m3[0]};
+            const double c2[3] = {m2[1] * m3[2] - m2[2] * m3[1], m2[2] * m3[0] - m2[0] * m3[2], m2[0] * m3[1] - m2[1] * m3[0]};
+            sum_sdd += spacing * 0.5 * (std::sqrt(c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2]) + std::sqrt(c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2]));
+            const float* c = &C[4 * (size_t)i];
+            sum_sid += std::sqrt((double)c[0] * c[0] + (double)c[1] * c[1] + (double)c[2] * c[2]);
+            const double w = m3[0] * m3[0] + m3[1] * m3[1] + m3[2] * m3[2];  // pp = M m3^T, dehomogenised
+            sum_u += (m1[0] * m3[0] + m1[1] * m3[1] + m1[2] * m3[2]) / w;
+            sum_v += (m2[0] * m3[0] + m2[1] * m3[1] + m2[2] * m3[2]) / w;
+        }
+        sid = sum_sid / n;
+        sdd = sum_sdd / n;
+        pp_u = sum_u / n;
+        pp_v = sum_v / n;
+    }
+    /// Several common sets of active parameters (:110-133)
+    void setActiveParameters(ParameterSet set)
+    {
+        for (int i = 0; i < 7; i++) active[i] = (set == All);
+        switch (set) {
+            default:
+            case Identity:
+            case All: break;
+            case DetectorShifts: active[0] = active[1] = true; break;
+            case SDDandSID: active[5] = active[6] = true; break;
+            case DetectorRotations: active[2] = active[3] = active[4] = true; break;
+            case DetectorRigid2D: active[0] = active[1] = active[4] = true; break;
+        }
+    }
+    int numberOfParametersActive() const
+    {
+        int k = 0;
+        for (int i = 0; i < 7; i++) k += active[i] ? 1 : 0;
+        return k;
+    }
+    /// Writes x_active into the active entries of `param` (Model::expand).
+    void expand(const double* x_active)
+    {
+        for (int i = 0, a = 0; i < 7; i++)
+            if (active[i]) param[i] = x_active[a++];
+    }
+    /// The homographies H and T of the current parameter vector (:150-203).
+    std::pair<Homography2D, Homography3D> getTransforms() const
+    {
+        std::pair<Homography2D, Homography3D> HT;
+        const double geom[4] = {pp_u, pp_v, sid, sdd};
+        ecc_model_calibration_correction(geom, param, HT.first.m, HT.second.m);
+        return HT;
+    }
+    /// Ps[i] = normalise(H * H_init * Ps[i] * T) (:136-148)
+    void transform(std::vector<ProjectionMatrix>& Ps, const Homography2D& H_init = Homography2D()) const
+    {
+        double inst[25];
+        instance(H_init, inst);
+        Homography2D H;
+        Homography3D T;
+        std::memcpy(H.m, inst, sizeof(H.m));
+        std::memcpy(T.m, inst + 9, sizeof(T.m));
+        for (size_t i = 0; i < Ps.size(); i++) {
+            Ps[i] = transformProjection(H, Ps[i], T);
+            ecc_model_normalize(Ps[i].data());
+        }
+    }
+    /// H * H_init (9 doubles) followed by T (16 doubles): one instance of MetricRadonIntermediate::evaluateBatchTransforms.
+    void instance(const Homography2D& H_init, double* out25) const
+    {
+        const std::pair<Homography2D, Homography3D> HT = getTransforms();
+        for (int c = 0; c < 3; c++)
+            for (int r = 0; r < 3; r++) {
+                double acc = 0;
+                for (int k = 0; k < 3; k++) acc += HT.first(r, k) * H_init(k, c);
+                out25[r + 3 * c] = acc;
+            }
+        std::memcpy(out25 + 9, HT.second.m, sizeof(double) * 16);
     }
 };
 
@@ -445,6 +572,24 @@ public:
         return ecc->evaluateBatchParams(Ps, params, 1, map, &idx);
     }
 };
+
+/// What the B200 path adds for the calibration-correction loop (tools/FDCTCalibrationCorrection with
+/// Models/ModelFDCTCalibrationCorrection.hxx: one parameter vector corrects the WHOLE trajectory, every cost evaluation
+/// re-derives and uploads all n matrices): K candidate vectors of the model's ACTIVE parameters scored in ONE launch -- the
+/// host builds K pairs of homographies (25 doubles each), the device applies them to all views, normalises, derives and
+/// scores.  Returns the K means over all pairs.
+inline std::vector<double> evaluateCalibrationCandidates(MetricRadonIntermediate& ecc, const std::vector<ProjectionMatrix>& Ps,
+                                                         Geometry::ModelFDCTCalibrationCorrection model,
+                                                         const std::vector<std::vector<double> >& candidates,
+                                                         const Geometry::Homography2D& H_init = Geometry::Homography2D())
+{
+    std::vector<double> transforms(25 * candidates.size());
+    for (size_t k = 0; k < candidates.size(); k++) {
+        model.expand(candidates[k].data());
+        model.instance(H_init, &transforms[25 * k]);
+    }
+    return ecc.evaluateBatchTransforms(Ps, transforms, 1, true);
+}
 
 }  // namespace EpipolarConsistency
 

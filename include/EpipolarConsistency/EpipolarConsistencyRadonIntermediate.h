@@ -239,6 +239,24 @@ public:
         return means;
     }
 
+    /// NEW: the same with explicit homographies -- transforms holds K * m instances of 25 doubles (H 3x3 then T 4x4,
+    /// column-major), P' = H P T on the device, normalised when asked (ecc_evaluate_batch_transforms).  m == 1: one correction
+    /// for the whole trajectory (Geometry::ModelFDCTCalibrationCorrection); m == n: one per view.
+    std::vector<double> evaluateBatchTransforms(const std::vector<ProjectionMatrix>& base, const std::vector<double>& transforms, int m,
+                                                bool normalize = false, float* out = 0x0)
+    {
+        const int K = m > 0 ? (int)(transforms.size() / ((size_t)25 * m)) : 0;
+        std::vector<double> means(K, 0.0);
+        if (K == 0) return means;
+        pushSettings();
+        std::vector<double> flat(12 * base.size());
+        for (size_t i = 0; i < base.size(); i++) std::memcpy(&flat[12 * i], base[i].data(), sizeof(double) * 12);
+        chk(ecc_evaluate_batch_transforms(ctx, base.empty() ? 0x0 : flat.data(), transforms.data(), K, m, 0x0, normalize ? 1 : 0, 0x0, 0, out,
+                                          means.data()),
+            "ecc_evaluate_batch_transforms");
+        return means;
+    }
+
     /// Visualisation helper of the reference (EpipolarConsistencyRadonIntermediate.cpp:324-393): that code samples on
     /// the CPU with its own texel mapping.  Here: the pair's metric value from the GPU path; sample vectors are not filled.
     /// The two redundant signals of pair (i, j) for plotting, in ascending kappa (EpipolarConsistencyRadonIntermediate.cpp

@@ -253,6 +253,24 @@ int ecc_evaluate_batch_params(ecc_context* ctx, const double* base_Ps, const dou
 int ecc_model_expand(ecc_context* ctx, const double* base_Ps, const double* params, int n_sets, int m,
                      const int* view_to_param, double* Ps_out);
 
+/* The same with EXPLICIT homographies: an instance is H (3x3) followed by T (4x4), 25 doubles, column-major; P' = H P T,
+ * divided by -sign(det M) |m3| when `normalize` is set (Geometry::normalizeProjectionMatrix, ProjectionMatrix.cpp:12-18).
+ * view_to_transform NULL: m == n (one instance per view) or m == 1 (ONE correction for the whole trajectory -- the
+ * calibration-correction loop: ModelFDCTCalibrationCorrection::transform, Models/ModelFDCTCalibrationCorrection.hxx:136-148;
+ * also one rigid transform for all views, tools/Registration/Registration3D3D.hxx).  transforms [h|d]: n_sets * m * 25. */
+int ecc_evaluate_batch_transforms(ecc_context* ctx, const double* base_Ps, const double* transforms, int n_sets, int m,
+                                  const int* view_to_transform, int normalize, const int* idx4, int n_pairs, float* out,
+                                  double* means);
+int ecc_transform_expand(ecc_context* ctx, const double* base_Ps, const double* transforms, int n_sets, int m,
+                         const int* view_to_transform, int normalize, double* Ps_out);
+/* ModelFDCTCalibrationCorrection::getTransforms (Models/ModelFDCTCalibrationCorrection.hxx:150-203): geom4 = the model's mean
+ * principal point u, v, source-isocentre and source-detector distance; x7 = translation u, v, yaw, pitch, roll, delta SID,
+ * delta SDD.  H 3x3, T 4x4, column-major.  Host function; the fp64 operation sequence is the library's own (shared with
+ * nothing on the device: the homographies are inputs of ecc_evaluate_batch_transforms). */
+void ecc_model_calibration_correction(const double* geom4, const double* x7, double* H, double* T);
+/* Geometry::normalizeProjectionMatrix on the host, with the device path's bits. */
+void ecc_model_normalize(double* P);
+
 /* evaluateForImagePair (EpipolarConsistencyRadonIntermediate.cpp:324-393, "visualization only"): the two redundant
  * signals of ONE pair, sampled on the device with the metric's own lookup (the reference walks them on the CPU with
  * RadonIntermediate::sample, whose texel mapping differs slightly from the metric's).  Entries are in

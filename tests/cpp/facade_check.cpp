@@ -328,6 +328,40 @@ static int run_gpu(const char* tmpdir)
         std::printf("fdctview %.12g %.12g %.12g %.12g\n", by_params[0], by_params[1], by_mats[0], by_mats[1]);
         if (std::fabs(by_params[0] - by_mats[0]) > 1e-12 * by_mats[0] || std::fabs(by_params[1] - by_mats[1]) > 1e-12 * by_mats[1]) return fail("FDCTMoCo::evaluateViewCandidates vs evaluateCandidates");
     }
+    {   // ModelFDCTCalibrationCorrection (Models/ModelFDCTCalibrationCorrection.hxx): one correction for the whole trajectory;
+        // K candidates expanded on the device in one launch = the host model's transform() + one evaluation per candidate
+        Geometry::ModelFDCTCalibrationCorrection calib(2.0, Ps, Geometry::ModelFDCTCalibrationCorrection::All);
+        if (std::fabs(calib.pp_u - 0.5 * n_u) > 1e-6 || std::fabs(calib.pp_v - 0.5 * n_v) > 1e-6) return fail("calibration model: mean principal point");
+        double f_px = 0, u0 = 0, v0 = 0;  // makeCircularTrajectory's focal length is n_v / (2 tan(atan(n_v px / sdd) / 2)), not sdd / px
+        ecc_camera_intrinsics(Ps[0].data(), &f_px, &u0, &v0);
+        if (std::fabs(calib.sid - 750.0) > 1e-3 || std::fabs(calib.sdd - 2.0 * f_px) > 1e-6 * calib.sdd) return fail("calibration model: mean SID / SDD");
+        if (calib.numberOfParametersActive() != 7 || calib.ParameterNames()[6] != "Source Detector Distance") return fail("calibration model: parameters");
+        std::vector<std::vector<double> > cc(4, std::vector<double>(7, 0.0));
+        cc[1][0] = 1.5;                       // detector shift u
+        cc[2][4] = 0.01; cc[2][6] = 12.0;     // roll and SDD
+        cc[3][2] = 0.002; cc[3][5] = -8.0;    // yaw and SID
+        MetricRadonIntermediate ecc(Ps, dtrs);
+        ecc.setObjectRadius(0).setEpipolarPlaneStep(0);
+        const std::vector<double> batch = evaluateCalibrationCandidates(ecc, Ps, calib, cc);
+        double one_by_one[4];
+        for (int k = 0; k < 4; k++) {
+            std::vector<ProjectionMatrix> moved = Ps;
+            calib.expand(cc[k].data());
+            calib.transform(moved);
+            ecc.setProjectionMatrices(moved);
+            one_by_one[k] = ecc.evaluate();
+        }
+        std::printf("calib %.12g %.12g %.12g %.12g %.12g %.12g %.12g %.12g\n", batch[0], batch[1], batch[2], batch[3], one_by_one[0], one_by_one[1],
+                    one_by_one[2], one_by_one[3]);
+        for (int k = 0; k < 4; k++)
+            if (std::fabs(batch[k] - one_by_one[k]) > 1e-12 * std::fabs(one_by_one[k])) return fail("calibration candidates: device-expanded vs host transform(), one by one");
+        // detector shift and yaw move the image content: they must score worse.  (Roll + SDD, candidate 2, need not: on this coarse
+        // scene a one per cent magnification lowers the interpolation residuals the consistent geometry is left with.)
+        if (!(batch[1] > batch[0] && batch[3] > batch[0])) return fail("calibration candidates: a shifted detector must score worse");
+        // a detector-shift-only parameter set: two active parameters
+        Geometry::ModelFDCTCalibrationCorrection shifts(n_u, n_v, 2.0, 750.0, 1200.0, Geometry::ModelFDCTCalibrationCorrection::DetectorShifts);
+        if (shifts.numberOfParametersActive() != 2 || !shifts.active[0] || !shifts.active[1] || shifts.active[4]) return fail("calibration model: DetectorShifts");
+    }
     {   // PreProccess facade: defaults clear the border and feather 16 px; cosine weight 1 at the principal point
         NRRD::Image<float> im(n_u, n_v);
         for (int i = 0; i < im.length(); i++) ((float*)im)[i] = 5.f;

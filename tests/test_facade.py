@@ -105,7 +105,7 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
             pairs[(int(t[1]), int(t[2]))] = float(t[3])
         elif t[0] in ("radius", "mean", "subset", "fixed"):
             vals[t[0]] = float(t[1])
-        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre", "signals", "fdct", "fdctview", "direct"):
+        elif t[0] in ("list", "batch", "model", "sim", "reg", "reg33", "pre", "signals", "fdct", "fdctview", "direct", "calib"):
             vals[t[0]] = [float(x) for x in t[1:]]
         elif t[0] == "l2s":
             vals.setdefault("l2s", []).append([float(x) for x in t[1:]])
@@ -207,3 +207,23 @@ def test_facade_gpu_matches_python_mirror(tmp_path):
     ctx.direct_set_fan_beam(True)
     assert same(fb, ctx.direct_evaluate_pair(1, 3)["value"]) and free_fb == fb
     ctx.direct_set_fan_beam(False)
+    # calibration-correction candidates (ModelFDCTCalibrationCorrection): the facade's batch = the Python mirror's batch of the
+    # same homographies, and its first candidate (all parameters zero) is the unperturbed mean
+    ctx.set_projection_matrices(Ps)
+    geom = [0.5 * n_u, 0.5 * n_v, 750.0, 2.0 * api.camera_intrinsics(Ps[0])[0]]  # the trajectory's own focal length
+    xs = np.zeros((4, 7))
+    xs[1, 0] = 1.5
+    xs[2, 4], xs[2, 6] = 0.01, 12.0
+    xs[3, 2], xs[3, 5] = 0.002, -8.0
+    T = np.stack([api.model_calibration_correction(geom, x) for x in xs]).reshape(4, 1, 25)
+    want = ctx.evaluate_batch_transforms(Ps, T, normalize=True)
+    for k in range(4):
+        assert abs(vals["calib"][k] - want[k]) <= 1e-6 * want[k]  # the facade estimates pp / SID / SDD from the matrices
+    assert abs(vals["calib"][0] - all0) <= 1e-5 * all0  # identity correction, matrices re-normalised
+    moved = ctx.transform_expand(Ps, T, normalize=True)
+    for k in range(4):
+        H, T3 = T[k, 0, :9].reshape(3, 3).T, T[k, 0, 9:].reshape(4, 4).T
+        for v in range(n):
+            Pm = H @ Ps[v].reshape(4, 3).T @ T3
+            Pm = Pm / (np.linalg.norm(Pm[2, :3]) * np.sign(np.linalg.det(Pm[:, :3])))
+            assert np.allclose(moved[k, v].reshape(4, 3).T, Pm, rtol=1e-12, atol=1e-9)

@@ -1130,6 +1130,56 @@ def test_batch_params_equals_batch_of_host_expanded_matrices(ctx, scene):
         ctx.evaluate_batch_params(scene["Ps"], x[:, :3, :])  # three instances for ten views and no map
 
 
+def test_batch_transforms_calibration_correction(ctx, scene):
+    """ecc_evaluate_batch_transforms / ecc_transform_expand: explicit homographies, P' = H P T normalised on the device.
+    One correction for the whole trajectory (ModelFDCTCalibrationCorrection, m = 1, no map): the expanded matrices are bit
+    for bit the host's (ecc_model_transform + ecc_model_normalize), the scores those of ecc_evaluate_batch fed with them,
+    per pair; the identity correction reproduces the plain evaluation; a mis-calibrated trajectory scores worse."""
+    setup_metric(ctx, scene, scene["dtr_exact"], api.INTERP_EXACT)
+    n, n_u, n_v = scene["n"], scene["n_u"], scene["n_v"]
+    geom = [0.5 * n_u, 0.5 * n_v, 750.0, 1200.0]
+    xs = np.zeros((5, 7))
+    xs[1, 0:2] = [1.5, -0.8]
+    xs[2, 2:5] = [0.002, -0.001, 0.01]
+    xs[3, 5:7] = [-8.0, 12.0]
+    xs[4] = [0.7, 0.3, -0.001, 0.002, -0.004, 5.0, -6.0]
+    T = np.stack([api.model_calibration_correction(geom, x) for x in xs]).reshape(5, 1, 25)
+    moved = ctx.transform_expand(scene["Ps"], T, normalize=True)
+    lib = api._lib.load()
+    for k in range(5):
+        for v in range(n):
+            want = np.zeros(12)
+            lib.ecc_model_transform(T[k, 0, :9].ctypes.data, scene["Ps"][v].ctypes.data, T[k, 0, 9:].ctypes.data, want.ctypes.data)
+            assert np.array_equal(moved[k, v], api.model_normalize(want)), (k, v)
+    pairs = n * (n - 1) // 2
+    a, b = np.zeros((5, pairs), np.float32), np.zeros((5, pairs), np.float32)
+    ma = ctx.evaluate_batch(moved, None, a)
+    mb = ctx.evaluate_batch_transforms(scene["Ps"], T, normalize=True, out=b)
+    assert np.array_equal(a, b) and np.array_equal(ma, mb)
+    plain = ctx.evaluate(None)
+    # detector shifts and rotations must score worse; the SID / SDD candidate (3) need not -- a common 3-D scale of the whole
+    # trajectory leaves the epipolar geometry as it is and a one per cent magnification is below this coarse scene's resolution
+    assert abs(mb[0] - plain) <= 1e-5 * plain and min(mb[1], mb[2], mb[4]) > 2 * mb[0]
+    # one instance per view (m == n) and a view map (instance 0 moves views 1 and 4 only), not normalised
+    Tn = np.repeat(T[1:3], n, axis=1)
+    mv = ctx.transform_expand(scene["Ps"], Tn)
+    assert np.array_equal(mv[0, 3], np.asarray(_transform(lib, T[1, 0], scene["Ps"][3])))
+    vmap = np.full(n, -1, np.int32)
+    vmap[[1, 4]] = 0
+    mm = ctx.transform_expand(scene["Ps"], T[1:2], vmap)
+    for v in range(n):
+        w = _transform(lib, T[1, 0], scene["Ps"][v]) if v in (1, 4) else scene["Ps"][v]
+        assert np.array_equal(mm[0, v], w)
+    with pytest.raises(api.EccError):
+        ctx.evaluate_batch_transforms(scene["Ps"], np.repeat(T, 3, axis=1))  # three instances for ten views and no map
+
+
+def _transform(lib, inst25, P):
+    out = np.zeros(12)
+    lib.ecc_model_transform(inst25[:9].ctypes.data, np.ascontiguousarray(P).ctypes.data, inst25[9:].ctypes.data, out.ctypes.data)
+    return out
+
+
 def test_static_split_calibration_and_pinning(ctx):
     """Robustness of the tuned constant (round-1 verdict): the share of the samples the window path takes in
     ECC_INTERP_HYBRID_STATIC is 580 / 605 per mille, measured on B200.  ecc_radon_calibrate_split measures the balance of

@@ -163,3 +163,35 @@ def test_team_radon_shard_tiles_the_quads():
             assert pos == world * Q or Q == 0
     assert shard(496, 8, 0) == [0, 64, 0, 4, 8] and shard(496, 8, 1) == [60, 64, 4, 8, 8]
     assert lib.ecc_team_radon_shard(8, 0, 0, None, None, None, None, None) != 0
+
+
+def test_calibration_correction_model_matches_the_reference_formulas():
+    """ModelFDCTCalibrationCorrection::getTransforms (Models/ModelFDCTCalibrationCorrection.hxx:150-203) restated with numpy:
+    H = H_shift Hpp H_roll H_scale Hppinv, T = diag(s, s, s, 1); the identity for zero parameters; normalisation as
+    Geometry::normalizeProjectionMatrix (ProjectionMatrix.cpp:12-18)."""
+    from epipolarconsistency_b200 import api
+    rng = np.random.default_rng(3)
+    geom = [317.3, 244.9, 748.0, 1203.5]
+    o = api.model_calibration_correction(geom, np.zeros(7))
+    assert np.array_equal(o[:9].reshape(3, 3).T, np.eye(3)) and np.array_equal(o[9:].reshape(4, 4).T, np.eye(4))
+    for _ in range(20):
+        x = rng.standard_normal(7) * np.array([3, 3, 0.01, 0.01, 0.05, 20, 20])
+        o = api.model_calibration_correction(geom, x)
+        H, T = o[:9].reshape(3, 3).T, o[9:].reshape(4, 4).T
+        I = np.eye(3)
+        Hpp, Hppinv, Hs, Hsc = I.copy(), I.copy(), I.copy(), I.copy()
+        Hpp[:, 2] = [geom[0], geom[1], 1.0]
+        Hppinv[0, 2], Hppinv[1, 2] = -geom[0], -geom[1]
+        Hr = np.array([[np.cos(x[4]), -np.sin(x[4]), 0], [np.sin(x[4]), np.cos(x[4]), 0], [0, 0, 1]])
+        Hs[0, 2] += x[0] + np.tan(x[2]) * geom[3]
+        Hs[1, 2] += x[1] + np.tan(x[3]) * geom[3]
+        Hsc[:2, :2] *= (geom[3] + x[6]) / geom[3]
+        want = Hs @ Hpp @ Hr @ Hsc @ Hppinv
+        assert np.allclose(H, want, rtol=1e-13, atol=1e-10)
+        Tw = np.eye(4)
+        Tw[:3, :3] *= (geom[2] + x[5]) / geom[2]
+        assert np.array_equal(T, Tw)
+    P = api.make_circular_trajectory(5, 750.0, 1200.0, 640, 480, 200.0, 0.5)[3]
+    for f in (1.0, -3.7, 1e-3):
+        M = api.model_normalize(f * P).reshape(4, 3).T
+        assert abs(np.linalg.norm(M[2, :3]) - 1) < 1e-14 and np.linalg.det(M[:, :3]) > 0
