@@ -67,6 +67,8 @@ SIGNATURES = {
     "ecc_direct_set_fan_beam": (C.c_int, [c_ctx, C.c_int]),
     "ecc_direct_set_reference_clip": (C.c_int, [c_ctx, C.c_int]),
     "ecc_direct_evaluate": (C.c_int, [c_ctx, c_vp, C.POINTER(C.c_double)]),
+    "ecc_direct_evaluate_range": (C.c_int, [c_ctx, C.c_longlong, C.c_longlong, c_vp, C.POINTER(C.c_double)]),
+    "ecc_direct_partition": (C.c_int, [c_ctx, C.c_int, c_vp]),
     "ecc_direct_evaluate_pair": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, C.POINTER(C.c_int),
                                           C.POINTER(C.c_double)]),
     "ecc_direct_pair_geometry": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(C.c_int),

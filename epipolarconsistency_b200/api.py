@@ -339,6 +339,18 @@ class Context:
         self._check(self.lib.ecc_direct_evaluate(self.h, _ptr(cost_image, _F32), C.byref(total)))
         return total.value
 
+    def direct_evaluate_range(self, begin, end, cost_image=None):
+        """Pairs [begin, end) of the enumeration i < j (i outer): their sum; the unit of multi-GPU sharding."""
+        total = C.c_double()
+        self._check(self.lib.ecc_direct_evaluate_range(self.h, int(begin), int(end), _ptr(cost_image, _F32), C.byref(total)))
+        return total.value
+
+    def direct_partition(self, n_parts):
+        """Bounds of n_parts contiguous pair ranges of equal work (epipolar planes)."""
+        bounds = np.zeros(n_parts + 1, np.int64)
+        self._check(self.lib.ecc_direct_partition(self.h, int(n_parts), _ptr(bounds, _I64)))
+        return bounds
+
     def direct_evaluate_pair(self, i, j, kappas=None):
         """computeForImagePair: dict(value, kappas, samples0, samples1); kappas given = the caller's plane angles."""
         n, v = C.c_int(), C.c_double()

@@ -30,6 +30,7 @@ namespace {
 
 constexpr float kDirectStep = 0.4f;   // EpipolarConsistencyDirect.cu:73
 constexpr int kLinesPerCta = 32;
+constexpr int kMaxPlanesPerPair = 1 << 22;  // 2 x the image diagonal is the automatic count; a plane step of 1e-6 rad stays below this
 
 // ---- the line integral ----------------------------------------------------------------------------------------------
 // line l (Hessian normal form, fp32) through an n_u x n_v image; n_v_clip = the height the clipping uses (the reference's
@@ -156,7 +157,7 @@ __global__ void direct_views_kernel(const double* __restrict__ Ps, int n, Direct
 // pair p of the enumeration i < j, i outer (MetricDirect::evaluate, EpipolarConsistencyDirect.cpp:236-247), or a listed pair
 __global__ void direct_pairs_kernel(const DirectView* __restrict__ views, int n, const int* __restrict__ pair_ij, int n_pairs, double radius,
                                     double dkappa, int n_u, int n_v, int fbcc, int n_given, DirectPair* __restrict__ pairs,
-                                    int* __restrict__ chunks)
+                                    int* __restrict__ chunks, int* __restrict__ status)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
@@ -167,14 +168,18 @@ __global__ void direct_pairs_kernel(const DirectView* __restrict__ views, int n,
     R.j = j;
     if (n_given > 0) R.n_lines = n_given;  // the caller's kappas (computeForImagePair with a filled `kappas`)
     if (R.n_lines < 0) R.n_lines = 0;
+    if (R.n_lines > kMaxPlanesPerPair) {  // refused by the host (status word), never launched
+        atomicMax(status, 1);
+        R.n_lines = 0;
+    }
     pairs[p] = R;
     chunks[p] = (R.n_lines + kLinesPerCta - 1) / kLinesPerCta;
 }
 
 // exclusive prefix sum of chunks[0..n) into offsets[0..n], one CTA
-__global__ void direct_scan_kernel(const int* __restrict__ chunks, int n, int* __restrict__ offsets)
+__global__ void direct_scan_kernel(const int* __restrict__ chunks, int n, int* __restrict__ offsets, int* __restrict__ status)
 {
-    __shared__ int carry_s;
+    __shared__ long long carry_s;
     __shared__ int warp_sums[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
@@ -198,13 +203,16 @@ __global__ void direct_scan_kernel(const int* __restrict__ chunks, int n, int* _
             warp_sums[lane] = w;
         }
         __syncthreads();
-        const int before = carry_s + (warp ? warp_sums[warp - 1] : 0) + s - v;
-        if (k < n) offsets[k] = before;
+        const long long before = carry_s + (warp ? warp_sums[warp - 1] : 0) + s - v;
+        if (k < n) offsets[k] = (int)before;
         __syncthreads();
         if (tid == blockDim.x - 1) carry_s = before + v;
         __syncthreads();
     }
-    if (tid == 0) offsets[n] = carry_s;
+    if (tid == 0) {
+        if (carry_s > 2147483647ll) atomicMax(status, 2);  // more CTAs than a grid can have
+        offsets[n] = carry_s > 2147483647ll ? 0 : (int)carry_s;
+    }
 }
 
 struct DirectLaunch {
@@ -351,22 +359,30 @@ int direct_prepare(ecc_context* ctx, const int* pair_ij_h, int n_pairs, int n_gi
     if (rc) return rc;
     rc = ensure_bytes(ctx, (void**)&D.ij_d, &D.ij_bytes, sizeof(int) * 2 * n_pairs);
     if (rc) return rc;
-    rc = ensure_bytes(ctx, (void**)&D.offsets_d, &D.offsets_bytes, sizeof(int) * (2 * (size_t)n_pairs + 2));
+    rc = ensure_bytes(ctx, (void**)&D.offsets_d, &D.offsets_bytes, sizeof(int) * (2 * (size_t)n_pairs + 3));
     if (rc) return rc;
     rc = ensure_bytes(ctx, (void**)&D.vals_d, &D.vals_bytes, sizeof(double) * ((size_t)n_pairs + 1));
     if (rc) return rc;
-    int* chunks_d = D.offsets_d + n_pairs + 1;
+    // layout: [n_pairs] offsets, total, status word, [n_pairs] CTAs per pair
+    int* status_d = D.offsets_d + n_pairs + 1;
+    int* chunks_d = D.offsets_d + n_pairs + 2;
+    ECC_CUDA(ctx, cudaMemsetAsync(status_d, 0, sizeof(int), ctx->stream));
     ECC_CUDA(ctx, cudaMemcpyAsync(D.Ps_d, ctx->Ps_h.data(), sizeof(double) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
     ECC_CUDA(ctx, cudaMemcpyAsync(D.ij_d, pair_ij_h, sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     const int s = prof_begin(ctx, FAM_GEOMETRY);
     direct_views_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(D.Ps_d, n, (DirectView*)D.views_d);
     direct_pairs_kernel<<<(n_pairs + 63) / 64, 64, 0, ctx->stream>>>((const DirectView*)D.views_d, n, D.ij_d, n_pairs, radius, ctx->dkappa, D.n_u,
-                                                                    D.n_v, D.fbcc, n_given, (DirectPair*)D.pairs_d, chunks_d);
-    direct_scan_kernel<<<1, 1024, 0, ctx->stream>>>(chunks_d, n_pairs, D.offsets_d);
+                                                                    D.n_v, D.fbcc, n_given, (DirectPair*)D.pairs_d, chunks_d, status_d);
+    direct_scan_kernel<<<1, 1024, 0, ctx->stream>>>(chunks_d, n_pairs, D.offsets_d, status_d);
     prof_end(ctx, s);
     ECC_CUDA(ctx, cudaGetLastError());
-    ECC_CUDA(ctx, cudaMemcpyAsync(total_ctas, D.offsets_d + n_pairs, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    int total_and_status[2] = {0, 0};
+    ECC_CUDA(ctx, cudaMemcpyAsync(total_and_status, D.offsets_d + n_pairs, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pair_ij_h and the CTA count
+    *total_ctas = total_and_status[0];
+    if (total_and_status[1] == 1)
+        return fail(ctx, ECC_ERR_UNSUPPORTED, "direct metric: the epipolar plane step gives a pair more than 4194304 planes");
+    if (total_and_status[1] == 2) return fail(ctx, ECC_ERR_UNSUPPORTED, "direct metric: more than 2^31 CTAs in one evaluation (plane step too fine for this many pairs)");
     return ECC_OK;
 }
 
@@ -503,29 +519,48 @@ int ecc_direct_set_reference_clip(ecc_context* ctx, int on)
     return ECC_OK;
 }
 
-int ecc_direct_evaluate(ecc_context* ctx, float* cost_image, double* sum)
+// pairs [begin, end) of the enumeration i < j, i outer (MetricDirect::evaluate's loop order): 2 ints per pair
+static const int* direct_pair_list(ecc_context* ctx, int n)
+{
+    DirectState& D = ctx->direct;
+    const size_t n_pairs = (size_t)n * (n - 1) / 2;
+    if (D.all_pairs_h.size() != 2 * n_pairs || D.all_pairs_n != n) {
+        D.all_pairs_h.resize(2 * n_pairs);
+        size_t k = 0;
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++) { D.all_pairs_h[k++] = i; D.all_pairs_h[k++] = j; }
+        D.all_pairs_n = n;
+    }
+    return D.all_pairs_h.data();
+}
+
+static int direct_check_state(ecc_context* ctx, const char* who, long long* n_pairs)
+{
+    DirectState& D = ctx->direct;
+    const int n = ctx->n_views;
+    if (n <= 0) return fail(ctx, ECC_ERR_STATE, std::string(who) + ": projection matrices not set");
+    if (D.n_images != n) return fail(ctx, ECC_ERR_STATE, std::string(who) + ": number of images and of projection matrices differ");
+    *n_pairs = (long long)n * (n - 1) / 2;
+    if (*n_pairs > (1ll << 28)) return fail(ctx, ECC_ERR_UNSUPPORTED, std::string(who) + ": too many pairs");
+    return ECC_OK;
+}
+
+int ecc_direct_evaluate_range(ecc_context* ctx, long long pair_begin, long long pair_end, float* cost_image, double* sum)
 {
     if (!ctx) return ECC_ERR_INVALID;
     Guard g(ctx);
     DirectState& D = ctx->direct;
-    const int n = ctx->n_views;
-    if (n <= 0) return fail(ctx, ECC_ERR_STATE, "ecc_direct_evaluate: projection matrices not set");
-    if (D.n_images != n) return fail(ctx, ECC_ERR_STATE, "ecc_direct_evaluate: number of images and of projection matrices differ");
-    const long long n_pairs_ll = (long long)n * (n - 1) / 2;
-    if (n_pairs_ll == 0) {
+    long long all = 0;
+    int rc = direct_check_state(ctx, "ecc_direct_evaluate_range", &all);
+    if (rc) return rc;
+    if (pair_begin < 0 || pair_end < pair_begin || pair_end > all) return fail(ctx, ECC_ERR_INVALID, "ecc_direct_evaluate_range: bad pair range");
+    const int n = ctx->n_views, n_pairs = (int)(pair_end - pair_begin);
+    if (n_pairs == 0) {
         if (sum) *sum = 0.0;
         return ECC_OK;
     }
-    if (n_pairs_ll > (1ll << 28)) return fail(ctx, ECC_ERR_UNSUPPORTED, "ecc_direct_evaluate: too many pairs");
-    const int n_pairs = (int)n_pairs_ll;
-    if ((int)D.all_pairs_h.size() != 2 * n_pairs) {
-        D.all_pairs_h.resize(2 * (size_t)n_pairs);
-        size_t k = 0;
-        for (int i = 0; i < n; i++)
-            for (int j = i + 1; j < n; j++) { D.all_pairs_h[k++] = i; D.all_pairs_h[k++] = j; }
-    }
     int total_ctas = 0;
-    int rc = direct_prepare(ctx, D.all_pairs_h.data(), n_pairs, 0, &total_ctas);
+    rc = direct_prepare(ctx, direct_pair_list(ctx, n) + 2 * pair_begin, n_pairs, 0, &total_ctas);
     if (rc) return rc;
     float* image_d = nullptr;
     const bool image_on_host = cost_image && !is_device_pointer(cost_image);
@@ -546,6 +581,43 @@ int ecc_direct_evaluate(ecc_context* ctx, float* cost_image, double* sum)
     if (image_on_host) ECC_CUDA(ctx, cudaMemcpyAsync(cost_image, image_d, sizeof(float) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream));
     ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (sum) *sum = total;
+    return ECC_OK;
+}
+
+int ecc_direct_evaluate(ecc_context* ctx, float* cost_image, double* sum)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    long long all = 0;
+    const int rc = direct_check_state(ctx, "ecc_direct_evaluate", &all);
+    if (rc) return rc;
+    return ecc_direct_evaluate_range(ctx, 0, all, cost_image, sum);
+}
+
+int ecc_direct_partition(ecc_context* ctx, int n_parts, long long* bounds)
+{
+    if (!ctx || !bounds || n_parts < 1) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    DirectState& D = ctx->direct;
+    long long all = 0;
+    int rc = direct_check_state(ctx, "ecc_direct_partition", &all);
+    if (rc) return rc;
+    bounds[0] = 0;
+    for (int k = 1; k <= n_parts; k++) bounds[k] = all;
+    if (all == 0) return ECC_OK;
+    int total_ctas = 0;
+    rc = direct_prepare(ctx, direct_pair_list(ctx, ctx->n_views), (int)all, 0, &total_ctas);
+    if (rc) return rc;
+    // the CTA offset table IS the work prefix (a CTA = 32 planes through both images): cut it into equal parts
+    std::vector<int> offsets((size_t)all + 1);
+    ECC_CUDA(ctx, cudaMemcpyAsync(offsets.data(), D.offsets_d, sizeof(int) * ((size_t)all + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    long long p = 0;
+    for (int k = 1; k < n_parts; k++) {
+        const double target = (double)total_ctas * k / n_parts;
+        while (p < all && (double)offsets[p + 1] <= target) p++;
+        if (p < all && target - offsets[p] > offsets[p + 1] - target) p++;  // the nearer pair boundary
+        bounds[k] = p;
+    }
     return ECC_OK;
 }
 

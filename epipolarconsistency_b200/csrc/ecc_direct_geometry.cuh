@@ -172,7 +172,8 @@ __host__ __device__ inline void direct_pair(const DirectView& V0, const DirectVi
     }
     R.kappa0 = lo;
     R.dkappa = dkappa;
-    R.n_lines = (int)((hi - lo) / dkappa);
+    const double planes = (hi - lo) / dkappa;
+    R.n_lines = planes < 2147483647.0 ? (int)planes : 2147483647;  // callers refuse absurd counts (kMaxPlanesPerPair)
     for (int k = 0; k < 3; k++) R.dir[k] = dir[k];
     for (int k = 0; k < 9; k++) R.H0[k] = R.H1[k] = 0;
     for (int k = 0; k < 4; k++) R.E[k] = 0;

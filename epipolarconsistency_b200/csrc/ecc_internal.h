@@ -149,7 +149,8 @@ struct DirectState {
     size_t partials_bytes = 0;
     float* scratch_d = nullptr;
     size_t scratch_bytes = 0;
-    std::vector<int> all_pairs_h;
+    std::vector<int> all_pairs_h;  // (i, j) of the enumeration i < j, i outer, for all_pairs_n views
+    int all_pairs_n = 0;
 };
 
 }  // namespace eccb200

@@ -144,6 +144,26 @@ class ShardedPipeline:
             s = float(acc.item())
         return s / total if total else 0.0
 
+    # -- direct metric (MetricDirect): pairs are independent, no exchange but the final sum ---------------------------------
+    def direct_evaluate(self, n_views, cost_image=None):
+        """MetricDirect::evaluate over the GPUs of the node: every rank holds the images and matrices (direct_set_images,
+        set_projection_matrices), the pair enumeration is cut into `world` ranges of equal work (epipolar planes,
+        ecc_direct_partition), each rank scores its range; one all-reduce of the fp64 sum (and of the cost image, whose
+        entries are disjoint and must be zero on entry) is the only collective.  Returns the SUM over all pairs."""
+        total = n_views * (n_views - 1) // 2
+        bounds = self.c.direct_partition(self.world) if self.world > 1 else np.array([0, total])
+        lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
+        s = self.c.direct_evaluate_range(lo, hi, cost_image)
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            acc = torch.tensor([s], dtype=torch.float64, device=self.device)
+            dist.all_reduce(acc, group=self.group)
+            if cost_image is not None:
+                dist.all_reduce(cost_image, group=self.group)
+            s = float(acc.item())
+        return s
+
     # -- batched mode (BASELINE config C4): K matrix sets against the same dtrs ----------------------------------------
     def evaluate_batch(self, Ps_sets, idx4=None):
         """Scores K complete projection-matrix sets (K, n, 12) against the dtrs every rank already holds: the sets are

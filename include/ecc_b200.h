@@ -321,6 +321,12 @@ int ecc_direct_set_reference_clip(ecc_context* ctx, int on);
  * entry i + j*n receives the pair's value, other entries keep the caller's.  sum: the SUM over the pairs (the direct
  * metric returns the sum, not the mean). */
 int ecc_direct_evaluate(ecc_context* ctx, float* cost_image, double* sum);
+/* The same restricted to pairs [pair_begin, pair_end) of that enumeration (i < j, i outer): the unit of multi-GPU sharding --
+ * pairs are independent, every GPU holds the images and matrices, the only exchange is the final sum.  sum = over those pairs. */
+int ecc_direct_evaluate_range(ecc_context* ctx, long long pair_begin, long long pair_end, float* cost_image, double* sum);
+/* Cuts the enumeration into n_parts contiguous ranges of (nearly) equal work = epipolar planes (the range of kappa, and with
+ * a fixed plane step the number of planes, differs from pair to pair); bounds: n_parts + 1 entries, host. */
+int ecc_direct_partition(ecc_context* ctx, int n_parts, long long* bounds);
 /* MetricDirect::evaluateForImagePair / computeForImagePair (.cpp:64-212, 249-258): one pair and its redundant signals.
  * kappas / samples0 / samples1: host arrays of `capacity` floats, each nullable.  n_given > 0: the first n_given entries of
  * kappas are the caller's epipolar plane angles (the reference's "unless provided"), else they receive the angles used.

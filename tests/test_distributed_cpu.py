@@ -32,6 +32,13 @@ class StubCompute:
     def evaluate_batch_params(self, base_Ps, params, view_to_param=None, idx4=None):
         return np.array([float(x[0, 0]) * 3.0 - 1.0 for x in params], np.float64)  # a set's "mean" = a function of its parameters
 
+    def direct_partition(self, n_parts):
+        total = self.n * (self.n - 1) // 2
+        return np.array(shard_bounds(total, n_parts), np.int64)
+
+    def direct_evaluate_range(self, lo, hi, cost_image=None):
+        return 0.5 * self.evaluate_range(lo, hi, cost_image)  # the "direct" value of a pair = half its intermediate value
+
     def evaluate_range(self, lo, hi, cost_image=None, want_sum=True):
         pairs = [(i, j) for i in range(self.n) for j in range(i + 1, self.n)][lo:hi]
         s = 0.0
@@ -120,7 +127,7 @@ def _worker(rank, world, port, n_total, results, mode="nccl"):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        if mode in ("nccl", "batch"):
+        if mode in ("nccl", "batch", "direct"):
             compute, transport = StubCompute(n_total, world), "nccl"
         else:
             compute, transport = StubTeam(n_total, world, rank, fail_create=(mode == "team-fails" and rank == 1)), "team"
@@ -142,6 +149,9 @@ def _worker(rank, world, port, n_total, results, mode="nccl"):
             extra = pipe.evaluate_batch(sets).tolist()
             params = np.arange(7 * n_total * 11, dtype=np.float64).reshape(7, n_total, 11)  # the same with parameter vectors
             extra = (extra, pipe.evaluate_batch_params(None, params).tolist())
+        elif mode == "direct":
+            dcost = torch.zeros((n_total, n_total))
+            extra = (pipe.direct_evaluate(n_total, dcost), dcost.numpy().copy())
         elif mode != "nccl":
             extra = (pipe.transport, pipe.team_error, compute.connected_with, compute.destroyed)
         results[rank] = (full[:, 0, 0].tolist(), mean, cost.numpy().copy(), extra)
@@ -216,3 +226,18 @@ def test_world2_batched_sets_are_sharded_and_gathered():
     for rank in (0, 1):
         assert res[rank][3][0] == want  # every rank ends with all K means, in set order
         assert res[rank][3][1] == want_params  # and so for sets given as parameter vectors
+
+
+def test_world2_direct_metric_is_sharded_by_pairs_and_summed():
+    """ShardedPipeline.direct_evaluate: the pair enumeration cut over the ranks, one all-reduce of the sum and of the cost
+    image with its disjoint entries; every rank ends with the whole."""
+    n_total = 7
+    res = _run(n_total, mode="direct")
+    pairs = [(i, j) for i in range(n_total) for j in range(i + 1, n_total)]
+    want = sum(0.5 * (1000.0 * i + j) for i, j in pairs)
+    for rank in (0, 1):
+        total, dcost = res[rank][3]
+        assert abs(total - want) < 1e-9
+        for i, j in pairs:
+            assert dcost[j, i] == 1000.0 * i + j  # the stub writes a pair's intermediate value; written exactly once
+

@@ -191,6 +191,32 @@ def test_evaluate_all_pairs_equals_pairwise_and_oracle(ctx, scene, fbcc):
     assert abs(total - want) / want < 2e-4
 
 
+def test_pair_ranges_compose_to_the_whole_and_partition_balances_the_planes(ctx, scene):
+    """ecc_direct_evaluate_range / ecc_direct_partition (multi-GPU sharding of the direct metric): the ranges of any cut give
+    the whole's pair values bit for bit and its sum to fp64 rounding; with a fixed plane step the pairs differ in work
+    (kappa range) and the cut follows the planes, not the pair count."""
+    n = scene["n"]
+    pairs = n * (n - 1) // 2
+    setup(ctx, scene["Ps"], scene["imgs"], dkappa=1.5e-3, radius=40.0)
+    whole = np.zeros((n, n), np.float32)
+    total = ctx.direct_evaluate(whole)
+    planes = np.array([len(ctx.direct_pair_geometry(i, j)["kappas"]) for i in range(n) for j in range(i + 1, n)])
+    assert planes.max() > 2 * planes.min()  # unequal work
+    for parts in (1, 2, 3, 8, 40):
+        b = ctx.direct_partition(parts)
+        assert b[0] == 0 and b[-1] == pairs and np.all(np.diff(b) >= 0)
+        cost = np.zeros((n, n), np.float32)
+        sums = [ctx.direct_evaluate_range(int(b[k]), int(b[k + 1]), cost) for k in range(parts)]
+        assert np.array_equal(cost, whole)
+        assert abs(sum(sums) - total) <= 1e-13 * total
+        if parts in (2, 3):
+            work = np.array([np.ceil(planes[int(b[k]):int(b[k + 1])] / 32).sum() for k in range(parts)])
+            assert work.max() - work.min() <= np.ceil(planes.max() / 32)  # within one pair of equal
+    assert ctx.direct_evaluate_range(4, 4, None) == 0.0
+    with pytest.raises(api.EccError):
+        ctx.direct_evaluate_range(3, pairs + 1, None)
+
+
 def test_fbcc_pole_inside_the_image_is_not_finite(ctx, scene):
     """Views 166 degrees apart: the baseline passes through the object, the epipole lies inside the image and with it the pole
     of the rectifying perspectivity -- weights overflow on the lines through it.  The reference's kernel has no guard
@@ -248,6 +274,12 @@ def test_metric_direct_class_and_errors(ctx, scene):
     ctx.set_projection_matrices(scene["Ps"])
     with pytest.raises(api.EccError):
         ctx.direct_evaluate_pair(0, scene["n"])
+    # an absurd plane step (a billion planes per pair) is refused, not attempted
+    ctx.set_epipolar_plane_step(1e-10)
+    with pytest.raises(api.EccError):
+        ctx.direct_evaluate(None)
+    ctx.set_epipolar_plane_step(0.0)
+    assert ctx.direct_evaluate(None) == total
     # an empty set and a single view
     ctx.direct_set_images(scene["imgs"][:1])
     ctx.set_projection_matrices(scene["Ps"][:1])
