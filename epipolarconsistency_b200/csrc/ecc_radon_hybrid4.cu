@@ -68,6 +68,7 @@ struct Hybrid4Params {
     int n_u, n_v, n_alpha, n_t, post;
     int groups_a, groups_t;
     int mode;
+    int tex_map;   // development (ECC_HYBRID4_TEXMAP): bin tiling of a texture warp's sub-tile, see the texture warps' loop
     int lane_map;  // bin tiling of a window warp: 2 = 4 angles x 8 t (default; measured: window path alone 1.10 ms/projection),
                    // 0 = 2 angles x 16 t as the texture warps (1.20), 1 = 1 angle x 32 t (1.42), 3 = 8 angles x 4 t (1.26)
     unsigned* counters;
@@ -358,7 +359,26 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
                 if (ag_i < p.ag_lo || ag_i > p.ag_hi) continue;
             }
             const long long clock0 = p.item_clock ? clock64() : 0;
-            const Item4 B = item_bins4(item, sub % kSubTiles, lane, p);
+            Item4 B = item_bins4(item, sub % kSubTiles, lane, p);
+            if (p.tex_map) {  // development: other tilings of the item's 8 angles x 32 t bins into 8 sub-tiles of 32 lanes
+                const int wi = sub % kSubTiles, a0 = (B.ix / kItemAngles) * kItemAngles, t0 = (B.iy / kItemT) * kItemT;
+                if (p.tex_map == 1) {         // sub-tile 2 angles x 16 t, quad = 1 angle x 4 t
+                    B.ix = a0 + (wi & 3) * 2 + (lane >> 4);
+                    B.iy = t0 + (wi >> 2) * 16 + (lane & 15);
+                } else if (p.tex_map == 2) {  // sub-tile 4 angles x 8 t, quad = 4 angles x 1 t
+                    B.ix = a0 + (wi & 1) * 4 + (lane & 3);
+                    B.iy = t0 + (wi >> 1) * 8 + (lane >> 2);
+                } else if (p.tex_map == 3) {  // sub-tile 8 angles x 4 t, quad = 4 angles x 1 t
+                    B.ix = a0 + (lane & 7);
+                    B.iy = t0 + wi * 4 + (lane >> 3);
+                } else if (p.tex_map == 4) {  // sub-tile 1 angle x 32 t, quad = 1 angle x 4 t
+                    B.ix = a0 + wi;
+                    B.iy = t0 + lane;
+                } else if (p.tex_map == 5) {  // sub-tile 4 angles x 8 t, quad = 2 angles x 2 t
+                    B.ix = a0 + (wi & 1) * 4 + ((lane >> 4) & 1) * 2 + (lane & 1);
+                    B.iy = t0 + (wi >> 1) * 8 + ((lane >> 2) & 3) * 2 + ((lane >> 1) & 1);
+                }
+            }
             if (B.ix >= p.n_alpha || B.iy >= p.n_t) continue;
             const BinLine L = bin_line(B.ix, B.iy, p.n_alpha, p.n_t, n_u, n_v);
             Sum4 r = {0.f, 0.f, 0.f, 0.f};
@@ -879,6 +899,8 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     P.mode = mode;
     static const int lane_map = env_int("ECC_HYBRID4_LANEMAP", 2);
     P.lane_map = lane_map;
+    static const int tex_map = env_int("ECC_HYBRID4_TEXMAP", 0);
+    P.tex_map = tex_map;
     const int threads = (kWindowWarps + nt) * 32;
     const int slot = prof_begin(ctx, FAM_RADON);
     const int rcl = cfg == 1 ? launch_window_config<Win4Fine>(ctx, H, P, cfg, threads, ctas, n_u, n_v)

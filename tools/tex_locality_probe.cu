@@ -27,12 +27,20 @@ __global__ void walk(cudaTextureObject_t tex, int w, int h, float angle, int ite
     else if (MODE == 1) { line = (lane >> 2) * 2 + ((lane >> 1) & 1); phase = 0; per_step = 1; dang = (lane & 1) * 0.00409f; }
     else if (MODE == 2) { line = lane >> 2; phase = lane & 3; per_step = 4; }
     else if (MODE == 3) { line = lane >> 3; phase = lane & 7; per_step = 8; }
-    else { line = 0; phase = lane; per_step = 32; }
+    else if (MODE == 4) { line = 0; phase = lane; per_step = 32; }
+    else { line = (lane >> 2) * 2 + ((lane >> 1) & 1); phase = 0; per_step = 1; dang = (lane & 1) * 0.00409f; }  // F: B with the kernel's skew
     const float a = angle + dang;
     const float dx = cosf(a), dy = sinf(a);
     // warps tile the image: origin of the warp's first line, lines 2.04 px apart along the normal
     const float ox = 40.f + (warp % 37) * 3.1f - dy * 2.04f * line, oy = 40.f + ((warp / 37) % 29) * 3.3f + dx * 2.04f * line;
     float t = 0.66f * phase;
+    // F: the lines of the Radon kernel start where they ENTER the image (an axis-aligned edge), not at the foot of a common
+    // normal: at the same loop iteration neighbouring lines are 2.04 / cos apart ALONG THE EDGE, i.e. shifted along their own
+    // direction by 2.04 tan(angle to the edge normal) per line
+    if (MODE == 5) {
+        const float th = fabsf(angle) > 0.7853982f ? 1.5707963f - fabsf(angle) : fabsf(angle);
+        t += 2.04f * tanf(th) * line;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float span = 700.f;
     for (int k = 0; k < iters; k++) {
@@ -71,10 +79,11 @@ int main()
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int clk_khz = 0;
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
-    const char* names[5] = {"A 32 parallel lines", "B quads 2 angles x 2 t", "C quads = 4 samples of a line", "D 8 samples x 4 lines", "E 32 samples of a line"};
-    const float angles[4] = {0.05f, 0.5f, 0.78f, 1.4f};
-    for (int ai = 0; ai < 4; ai++)
-        for (int mode = 0; mode < 5; mode++) {
+    const char* names[6] = {"A 32 parallel lines", "B quads 2 angles x 2 t", "C quads = 4 samples of a line", "D 8 samples x 4 lines", "E 32 samples of a line",
+                            "F = B, lines skewed as they enter an edge"};
+    const float angles[6] = {0.05f, 0.3f, 0.5f, 0.65f, 0.78f, 1.4f};
+    for (int ai = 0; ai < 6; ai++)
+        for (int mode = 0; mode < 6; mode++) {
             float ms = 0;
             for (int rep = 0; rep < 2; rep++) {
                 cudaEventRecord(e0);
@@ -82,7 +91,8 @@ int main()
                 else if (mode == 1) walk<1><<<threads / 256, 256>>>(tex, w, h, angles[ai], iters, o_d);
                 else if (mode == 2) walk<2><<<threads / 256, 256>>>(tex, w, h, angles[ai], iters, o_d);
                 else if (mode == 3) walk<3><<<threads / 256, 256>>>(tex, w, h, angles[ai], iters, o_d);
-                else walk<4><<<threads / 256, 256>>>(tex, w, h, angles[ai], iters, o_d);
+                else if (mode == 4) walk<4><<<threads / 256, 256>>>(tex, w, h, angles[ai], iters, o_d);
+                else walk<5><<<threads / 256, 256>>>(tex, w, h, angles[ai], iters, o_d);
                 cudaEventRecord(e1);
                 CK(cudaEventSynchronize(e1));
                 cudaEventElapsedTime(&ms, e0, e1);
