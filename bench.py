@@ -538,6 +538,7 @@ def run_tracking(B):
         lat.append(time.perf_counter() - t0)
     wall = time.perf_counter() - t_all
     lat = np.array(lat) * 1e6
+    kernels_per_call, _ = ctx.track_info()
     # the pair kernel alone, from the plain path under the event profile (same kernel, same launch shape)
     ctx.profile_reset()
     ctx.profile_enable(True)
@@ -553,7 +554,9 @@ def run_tracking(B):
     if rank == 0:
         line = B.line(world * calls / (ms_step * 1e-3), ms_step, "weak")
         line["config"] = {"workload": W["name"], "reference_views": live, "pairs_per_call": live, "calls_per_step": calls,
-                          "path": "ecc_update_and_evaluate: one recorded CUDA graph per call {64-byte view upload, pair kernel, finalize + sum into pinned host memory}",
+                          "path": "ecc_update_and_evaluate: one recorded CUDA graph per call, " + (
+                              "{80-byte view upload, ONE kernel: pairs, sums by its last CTA, values + sum + flag into pinned host memory}" if kernels_per_call == 1
+                              else "{64-byte view upload, pair kernel, finalize + sum into pinned host memory}"),
                           "sharding": "replicas only (400 pairs are too few to shard): %d independent replica(s)" % world,
                           "l2": "intermediates larger than L2 (%.2f GB); a call touches the live view's and all reference views' intermediates" % (n * n_a * n_t * 4 / 1e9)}
         line["stages"] = {"pair_kernel_us_plain_path": 1e3 * prof["pairs"][0] / max(prof["pairs"][1], 1), "mean_ecc_last_call": mean,
@@ -561,7 +564,7 @@ def run_tracking(B):
         line["e2e"] = {"value": world * len(lat) / wall, "unit": "calls/s", "ms_per_step": wall * 1e3 / args.steps,
                        "h2d_bytes_per_step": calls * 64, "d2h_bytes_per_step": calls * (8 + 4 * live),
                        "note": "host clock around the same calls: a call takes its matrix from host memory and returns mean and values to the host"}
-        line["gpu_launches"] = int(2 * calls * args.steps)  # pair kernel + finalize/sum kernel per call (graph nodes)
+        line["gpu_launches"] = int(kernels_per_call * calls * args.steps)  # kernel nodes of the replayed graph (ecc_track_info)
         line["clocks"] = clocks
         line["roofline"] = B.pairs_roofline(prof, live_samples)
         if args.cpu_baseline and world == 1:

@@ -48,6 +48,7 @@ SIGNATURES = {
     "ecc_evaluate_range": (C.c_int, [c_ctx, C.c_longlong, C.c_longlong, c_vp, C.POINTER(C.c_double)]),
     "ecc_evaluate_indices": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.POINTER(C.c_double)]),
     "ecc_update_and_evaluate": (C.c_int, [c_ctx, C.c_int, c_vp, c_vp, C.c_int, c_vp, C.POINTER(C.c_double)]),
+    "ecc_track_info": (C.c_int, [c_ctx, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "ecc_evaluate_batch": (C.c_int, [c_ctx, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
     "ecc_pair_signals": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

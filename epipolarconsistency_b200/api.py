@@ -232,6 +232,12 @@ class Context:
         self._check(self.lib.ecc_update_and_evaluate(self.h, int(index), _ptr(P, _F64), _ptr(idx4, _I32), idx4.shape[0], _ptr(out, _F32), C.byref(m)))
         return m.value
 
+    def track_info(self):
+        """(kernel launches per replayed tracking call: 0 nothing recorded / 1 fused / 2 plain recording, replays so far)"""
+        k, r = C.c_int(), C.c_longlong()
+        self._check(self.lib.ecc_track_info(self.h, C.byref(k), C.byref(r)))
+        return k.value, r.value
+
     def evaluate_batch(self, Ps_sets, idx4=None, out=None, want_means=True):
         if isinstance(Ps_sets, np.ndarray):
             Ps_sets = np.ascontiguousarray(Ps_sets, np.float64)

@@ -9,6 +9,7 @@
 // Differences by design: all state lives in one context per GPU, every copy and launch is
 // asynchronous on the context's stream with one synchronisation at the end of a call that returns
 // a value, errors are returned instead of exit().
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -831,43 +832,81 @@ static void track_free(ecc_context* ctx)
     if (T.exec) cudaGraphExecDestroy(T.exec);
     if (T.idx_d) cudaFree(T.idx_d);
     if (T.pinned) cudaFreeHost(T.pinned);
+    if (T.live_d) cudaFree(T.live_d);
+    if (T.done_d) cudaFree(T.done_d);
     T = TrackGraph();
 }
 
-// Records {H2D of the derived view (64 bytes), pair kernel, finalize + sum writing into pinned host memory} on the context's
-// own stream: four nodes.
+// The pinned block of a tracking step: what the host hands over and what the launch hands back.
+struct TrackPinned {
+    float view[16];     // [12 floats (P+)^T | 4 floats C] of the live view
+    unsigned seq;       // sequence number of the call, uploaded with the view
+    unsigned pad[3];
+    double sum;         // sum of the listed pairs' values
+    volatile unsigned flag;  // the sequence number once values and sum are in place (fused recording)
+    unsigned pad2;
+    float vals[1];      // [n_pairs]
+};
+
+// Records a tracking step on the context's own stream.  Fused recording (CTA-per-pair launches, i.e. lists of fewer than 64
+// pairs per SM): TWO nodes -- one 80-byte copy {derived view, sequence number} and the pair kernel, whose last CTA adds up,
+// writes values and sum into the pinned block, stores the view into the arrays and raises the flag the host waits on.
+// Otherwise FOUR nodes: two copies of the derived view into the arrays, pair kernel, finalize + sum into the pinned block.
 static int track_capture(ecc_context* ctx, int index, int n_pairs, bool want_out, const PairLaunch& L_in, const int* idx_user_d)
 {
     TrackGraph& T = ctx->track;
     if (T.exec) { cudaGraphExecDestroy(T.exec); T.exec = nullptr; }
-    float* view_pin = (float*)T.pinned;            // [12 floats (P+)^T | 4 floats C]
-    double* sum_pin = (double*)(view_pin + 16);
-    float* vals_pin = (float*)(sum_pin + 1);
-    cudaStream_t saved = ctx->stream, cap = ctx->own_stream;
-    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return ECC_ERR_CUDA; }
-    ctx->stream = cap;
-    int rc = ECC_OK;
-    do {
-        if (cudaMemcpyAsync(ctx->PinvTs_d + (size_t)12 * index, view_pin, sizeof(float) * 12, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
-        if (cudaMemcpyAsync(ctx->Cs_d + (size_t)4 * index, view_pin + 12, sizeof(float) * 4, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
-        PairLaunch L = L_in;
-        L.idx4_d = idx_user_d ? idx_user_d : T.idx_d;  // a device-resident list is read in place at every replay
-        L.vals_d = ctx->vals_d;
-        L.n_pairs = n_pairs;
-        L.defer_finalize = 1;
-        PairLaunch R;
-        if ((rc = launch_pairs(ctx, L, &R))) break;
-        // finalize + sum in one launch that writes the results straight into the pinned block (no copy nodes)
-        if ((rc = launch_finalize_sum(ctx, R, sum_pin, want_out ? vals_pin : nullptr))) break;
-    } while (0);
-    ctx->stream = saved;
-    cudaGraph_t graph = nullptr;
-    const cudaError_t e = cudaStreamEndCapture(cap, &graph);
-    if (rc == ECC_OK && (e != cudaSuccess || !graph)) rc = ECC_ERR_CUDA;
-    if (rc == ECC_OK && cudaGraphInstantiate(&T.exec, graph, 0) != cudaSuccess) { T.exec = nullptr; rc = ECC_ERR_CUDA; }
-    if (graph) cudaGraphDestroy(graph);
-    cudaGetLastError();
-    return rc;
+    TrackPinned* pin = (TrackPinned*)T.pinned;
+    static const bool no_fuse = getenv("ECC_TRACK_NO_FUSE") != nullptr;  // development: the four-node recording
+    T.fused = false;
+    for (int attempt = no_fuse ? 1 : 0; attempt < 2; attempt++) {
+        const bool fuse = attempt == 0;
+        cudaStream_t saved = ctx->stream, cap = ctx->own_stream;
+        if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return ECC_ERR_CUDA; }
+        ctx->stream = cap;
+        int rc = ECC_OK;
+        bool fused_ok = false;
+        do {
+            PairLaunch L = L_in;
+            L.idx4_d = idx_user_d ? idx_user_d : T.idx_d;  // a device-resident list is read in place at every replay
+            L.vals_d = ctx->vals_d;
+            L.n_pairs = n_pairs;
+            L.defer_finalize = 1;
+            if (fuse) {
+                if (cudaMemcpyAsync(T.live_d, pin, 80, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
+                L.live_d = T.live_d;
+                L.live_index = index;
+                L.done_d = T.done_d;
+                L.fused_sum_out = &pin->sum;
+                L.fused_vals_out = want_out ? pin->vals : nullptr;
+                L.fused_flag = const_cast<unsigned*>(&pin->flag);
+            } else {
+                if (cudaMemcpyAsync(ctx->PinvTs_d + (size_t)12 * index, pin->view, sizeof(float) * 12, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
+                if (cudaMemcpyAsync(ctx->Cs_d + (size_t)4 * index, pin->view + 12, sizeof(float) * 4, cudaMemcpyHostToDevice, cap) != cudaSuccess) { rc = ECC_ERR_CUDA; break; }
+            }
+            PairLaunch R;
+            if ((rc = launch_pairs(ctx, L, &R))) break;
+            fused_ok = fuse && R.done_d != nullptr;
+            if (fuse && !fused_ok) break;  // not a CTA-per-pair launch: record again, the plain way
+            // plain: finalize + sum in one launch that writes the results straight into the pinned block (no copy nodes)
+            if (!fuse && (rc = launch_finalize_sum(ctx, R, &pin->sum, want_out ? pin->vals : nullptr))) break;
+        } while (0);
+        ctx->stream = saved;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(cap, &graph);
+        if (rc == ECC_OK && (e != cudaSuccess || !graph)) rc = ECC_ERR_CUDA;
+        if (rc == ECC_OK && fuse && !fused_ok) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            continue;
+        }
+        if (rc == ECC_OK && cudaGraphInstantiate(&T.exec, graph, 0) != cudaSuccess) { T.exec = nullptr; rc = ECC_ERR_CUDA; }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc == ECC_OK) T.fused = fused_ok;
+        return rc;
+    }
+    return ECC_ERR_CUDA;
 }
 
 int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const int* idx4, int n_pairs, float* out, double* mean)
@@ -932,12 +971,18 @@ int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const 
             }
             ECC_CUDA(ctx, cudaMemcpy(T.idx_d, idx4, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyHostToDevice));
         }
-        const size_t need = sizeof(float) * 16 + sizeof(double) + sizeof(float) * (size_t)n_pairs;
+        const size_t need = sizeof(TrackPinned) + sizeof(float) * (size_t)n_pairs;
         if (T.pinned_bytes < need) {
             if (T.pinned) cudaFreeHost(T.pinned);
             T.pinned = nullptr; T.pinned_bytes = 0;
             ECC_CUDA(ctx, cudaMallocHost(&T.pinned, need));
             T.pinned_bytes = need;
+            std::memset(T.pinned, 0, need);
+        }
+        if (!T.live_d) {
+            ECC_CUDA(ctx, cudaMalloc(&T.live_d, 80));
+            ECC_CUDA(ctx, cudaMalloc(&T.done_d, sizeof(unsigned)));
+            ECC_CUDA(ctx, cudaMemset(T.done_d, 0, sizeof(unsigned)));
         }
         if (track_capture(ctx, index, n_pairs, out != nullptr, L, idx_dev ? idx4 : nullptr) != ECC_OK) {
             T.failed = true;  // e.g. a driver without stream capture for one of the nodes: plain path from now on
@@ -949,14 +994,40 @@ int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const 
         T.pending_key.clear();
     }
     // replay: the matrix goes through the pinned block, everything else is in the recorded nodes
-    float* view_pin = (float*)T.pinned;
-    derive_view(P, view_pin, view_pin + 12);  // on the host, bit-identical to the device derivation
+    TrackPinned* pin = (TrackPinned*)T.pinned;
+    derive_view(P, pin->view, pin->view + 12);  // on the host, bit-identical to the device derivation
+    pin->seq = ++T.seq ? T.seq : ++T.seq;       // never zero
     ECC_CUDA(ctx, cudaGraphLaunch(T.exec, ctx->stream));
-    ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (T.fused) {
+        // the kernel's last CTA raises the flag once values and sum are in the pinned block: the host watches the flag instead
+        // of waiting for the stream to drain (the stream is looked at now and then, so that a failed launch cannot hang the call)
+        static const bool no_poll = getenv("ECC_TRACK_NO_POLL") != nullptr;  // development
+        unsigned spins = 0;
+        while (!no_poll && pin->flag != pin->seq) {
+            if ((++spins & 0x3fffu) == 0) {
+                const cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q == cudaSuccess) break;  // finished: the flag is there, or the launch did not do its work (checked below)
+                if (q != cudaErrorNotReady) return fail(ctx, ECC_ERR_CUDA, std::string("ecc_update_and_evaluate: ") + cudaGetErrorString(q));
+            }
+        }
+        if (no_poll || pin->flag != pin->seq) ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pin->flag != pin->seq) return fail(ctx, ECC_ERR_CUDA, "ecc_update_and_evaluate: the fused launch did not complete");
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+        ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     T.replays++;
-    const double* sum_pin = (const double*)(view_pin + 16);
-    if (mean) *mean = *sum_pin / (double)n_pairs;
-    if (out) std::memcpy(out, (const float*)(sum_pin + 1), sizeof(float) * (size_t)n_pairs);
+    if (mean) *mean = pin->sum / (double)n_pairs;
+    if (out) std::memcpy(out, pin->vals, sizeof(float) * (size_t)n_pairs);
+    return ECC_OK;
+}
+
+int ecc_track_info(ecc_context* ctx, int* kernels_per_call, long long* replays)
+{
+    if (!ctx) return ECC_ERR_INVALID;
+    Guard g(ctx);
+    if (kernels_per_call) *kernels_per_call = !ctx->track.exec ? 0 : (ctx->track.fused ? 1 : 2);
+    if (replays) *replays = ctx->track.replays;
     return ECC_OK;
 }
 

@@ -104,8 +104,12 @@ struct TrackGraph {
     std::vector<int> idx_h;      // the host pair list the device copy below was made from
     int* idx_d = nullptr;        // own copy of the pair list (the context's idx_d is scratch of other calls)
     size_t idx_cap = 0;
-    void* pinned = nullptr;      // [12 doubles P | double sum | floats vals]
+    void* pinned = nullptr;      // [16 floats view | sequence number, pad | double sum | flag, pad | floats vals]
     size_t pinned_bytes = 0;
+    float* live_d = nullptr;     // device copy of the first 80 bytes of the pinned block (one copy node per replay)
+    unsigned* done_d = nullptr;  // CTA counter of the fused launch (left at zero by every launch)
+    unsigned seq = 0;
+    bool fused = false;          // the recording is the two-node one (pair kernel with the fused tail)
     bool failed = false;         // capture did not work here: stay on the plain path
     long long replays = 0;
 };
@@ -289,6 +293,17 @@ struct PairLaunch {
     // outputs
     float* vals_d;   // n_sets*n_pairs
     float* image_d;  // all-pairs: n_views*n_views cost image or null (only with n_sets==1)
+    // tracking steps (ecc_update_and_evaluate, CTA-per-pair launches of one set): the whole call in ONE launch.  The live view
+    // is read from live_d ([12 floats (P+)^T | 4 floats C | sequence number], uploaded by the one copy node in front of the
+    // kernel) instead of entry live_index of the arrays; the CTA that finishes last (done_d counts them) adds the splits'
+    // partial sums and the pairs' values in launch_finalize_sum's order, writes values and sum to fused_vals_out / fused_sum_out
+    // (pinned host memory), stores the live view into the arrays, and publishes the sequence number at fused_flag.
+    const float* live_d = nullptr;
+    int live_index = -1;
+    unsigned* done_d = nullptr;
+    double* fused_sum_out = nullptr;
+    float* fused_vals_out = nullptr;
+    unsigned* fused_flag = nullptr;
 };
 // resolved (nullable): the launch record as launched (splits, partials_d filled in)
 int launch_pairs(ecc_context* ctx, const PairLaunch& L, PairLaunch* resolved = nullptr);

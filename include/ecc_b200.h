@@ -215,10 +215,15 @@ int ecc_evaluate_indices(ecc_context* ctx, const int* idx4, int n_pairs, float* 
 /* One step of a tracking / single-view loop (Gui/SingleImageMotion.h:84-90: one matrix changes, the pair list stays):
  * ecc_update_projection_matrix(index, P) followed by ecc_evaluate_indices(idx4, n_pairs, out, mean), with the same
  * results.  From the third call with the same index, list and settings on, the step is replayed as ONE recorded CUDA graph
- * {upload of the matrix, derivation of its view, pair kernels, sum, download} instead of seven API calls (BASELINE config
- * C5: the step is launch-latency bound).  idx4 [h|d]; out: host memory or NULL (device memory takes the plain path). */
+ * {upload of the derived view, pair kernel, sums, results into pinned host memory} instead of seven API calls (BASELINE
+ * config C5: the step is launch-latency bound; see ecc_track_info).  idx4 [h|d]; out: host memory or NULL (device memory takes the plain path). */
 int ecc_update_and_evaluate(ecc_context* ctx, int index, const double* P, const int* idx4, int n_pairs, float* out,
                             double* mean);
+/* What ecc_update_and_evaluate replays at the moment: 0 = nothing recorded (plain calls), 1 = the fused recording (lists
+ * of fewer than 64 pairs per SM: one 80-byte copy and ONE kernel, whose last CTA adds up, delivers values and sum into
+ * pinned host memory and raises the flag the host waits on), 2 = the plain recording (two copies, pair kernel, finalize
+ * + sum kernel).  The number is the count of kernel launches per call.  kernels_per_call [h]. */
+int ecc_track_info(ecc_context* ctx, int* kernels_per_call, long long* replays);
 
 /* Batched mode (new capability): n_sets complete projection-matrix sets
  * (n_sets * n * 12 doubles, n = number of matrices per set = current n of the context) scored

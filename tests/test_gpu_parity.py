@@ -4,6 +4,8 @@ oracle/_ref/libecc_ref_cuda.so travelled with the snapshot -- against the refere
 
 Tolerances (north_star): Radon bins within 1e-4 of the intermediate's peak; per-pair ECC within 1e-3
 relative of the reference CUDA path; summed metric within 1e-4 relative of the CPU float path."""
+import os
+import sys
 import numpy as np
 import pytest
 
@@ -811,8 +813,14 @@ def test_update_and_evaluate_graph_replay_equals_plain_calls(ctx, scene):
         P = perturbed()
         out = np.zeros(len(idx), np.float32)
         mean = ctx.update_and_evaluate(live, P, idx, out)
+        # the call leaves the context as update_projection_matrix would: an evaluation right after it sees the new view
+        after = np.zeros(len(idx), np.float32)
+        assert ctx.evaluate_indices(idx, after) == mean and np.array_equal(after, out), step
         want_mean, want = plain(live, P, idx)
         assert mean == want_mean and np.array_equal(out, want), step
+    kernels, replays = ctx.track_info()
+    # a short list: the fused recording (one kernel per call) unless the plain one is forced (test below)
+    assert kernels == int(os.environ.get("ECC_EXPECT_TRACK_KERNELS", "1")) and replays >= 4
     # another list (shorter), device-resident, no per-pair output
     import torch
     idx2 = torch.from_numpy(idx[:5].copy()).cuda()
@@ -844,6 +852,16 @@ def test_update_and_evaluate_graph_replay_equals_plain_calls(ctx, scene):
         want_mean, _ = plain(0, P, idx0)
         assert mean == want_mean, step
     ctx.set_projection_matrices(scene["Ps"])
+
+
+def test_update_and_evaluate_plain_recording():
+    """The four-node recording (what lists too long for the fused launch get) through the same test, in a process of its own
+    (the switch is read once per process)."""
+    import subprocess
+    env = dict(os.environ, ECC_TRACK_NO_FUSE="1", ECC_EXPECT_TRACK_KERNELS="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                        __file__ + "::test_update_and_evaluate_graph_replay_equals_plain_calls"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_ranges_are_bit_identical_to_the_whole_job_in_warp_per_pair_mode(ctx):
