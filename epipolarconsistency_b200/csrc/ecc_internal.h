@@ -45,7 +45,8 @@ struct Hybrid4Stage {
     std::vector<cudaArray_t> arrays;           // float4 arrays, one per quad
     std::vector<cudaTextureObject_t> tex_h;
     cudaTextureObject_t* tex_d = nullptr;
-    void* lin = nullptr;                       // [quads][n_v][n_u] float4
+    std::vector<cudaSurfaceObject_t> surf_h;   // the same arrays as surfaces: the staging kernel writes the texels in place
+    cudaSurfaceObject_t* surf_d = nullptr;
     void* pad_n = nullptr;                     // [quads][n_v+1][n_u+1] float4
     void* pad_t = nullptr;                     // [quads][n_u+1][n_v+1] float4
     unsigned* queue = nullptr;

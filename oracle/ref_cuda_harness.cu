@@ -299,17 +299,24 @@ double ref_cuda_metric_evaluate(void* h, const int* idx4, int n_pairs, float rad
     const bool all = (idx4 == nullptr);
     const int pairs = all ? n * (n - 1) / 2 : n_pairs;
     const size_t out_len = all ? (size_t)n * n : (size_t)pairs;
-    if (grow(&M->K01s_d, &M->k01_cap, (size_t)pairs * 16)) return -1;
-    if (grow(&M->out_d, &M->out_cap, out_len)) return -1;
-    if (grow(&M->corr_d, &M->corr_cap, (size_t)pairs)) return -1;
-    cudaMemset(M->out_d, 0, sizeof(float) * out_len);
-    cudaMemset(M->corr_d, 0, sizeof(float) * pairs);
+    // One record more than the list has, zeroed: the reference's index-list kernel lets thread idx_x == num_pairs through
+    // ("if (idx_x>num_pairs) return;", EpipolarConsistencyRadonIntermediate.cu:165), which reads K01s, the index quad and
+    // the texture handle of a pair BEHIND the list and stores to out / out_corr there.  With zeros it finds dkappa = kappa_max
+    // = 0 and leaves; with whatever the allocator left behind the buffers it faulted (CUDA error 700) once the library's
+    // own allocations changed.
+    if (grow(&M->K01s_d, &M->k01_cap, (size_t)(pairs + 1) * 16)) return -1;
+    if (grow(&M->out_d, &M->out_cap, out_len + 1)) return -1;
+    if (grow(&M->corr_d, &M->corr_cap, (size_t)pairs + 1)) return -1;
+    cudaMemset(M->K01s_d, 0, sizeof(float) * 16 * (pairs + 1));
+    cudaMemset(M->out_d, 0, sizeof(float) * (out_len + 1));
+    cudaMemset(M->corr_d, 0, sizeof(float) * (pairs + 1));
     if (!all) {
-        if (M->idx_cap < (size_t)pairs * 4) {
+        if (M->idx_cap < (size_t)(pairs + 1) * 4) {
             cudaFree(M->idx_d);
-            cudaMalloc(&M->idx_d, sizeof(int) * 4 * pairs);
-            M->idx_cap = (size_t)pairs * 4;
+            cudaMalloc(&M->idx_d, sizeof(int) * 4 * (pairs + 1));
+            M->idx_cap = (size_t)(pairs + 1) * 4;
         }
+        cudaMemset(M->idx_d, 0, sizeof(int) * 4 * (pairs + 1));
         cudaMemcpy(M->idx_d, idx4, sizeof(int) * 4 * pairs, cudaMemcpyHostToDevice);
     }
     cudaEvent_t e0, e1;
@@ -366,17 +373,20 @@ double ref_cuda_metric_evaluate_corr(void* h, const int* idx4, int n_pairs, floa
     const bool all = (idx4 == nullptr);
     const int pairs = all ? n * (n - 1) / 2 : n_pairs;
     const size_t out_len = all ? (size_t)n * n : (size_t)pairs;
-    if (grow(&M->K01s_d, &M->k01_cap, (size_t)pairs * 16)) return -1;
-    if (grow(&M->out_d, &M->out_cap, out_len)) return -1;
-    if (grow(&M->corr_d, &M->corr_cap, (size_t)pairs * 6)) return -1;
-    cudaMemset(M->out_d, 0, sizeof(float) * out_len);
-    cudaMemset(M->corr_d, 0, sizeof(float) * pairs * 6);
+    // one zeroed record more than the list has: see ref_cuda_metric_evaluate
+    if (grow(&M->K01s_d, &M->k01_cap, (size_t)(pairs + 1) * 16)) return -1;
+    if (grow(&M->out_d, &M->out_cap, out_len + 1)) return -1;
+    if (grow(&M->corr_d, &M->corr_cap, (size_t)(pairs + 1) * 6)) return -1;
+    cudaMemset(M->K01s_d, 0, sizeof(float) * 16 * (pairs + 1));
+    cudaMemset(M->out_d, 0, sizeof(float) * (out_len + 1));
+    cudaMemset(M->corr_d, 0, sizeof(float) * (pairs + 1) * 6);
     if (!all) {
-        if (M->idx_cap < (size_t)pairs * 4) {
+        if (M->idx_cap < (size_t)(pairs + 1) * 4) {
             cudaFree(M->idx_d);
-            cudaMalloc(&M->idx_d, sizeof(int) * 4 * pairs);
-            M->idx_cap = (size_t)pairs * 4;
+            cudaMalloc(&M->idx_d, sizeof(int) * 4 * (pairs + 1));
+            M->idx_cap = (size_t)(pairs + 1) * 4;
         }
+        cudaMemset(M->idx_d, 0, sizeof(int) * 4 * (pairs + 1));
         cudaMemcpy(M->idx_d, idx4, sizeof(int) * 4 * pairs, cudaMemcpyHostToDevice);
     }
     epipolarConsistency(M->n_u, M->n_v, M->n_dtrs, (char*)M->tex_d, M->n_alpha, M->n_t, M->step_alpha, M->step_t, n,
