@@ -400,6 +400,11 @@ def run_radon(B):
     dtrs_host = torch.empty((hi - lo, n_t, n_a), dtype=torch.float32, pin_memory=True)
 
     def step(src, to_host):
+        if to_host and world == 1:
+            # host images in, host intermediates out (what the ComputeRadonIntermediate tool does): one call; uploads and
+            # downloads run under the kernels of the neighbouring chunks
+            ctx.radon_compute(src, n_a, n_t, out=dtrs_host, interp=B.radon_interp)
+            return pipe._full
         full = pipe.radon_allgather(src, n, n_a, n_t, interp=B.radon_interp)
         if to_host:  # the step's result: this rank's intermediates, read back
             dtrs_host.copy_(full[lo:hi], non_blocking=True)

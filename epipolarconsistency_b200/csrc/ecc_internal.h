@@ -166,6 +166,8 @@ struct ecc_context {
     cudaStream_t own_stream = nullptr;  // created by ecc_create
     cudaStream_t copy_stream = nullptr; // uploads of host images under the Radon kernels (created on first use)
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaStream_t down_stream = nullptr; // downloads of finished intermediates to host memory under the next chunk's kernels
+    cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
     int sm_count = 148;
     std::string last_error;
 

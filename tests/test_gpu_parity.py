@@ -130,6 +130,27 @@ def test_radon_host_and_device_buffers_agree(ctx, scene):
     assert np.array_equal(host, dev.cpu().numpy())
 
 
+def test_radon_long_batches_every_mix_of_host_and_device_memory(ctx):
+    """Batches long enough for the chunked paths (growing chunks behind host images, two short chunks in front of the last
+    download to host memory, three staging streams): the same bits whichever side lives where."""
+    import torch
+    rng = np.random.default_rng(17)
+    img = rng.random((300, 40, 56), dtype=np.float32)
+    img_d = torch.from_numpy(img).cuda()
+    for interp in (api.INTERP_HYBRID_STATIC, api.INTERP_TEXTURE):
+        want = ctx.radon_compute(img_d, 48, 40, interp=interp).cpu().numpy()
+        assert np.array_equal(ctx.radon_compute(img, 48, 40, interp=interp), want)  # host -> host
+        out_h = np.full_like(want, np.nan)
+        ctx.radon_compute(img_d, 48, 40, interp=interp, out=out_h)  # device -> host
+        assert np.array_equal(out_h, want)
+        out_d = torch.empty((300, 40, 48), dtype=torch.float32, device="cuda")
+        ctx.radon_compute(img, 48, 40, interp=interp, out=out_d)  # host -> device
+        assert np.array_equal(out_d.cpu().numpy(), want)
+        again = np.full_like(want, np.nan)
+        ctx.radon_compute(img[::-1].copy(), 48, 40, interp=interp, out=again)  # a second call reuses the staging buffers
+        assert np.array_equal(again, want[::-1])
+
+
 def test_radon_batches_larger_than_pool(ctx):
     rng = np.random.default_rng(5)
     img = rng.random((70, 24, 40), dtype=np.float32)
