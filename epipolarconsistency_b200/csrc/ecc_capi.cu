@@ -311,6 +311,8 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
     const int chunk = n_images < 128 ? n_images : 128;
     static const int first_env = getenv("ECC_FIRST_CHUNK") ? atoi(getenv("ECC_FIRST_CHUNK")) : 4;
     const int first_want = first_env >= 4 ? first_env / 4 * 4 : 4;
+    static const int growth_env = getenv("ECC_CHUNK_GROWTH") ? atoi(getenv("ECC_CHUNK_GROWTH")) : 0;  // development knob
+    const int growth = growth_env >= 2 ? growth_env : 2;
     const int first_chunk = (!in_dev && n_images > first_want) ? first_want : chunk;
     int rc;
     if (!in_dev && (rc = ensure_bytes(ctx, (void**)&ctx->img_stage_d, &ctx->img_stage_bytes, sizeof(float) * img_elems * chunk * 2))) return rc;
@@ -353,7 +355,7 @@ int eccb200::radon_compute_impl(ecc_context* ctx, const float* images, int n_ima
             n = (body - first < want) ? body - first : want;
             if (body - first - n > 0 && body - first - n < 8 && body - first <= chunk && n >= 8) n = body - first;  // no tiny last launch
         }
-        want = (2 * want < chunk) ? 2 * want : chunk;
+        want = (growth * want < chunk) ? growth * want / 4 * 4 : chunk;
         const float* src = images + (size_t)first * img_elems;
         const int b = k & 1;
         if (!in_dev) {

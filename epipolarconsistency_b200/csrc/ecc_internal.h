@@ -63,6 +63,9 @@ struct Hybrid4Stage {
     // order of a quad's items for the static split: order[0 .. split_items) -> window path, the rest -> texture path
     int* order_d = nullptr;
     int order_len = 0;
+    // running sample counts along the two lists of a quad (window entries; texture sub-tiles): where a PART of a quad is cut
+    // (QuadPart), so that both paths get the same share of their samples -- not of their entries
+    std::vector<double> win_prefix, tex_prefix;
 };
 
 // Peer mirrors of an output buffer (multi-GPU team, ecc_team.cu): a kernel that stores out[k] also stores the same

@@ -706,6 +706,11 @@ int static_split_items(ecc_context* ctx, Hybrid4Stage& H, int n_u, int n_v, int 
     }
     ECC_CUDA(ctx, cudaMemcpyAsync(H.order_d, order.data(), sizeof(int) * per_quad, cudaMemcpyHostToDevice, ctx->stream));
     ECC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `order` is a local
+    H.win_prefix.assign(1, 0.0);
+    for (int k = 0; k < m; k++) H.win_prefix.push_back(H.win_prefix.back() + counts[order[k]]);
+    H.tex_prefix.assign(1, 0.0);
+    for (int k = m; k < per_quad; k++)
+        for (int sub = 0; sub < kSubTiles; sub++) H.tex_prefix.push_back(H.tex_prefix.back() + counts[order[k]] / kSubTiles);
     H.split_items = m;
     H.split_key[0] = n_u; H.split_key[1] = n_v; H.split_key[2] = n_alpha; H.split_key[3] = n_t;
     H.split_cfg = cfg;
@@ -882,10 +887,21 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
         // (one with hi = k / den, the other with lo = k / den) take complementary entries
         const long long split = P.split_items, subs = (long long)(P.groups_a * P.groups_t - P.split_items) * kSubTiles;
         if (nq == 1 && part.lo_num >= part.hi_num) return fail(ctx, ECC_ERR_INVALID, "radon_hybrid4_launch: empty part of a quad");
-        P.w_begin = (unsigned)(split * part.lo_num / part.den);
-        P.w_end = (unsigned)((long long)(nq - 1) * split + split * part.hi_num / part.den);
-        P.x_begin = (unsigned)(subs * part.lo_num / part.den);
-        P.x_end = (unsigned)((long long)(nq - 1) * subs + subs * part.hi_num / part.den);
+        // A part of a quad takes the same share of the SAMPLES of both lists (the items of a list differ in cost by the length
+        // of their lines: cutting by entries gave one rank the short lines of the window list and the long ones of the texture
+        // list -- its two pipes out of balance, half of what sharing the quad should have saved was lost).  The cut is a
+        // function of the fraction alone, so the two ranks that share a quad take complementary entries.
+        auto cut = [&](const std::vector<double>& prefix, int num) -> long long {
+            const long long len = (long long)prefix.size() - 1;
+            if (num <= 0) return 0;
+            if (num >= part.den) return len;
+            const double want = prefix.back() * (double)num / (double)part.den;
+            return (long long)(std::lower_bound(prefix.begin(), prefix.end(), want) - prefix.begin());
+        };
+        P.w_begin = (unsigned)cut(H.win_prefix, part.lo_num);
+        P.w_end = (unsigned)((long long)(nq - 1) * split + cut(H.win_prefix, part.hi_num));
+        P.x_begin = (unsigned)cut(H.tex_prefix, part.lo_num);
+        P.x_end = (unsigned)((long long)(nq - 1) * subs + cut(H.tex_prefix, part.hi_num));
     }
     static const int ag_lo = env_int("ECC_ITEM_AG_LO", 0), ag_hi = env_int("ECC_ITEM_AG_HI", INT_MAX);
     P.ag_lo = ag_lo;
