@@ -83,6 +83,13 @@ struct Hybrid4Params {
     // shards) -- window entries [w_begin, w_end) of n_quads * split_items, texture sub-tiles [x_begin, x_end) of
     // n_quads * (items per quad - split_items) * kSubTiles
     unsigned w_begin, w_end, x_begin, x_end;
+    // Window entries from w_last on -- the launch's last quad -- are taken in REVERSE order.  A quad's items are numbered t group
+    // by t group from one edge of the t axis, so the window list [0, split) ends with the t groups at the centre: the longest
+    // lines, half a millisecond per item, and a launch ended with a few CTAs on those while the rest idled (0.43 ms per launch
+    // beyond linear, profiles/radon_launch_size_r02.txt).  Backwards, the launch ends with the short lines at the edge.  The
+    // texture list (from the centre to the other edge) already runs that way.  Only the last quad: walking EVERY quad
+    // backwards made long launches 1.3 % slower (window and texture warps then work on the centre at the same time).
+    unsigned w_last;
     float* out;
     Mirrors mir;  // multi-GPU team: every bin is also stored into the other ranks' buffers (NVLink peer stores)
 };
@@ -402,7 +409,9 @@ radon_hybrid4_kernel(const __grid_constant__ CUtensorMap map_n, const __grid_con
     for (;;) {
         if (tid == 0) {
             if (p.split_items >= 0) {  // static split: items [0, split_items) of every quad, in order
-                const unsigned w = atomicAdd(&p.counters[0], 1u) + p.w_begin;
+                unsigned w = atomicAdd(&p.counters[0], 1u) + p.w_begin;
+                // the launch's LAST quad is walked backwards (same entries, other order): see Hybrid4Params::w_last
+                if (w >= p.w_last && w < p.w_end) w = p.w_last + (p.w_end - 1u - w);
                 s_item = (p.split_items > 0 && w < p.w_end)
                              ? (int)(w / p.split_items) * (p.groups_a * p.groups_t) + __ldg(&p.order[w % p.split_items]) : -1;
             } else {
@@ -879,6 +888,7 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
     P.split_items = -1;
     P.order = nullptr;
     P.w_begin = P.w_end = P.x_begin = P.x_end = 0;
+    P.w_last = 0;
     if (static_split) {
         const int rcs = static_split_items(ctx, H, n_u, n_v, n_alpha, n_t, P.groups_a, P.groups_t, cfg, &P.split_items);
         if (rcs) return rcs;
@@ -900,6 +910,9 @@ int radon_hybrid4_launch(ecc_context* ctx, const float* images_d, int n, int n_u
         };
         P.w_begin = (unsigned)cut(H.win_prefix, part.lo_num);
         P.w_end = (unsigned)((long long)(nq - 1) * split + cut(H.win_prefix, part.hi_num));
+        static const int keep_order = env_int("ECC_HYBRID4_KEEP_ORDER", 0);  // development: the last quad in list order, too
+        const long long last_begin = (long long)(nq - 1) * split;
+        P.w_last = keep_order ? P.w_end : (unsigned)std::max<long long>(P.w_begin, last_begin);
         P.x_begin = (unsigned)cut(H.tex_prefix, part.lo_num);
         P.x_end = (unsigned)((long long)(nq - 1) * subs + cut(H.tex_prefix, part.hi_num));
     }
