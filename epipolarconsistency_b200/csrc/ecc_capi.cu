@@ -241,7 +241,7 @@ void ecc_destroy(ecc_context* ctx)
         cudaStreamDestroy(ctx->down_stream);
         for (int b = 0; b < 2; b++) { cudaEventDestroy(ctx->ev_out_ready[b]); cudaEventDestroy(ctx->ev_out_free[b]); }
     }
-    void* bufs[] = {ctx->batch.Ps_d, ctx->batch.Cs_d, ctx->batch.A_d, ctx->batch.radii_d, ctx->batch.params_d, ctx->batch.base_d, ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, (void*)ctx->dtr_ptrs_d, ctx->vals_d, ctx->partials_d,
+    void* bufs[] = {ctx->batch.Ps_d, ctx->batch.Cs_d, ctx->batch.A_d, ctx->batch.radii_d, ctx->batch.params_d, ctx->batch.base_d, ctx->Ps_d, ctx->Cs_d, ctx->PinvTs_d, ctx->dtrs_owned, ctx->dtr_tex_d, (void*)ctx->dtr_ptrs_d, ctx->vals_d, ctx->partials_d, ctx->pair_records_d,
                     ctx->sums_d, ctx->idx_d, ctx->counts_d, ctx->img_stage_d, ctx->out_stage_d, ctx->cost_d};
     for (void* b : bufs)
         if (b) cudaFree(b);

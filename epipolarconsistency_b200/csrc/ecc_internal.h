@@ -211,6 +211,8 @@ struct ecc_context {
     float* vals_d = nullptr;  // one float per evaluated (set,pair)
     float* partials_d = nullptr;  // partial sums of split CTA-per-pair launches
     size_t partials_cap = 0;
+    float* pair_records_d = nullptr;  // warp-per-pair launches: the pairs' maps, one 64-byte record each (launch_pairs)
+    size_t pair_records_bytes = 0;
     size_t vals_cap = 0;
     double* sums_d = nullptr;  // one double per set
     size_t sums_cap = 0;
@@ -295,6 +297,9 @@ struct PairLaunch {
     int defer_finalize;  // split launches: leave the partial sums for launch_finalize_sum
     int splits;          // set by launch_pairs: CTAs per pair (CTA-per-pair launches)
     float* partials_d;   // [items][splits][3] when splits > 1
+    // set by launch_pairs, warp-per-pair launches: [items][16] floats -- every pair's maps computed ONCE by one thread of
+    // pair_records_kernel instead of by all 32 lanes of the pair's warp (ecc_pairs.cu); null = the warp computes them
+    const float* records_d = nullptr;
     float* corr_sums_d;  // correlation variant, nullable: the reference launcher's six sums per pair (forces splits = 1)
     // outputs
     float* vals_d;   // n_sets*n_pairs

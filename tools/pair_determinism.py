@@ -9,7 +9,7 @@ import bench
 W = bench.WORKLOADS["c3"]
 n, n_u, n_v, n_a, n_t = W["n"], W["n_u"], W["n_v"], W["n_alpha"], W["n_t"]
 ctx = api.Context(0)
-Ps = api.make_circular_trajectory(n, W["sid"], W["sdd"], n_u, n_v, W["arc"], W["px"])
+Ps = api.make_circular_trajectory(n, bench.GEO["sid"], bench.GEO["sdd"], n_u, n_v, W["arc"], W["px"])
 imgs = torch.empty((n, n_v, n_u), dtype=torch.float32, device="cuda")
 ctx.synth_projections(Ps, n_u, n_v, bench.ELLIPSOIDS, imgs)
 dtrs = ctx.radon_compute(imgs, n_a, n_t, interp=api.INTERP_TEXTURE)
