@@ -77,6 +77,9 @@ SM_COUNT = 148
 # projections, by Radon engine (hybrid-static: profiles/ncu_radon_hybrid4_r02.txt, a 112-projection launch: 1728.5 + 287.3 MB;
 # hybrid: profiles/ncu_radon_hybrid4_bench_r01b.txt); known for the C3 image size only
 RADON_TRAFFIC_128 = {"hybrid-static": 2.3038e9, "hybrid": 1.4524e9}
+# the same for one pair-kernel launch of a workload at its full size on one GPU (profiles/ncu_pairs_c3_r02.txt: 320.3 MB read;
+# profiles/ncu_pairs_c4_r02_setsinner.txt); None = not captured
+PAIRS_TRAFFIC = {"c3": 3.26e8}
 
 
 def hbm_peak():
@@ -295,20 +298,28 @@ class Bench:
                         "is expected, `traffic` is what DRAM really moves per launch; tex_rate_frac = samples/s over the texture "
                         "unit's measured rate alone (1.09e12/s at 1965 MHz, profiles/tex_probe_r01.txt)" % samples}
 
-    def pairs_roofline(self, prof, kappa_samples_this_rank_per_launch):
-        """Pair kernel: 64 B of taps per kappa sample (4 lookups x 4 taps x 4 B) against the HBM copy peak
-        as the contract asks, and against the measured random-sector rates of this GPU's L2."""
+    def pairs_roofline(self, prof, kappa_samples_this_rank_per_launch, clocks=None):
+        """Pair kernel: 64 B of taps per kappa sample (4 lookups x 4 taps x 4 B).  The taps are served by the
+        texture unit out of L1TEX/L2 (ncu: two thirds of the sectors hit L1TEX), so the bound that applies is the texture data pipe,
+        64 B/clk/SM -- the same on-chip roofline as the Radon kernel's texture path; the HBM copy peak and the measured
+        random-sector rates of this GPU are side fields (DRAM moves a few hundred MB per launch)."""
         ms, launches = prof["pairs"]
         gbs = 64.0 * kappa_samples_this_rank_per_launch / (ms / max(launches, 1) * 1e-3) / 1e9 if ms > 0 else 0.0
         hbm, hbm_src = hbm_peak()
-        return {"bound": "hbm", "kernel": "pairs_kernel (gathers served by L1TEX/L2; issue bound)", "achieved": gbs, "peak": hbm, "unit": "GB/s",
-                "frac": gbs / hbm, "peak_source": hbm_src, "kappa_samples_per_launch": float(kappa_samples_this_rank_per_launch),
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        onchip = 64.0 * SM_COUNT * mhz * 1e6 / 1e9
+        return {"bound": "onchip(tex)", "kernel": "pairs_kernel", "achieved": gbs, "peak": onchip, "unit": "GB/s", "frac": gbs / onchip,
+                "peak_source": "64 B/clk/SM (texture data pipe) x %d SMs x the SM clock sampled during this run (%.0f MHz)" % (SM_COUNT, mhz),
+                "hbm_peak": hbm, "hbm_peak_source": hbm_src, "hbm_frac": gbs / hbm,
+                "kappa_samples_per_launch": float(kappa_samples_this_rank_per_launch),
                 # random-gather rates of this pool's B200 (tools/gather_probe.cu, profiles/gather_probe_r01.txt): 32-byte
                 # sectors from an L2-resident set / from a 1.17 GB set, bilinear texture fetches from 1.1 GB
                 "gather_peaks_gbs": {"l2_random_sectors": 4380.0, "hbm_random_sectors": 1021.0, "texture_random_1GB": 427.0},
-                "frac_of_l2_gather": gbs / 4380.0, "traffic": None,
-                "note": "64 B of taps per kappa sample; above the random-gather rates because neighbouring kappa samples share "
-                        "taps in L1TEX (ncu: issue slots 66 %, texture pipe 31 %, profiles/ncu_pairs_r01b.txt)"}
+                "frac_of_l2_gather": gbs / 4380.0, "traffic": PAIRS_TRAFFIC.get(self.args.workload) if self.world == 1 else None,
+                "note": "64 B of taps per kappa sample, served by the texture unit from L1TEX/L2: hbm_frac is not a bound (neighbouring "
+                        "kappa samples share their sectors on chip), `traffic` is what DRAM moves per launch (ncu, profiles/INDEX.md); "
+                        "the kernel waits on its dependent coordinate arithmetic and on first-touch misses, not on the data pipe "
+                        "(DESIGN.md section 3.2)"}
 
 
 def run_pipeline(B):
@@ -380,7 +391,7 @@ def run_pipeline(B):
         line["gpu_launches"] = int(sum(v[1] for v in prof.values()))
         line["clocks"] = clocks
         line["roofline"] = B.radon_roofline(prof, clocks, work)
-        line["roofline_pairs"] = B.pairs_roofline(prof, float(counts[int(my_lo):int(my_hi)].sum()))
+        line["roofline_pairs"] = B.pairs_roofline(prof, float(counts[int(my_lo):int(my_hi)].sum()), clocks)
         if args.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(W, B.Ps, full_dtrs=pipe._full)
             line["ref_cuda"] = ref_cuda_leg(B, images, pipe._full, radon_ms / args.steps / max(work, 1), pairs_ms / args.steps, ms_step)
@@ -489,7 +500,7 @@ def run_batch(B):
         line["gpu_launches"] = int(sum(v[1] for v in prof.values()))
         line["clocks"] = clocks
         # kappa samples of a set vary little with the perturbation: counted on the unperturbed set
-        line["roofline"] = B.pairs_roofline(prof, float(counts.sum()) * (hi - lo))
+        line["roofline"] = B.pairs_roofline(prof, float(counts.sum()) * (hi - lo), clocks)
         if args.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(W, B.Ps, full_dtrs=dtrs, pairs_only=True, per="set")
         print(json.dumps(line))
@@ -571,7 +582,7 @@ def run_tracking(B):
                        "note": "host clock around the same calls: a call takes its matrix from host memory and returns mean and values to the host"}
         line["gpu_launches"] = int(kernels_per_call * calls * args.steps)  # kernel nodes of the replayed graph (ecc_track_info)
         line["clocks"] = clocks
-        line["roofline"] = B.pairs_roofline(prof, live_samples)
+        line["roofline"] = B.pairs_roofline(prof, live_samples, clocks)
         if args.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(W, B.Ps, full_dtrs=dtrs, pairs_only=True, per="call", idx=idx)
         print(json.dumps(line))
