@@ -446,6 +446,34 @@ def test_batched_sets_equal_individual_evaluations(ctx, scene):
     assert np.array_equal(out2[:, 1], out[:, ol_pair_index(2, 8, n)])
 
 
+@pytest.mark.parametrize("interp", ["texture", "exact"])
+def test_batched_warp_per_pair_launches_equal_single_sets_bit_for_bit(ctx, scene, interp):
+    """Batched launches long enough for the warp-per-pair kernel take their work in another order (the K instances of a pair in
+    consecutive CTAs) and read the pairs' maps from records computed once per pair (pair_records_kernel); single sets compute
+    them in the warp.  Same function, same inputs, and a pair's value does not depend on the CTA that computes it: the values
+    must be the single-set launches' bits."""
+    if interp == "texture":
+        setup_metric(ctx, scene, scene["dtr_tex"], api.INTERP_TEXTURE)
+    else:
+        setup_metric(ctx, scene, scene["dtr_exact"], api.INTERP_EXACT)
+    rng = np.random.default_rng(7)
+    K, n = 3, scene["n"]
+    sets = np.stack([scene["Ps"] * (1 + 2e-4 * rng.standard_normal(scene["Ps"].shape)) for _ in range(K)])
+    sets[0] = scene["Ps"]
+    base = np.array([(i, j, i, j) for i in range(n) for j in range(n) if i != j], np.int32)
+    big = np.ascontiguousarray(np.tile(base, (120, 1)))  # 10800 pairs per set > 148 * 64: warp per pair
+    out = np.zeros((K, len(big)), np.float32)
+    means = ctx.evaluate_batch(sets, big, out)
+    for k in range(K):
+        ctx.set_projection_matrices(sets[k])
+        single = np.zeros(len(big), np.float32)
+        mean = ctx.evaluate_indices(big, single)
+        assert np.array_equal(single, out[k]), f"set {k}: {int((single != out[k]).sum())} of {len(big)} values differ"
+        assert abs(mean - means[k]) <= 1e-12 * abs(mean)
+        assert np.array_equal(out[k, :len(base)], out[k, len(base):2 * len(base)])  # every copy of the list, the same bits
+    ctx.set_projection_matrices(scene["Ps"])
+
+
 def ol_pair_index(i, j, n):
     return i * (2 * n - i - 1) // 2 + (j - i - 1)
 
