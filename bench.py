@@ -78,8 +78,8 @@ SM_COUNT = 148
 # hybrid: profiles/ncu_radon_hybrid4_bench_r01b.txt); known for the C3 image size only
 RADON_TRAFFIC_128 = {"hybrid-static": 2.3038e9, "hybrid": 1.4524e9}
 # the same for one pair-kernel launch of a workload at its full size on one GPU (profiles/ncu_pairs_c3_r02.txt: 320.3 MB read;
-# profiles/ncu_pairs_c4_r02_setsinner.txt); None = not captured
-PAIRS_TRAFFIC = {"c3": 3.26e8}
+# profiles/ncu_pairs_c4_r02_setsinner.txt: 399.4 MB read + 13.1 MB written); None = not captured
+PAIRS_TRAFFIC = {"c3": 3.26e8, "c4": 4.125e8}
 
 
 def hbm_peak():
